@@ -1,0 +1,227 @@
+"""Generate the golden vectors under tests/golden/ by running the UNMODIFIED
+reference (AgamChopra/TorchRegister, /root/reference) on CPU in the build
+container.  The reference cannot travel to the GPU box, its outputs can.
+
+    python tests/golden/make_golden.py            # rewrites tests/golden/*.npz
+
+What is recorded per case: the exact inputs (small), the reference's per-epoch
+losses (captured through the debug=True plt.plot hook, oracle/ref_shim.py), its
+final/best theta, warped volumes, and the same run in float64 (the reference is
+dtype agnostic when inputs and the Regressor parameter are double) as the
+noise-floor adjudicator.
+
+Deviations from a stock reference run, all test-harness side:
+  * initial rigid parameters are injected by subclassing utils.Regressor (the
+    reference draws torch.rand on `device`, utils.py:317-321); one case per
+    dimensionality keeps the reference's own seeded draw instead;
+  * 3-D cases that go through the default-criteria branch replace NMILoss by a
+    zero stub: the reference evaluates NMI even at weight 0 and its 3-D KDE needs
+    tens of GB (utils.py:24-30,242-247) which this container does not have.  The
+    2-D cases run the real NMI and `case_2d_stub_equivalence` asserts that the
+    stub leaves a weight-0 run bit-identical.
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import random
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, ROOT)
+
+from oracle import ref_shim                                   # noqa: E402
+from torchregister_b200.synth import make_pair, smooth_flow   # noqa: E402
+
+api, rw, ru = ref_shim.load()
+torch.set_num_threads(max(1, os.cpu_count() or 1))
+torch.backends.cudnn.allow_tf32 = False
+_REAL_NMI = rw.NMILoss
+_REAL_REG = ru.Regressor
+
+
+class _ZeroNMI(nn.Module):
+    def forward(self, y, yp):
+        return yp.sum() * 0
+
+
+def _patch_regressor(p0, dtype):
+    if p0 is None:
+        rw.Regressor = _REAL_REG
+        return
+
+    class Injected(_REAL_REG):
+        def __init__(self, moving, device):
+            super().__init__(moving, device)
+            self.reg = nn.Parameter(torch.as_tensor(p0).to(dtype).clone(), requires_grad=True)
+
+    rw.Regressor = Injected
+
+
+def _quiet(fn, *a, **k):
+    with contextlib.redirect_stdout(io.StringIO()):
+        return fn(*a, **k)
+
+
+def run_affine_like(mode, mov, tgt, lr, epochs, criterions, weights, p0=None, dtype=torch.float32,
+                    stub_nmi=False, seed=None):
+    mov, tgt = mov.to(dtype), tgt.to(dtype)
+    rw.NMILoss = _ZeroNMI if stub_nmi else _REAL_NMI
+    _patch_regressor(p0 if mode == "rigid" else None, dtype)
+    if seed is not None:
+        torch.manual_seed(seed)
+    random.seed(0)
+    kw = dict(lr=lr, epochs=epochs, per=0.1, device="cpu", debug=True, grad_edges=False)
+    if criterions is not None:
+        kw["criterions"] = criterions
+    if weights is not None:
+        kw["weights"] = weights
+    fn = rw.rigid_register if mode == "rigid" else rw.affine_register
+    if mode == "affine" and dtype == torch.float64:
+        # the inert MLP is created in float32 by the reference; run it under a
+        # float64 default dtype so the whole graph is double.
+        old = torch.get_default_dtype()
+        torch.set_default_dtype(torch.float64)
+        try:
+            (fw, bw), (ft, bt) = _quiet(fn, mov, tgt, **kw)
+        finally:
+            torch.set_default_dtype(old)
+    else:
+        (fw, bw), (ft, bt) = _quiet(fn, mov, tgt, **kw)
+    losses = ref_shim.last_losses()
+    assert losses is not None and len(losses) == epochs, (len(losses or []), epochs)
+    rw.NMILoss = _REAL_NMI
+    rw.Regressor = _REAL_REG
+    return dict(losses=np.asarray(losses, np.float64), final_theta=ft.detach().numpy().copy(),
+                best_theta=bt.detach().numpy().copy(), final_warped=fw.detach().numpy().copy(),
+                best_warped=bw.detach().numpy().copy())
+
+
+def save(name, **arrays):
+    path = os.path.join(HERE, name + ".npz")
+    np.savez_compressed(path, **arrays)
+    print("wrote", os.path.relpath(path, ROOT), "%.1f KB" % (os.path.getsize(path) / 1024))
+
+
+def case_affine_like(name, shape, mode, kind, lr, epochs, criterions, weights, eff_weights, p0=None,
+                     stub_nmi=False, seed=None):
+    mov, tgt = make_pair(shape, kind)
+    p0_rec = p0
+    if mode == "rigid" and p0 is None:
+        torch.manual_seed(seed)
+        p0_rec = torch.rand(6 if len(shape) == 3 else 3)      # the draw the reference makes (utils.py:317-321)
+    r32 = run_affine_like(mode, mov, tgt, lr, epochs, criterions, weights, p0, torch.float32, stub_nmi, seed)
+    p64 = p0_rec if mode == "rigid" else None
+    crit64 = None if criterions is None else [nn.MSELoss()]
+    r64 = run_affine_like(mode, mov, tgt, lr, epochs, crit64, weights, p64, torch.float64, stub_nmi, None)
+    out = dict(moving=mov.numpy(), target=tgt.numpy(), lr=np.float64(lr), epochs=np.int64(epochs),
+               weights=np.asarray(eff_weights, np.float64), mode=np.array(mode),
+               p0=np.zeros(0, np.float32) if p0_rec is None else np.asarray(p0_rec, np.float32))
+    for k, v in r32.items():
+        out[k] = v
+    for k in ("losses", "final_theta", "best_theta"):
+        out[k + "_f64"] = r64[k]
+    out["final_warped_f64"] = r64["final_warped"]
+    save(name, **out)
+    return r32
+
+
+def case_2d_stub_equivalence():
+    mov, tgt = make_pair((48, 40), "rigid")
+    p0 = torch.tensor([0.03, 0.02, -0.01])
+    a = run_affine_like("rigid", mov, tgt, 1e-4, 5, None, [0.0, 1.0, 0.0], p0, stub_nmi=False)
+    b = run_affine_like("rigid", mov, tgt, 1e-4, 5, None, [0.0, 1.0, 0.0], p0, stub_nmi=True)
+    assert np.array_equal(a["losses"], b["losses"]) and np.array_equal(a["final_theta"], b["final_theta"]), \
+        "zero-weight NMI stub changed the result"
+    print("stub equivalence (2-D, weight 0): bit-identical")
+
+
+def case_flow_node(name, shape, w_mse, w_ncc):
+    nd = len(shape)
+    mov, tgt = make_pair(shape, "flow")
+    g = torch.Generator().manual_seed(7)
+    flow = smooth_flow(shape, 2.5) + 0.3 * torch.randn(1, nd, *shape, generator=g)
+    # push a few samples outside the volume to exercise zero padding
+    flow[0, :, ..., :2] -= 4.0
+    out = dict(moving=mov.numpy(), target=tgt.numpy(), flow=flow.numpy(),
+               weights=np.asarray([w_mse, w_ncc, 0.0]))
+    for dtype, sfx in ((torch.float32, ""), (torch.float64, "_f64")):
+        st = ru.SpatialTransformer(shape, "bilinear").to(dtype)
+        st.grid = st.grid.to(dtype)
+        fl = flow.to(dtype).clone().requires_grad_(True)
+        y = st(mov.to(dtype), fl)
+        err = w_mse * nn.MSELoss()(tgt.to(dtype), y) + w_ncc * ru.NCCLoss()(tgt.to(dtype), y)
+        err.backward()
+        out["loss" + sfx] = np.float64(err.item())
+        out["dflow" + sfx] = fl.grad.numpy().copy()
+        out["warped" + sfx] = y.detach().numpy().copy()
+        # plain VJP with a fixed cotangent (user-criterion route)
+        fl2 = flow.to(dtype).clone().requires_grad_(True)
+        y2 = st(mov.to(dtype), fl2)
+        cot = torch.cos(torch.arange(y2.numel(), dtype=dtype) * 0.37).view_as(y2)
+        y2.backward(cot)
+        out["cot" + sfx] = cot.numpy().copy()
+        out["vjp" + sfx] = fl2.grad.numpy().copy()
+    save(name, **out)
+
+
+def case_register_api(name, shape, mode, weights, lr, epochs, seed):
+    """Register(...).optim + __call__ on a 2-channel input, the reference's own RNG draw."""
+    mov, tgt = make_pair(shape, "rigid" if mode == "rigid" else "affine")
+    rw.NMILoss = _ZeroNMI if len(shape) == 3 else _REAL_NMI
+    rw.Regressor = _REAL_REG
+    torch.manual_seed(seed)
+    p0 = torch.rand(6 if len(shape) == 3 else 3)
+    torch.manual_seed(seed)
+    random.seed(0)
+    reg = api.Register(mode=mode, device="cpu", weight=weights, debug=True)
+    _quiet(reg.optim, mov, tgt, lr=lr, max_epochs=epochs)
+    two = torch.cat([mov, 0.5 * tgt + 0.1], dim=1)
+    out = reg(two).detach()
+    rw.NMILoss = _REAL_NMI
+    save(name, moving=mov.numpy(), target=tgt.numpy(), p0=p0.numpy(), lr=np.float64(lr),
+         epochs=np.int64(epochs), weights=np.asarray(weights, np.float64), mode=np.array(mode),
+         losses=np.asarray(ref_shim.last_losses(), np.float64), theta=reg.theta.detach().numpy().copy(),
+         call_in=two.numpy(), call_out=out.numpy())
+
+
+def main():
+    case_2d_stub_equivalence()
+    p3 = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02])
+    p2 = torch.tensor([0.03, 0.02, -0.01])
+    S3, S2 = (24, 20, 16), (48, 40)
+    # rigid, the reference's "criterion given -> MSE only" branch (warpings.py:125-127)
+    case_affine_like("rigid3d_mse", S3, "rigid", "rigid", 5e-2, 12, [nn.MSELoss()], [1.0], [1, 0, 0], p3)
+    case_affine_like("rigid2d_mse", S2, "rigid", "rigid", 5e-2, 12, [nn.MSELoss()], [1.0], [1, 0, 0], p2)
+    # NCC only through weight=[0,1,0] (the only way to get pure NCC through the API)
+    case_affine_like("rigid3d_ncc", S3, "rigid", "rigid", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0], p3, stub_nmi=True)
+    case_affine_like("rigid2d_ncc", S2, "rigid", "rigid", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0], p2)
+    # mixed MSE+NCC
+    case_affine_like("rigid3d_mix", S3, "rigid", "rigid", 1e-4, 12, None, [0.5, 0.5, 0.0], [.5, .5, 0], p3, stub_nmi=True)
+    # the reference's own seeded torch.rand draw (large angles, zero-padding exercised)
+    case_affine_like("rigid3d_rand", S3, "rigid", "rigid", 1e-4, 8, None, [0.0, 1.0, 0.0], [0, 1, 0], None, stub_nmi=True, seed=0)
+    case_affine_like("rigid2d_rand", S2, "rigid", "rigid", 1e-4, 8, None, [0.5, 0.5, 0.0], [.5, .5, 0], None, seed=0)
+    # affine (identity start: samples sit on the voxel lattice at epoch 0)
+    case_affine_like("affine3d_ncc", S3, "affine", "affine", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0], stub_nmi=True)
+    case_affine_like("affine3d_mix", S3, "affine", "affine", 1e-4, 12, None, [0.5, 0.5, 0.0], [.5, .5, 0], stub_nmi=True)
+    case_affine_like("affine2d_mse", S2, "affine", "affine", 5e-2, 12, [nn.MSELoss()], [1.0], [1, 0, 0])
+    case_affine_like("affine2d_ncc", S2, "affine", "affine", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0])
+    # default weights incl. the NMI term (2-D only; pins the "next" row f-1)
+    case_affine_like("rigid2d_default", S2, "rigid", "rigid", 1e-5, 4, None, None, [.33, .33, .33], p2)
+    # flow node
+    case_flow_node("flownode3d", (12, 14, 16), 0.5, 0.5)
+    case_flow_node("flownode2d", (40, 36), 0.5, 0.5)
+    case_flow_node("flownode3d_mse", (12, 14, 16), 1.0, 0.0)
+    # public API
+    case_register_api("api_rigid3d", S3, "rigid", [0.0, 1.0, 0.0], 1e-4, 6, seed=3)
+    case_register_api("api_affine2d", S2, "affine", [0.5, 0.5, 0.0], 1e-4, 6, seed=3)
+
+
+if __name__ == "__main__":
+    main()
