@@ -1,0 +1,172 @@
+/* trb.h — C ABI of libtrb_b200.so: B200 (sm_100a) kernels for the iterative
+ * registration hot path of AgamChopra/TorchRegister.
+ *
+ * The reference has no FFI of its own (pure Python over torch ops); the entry
+ * points below are what a binding for this path replaces, cited as file:line
+ * relative to /root/reference/src/TorchRegister/.  INTEGRATION.md shows the
+ * ctypes stub a reference maintainer would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer marked "dev" is a CUDA
+ *     device pointer owned by the caller (torch allocations in our host code);
+ *     the library borrows them for the duration of the enqueued work and never
+ *     frees or retains them;
+ *   - `stream` is a cudaStream_t passed as void*; every call is asynchronous on
+ *     that stream and performs no host synchronisation;
+ *   - return value 0 = ok, otherwise a negative trb error or a positive
+ *     cudaError_t; trb_last_error() gives a message (thread local);
+ *   - volumes are fp32, contiguous, [D][H][W] (3-D) or [H][W] (2-D, pass D=1);
+ *     a batch of independent pairs is addressed with `pair_stride` (elements);
+ *   - theta is row-major ndim x (ndim+1), row r <-> sampling coordinate r
+ *     (0 = x/W axis, 1 = y/H, 2 = z/D) exactly as F.affine_grid consumes it.
+ */
+#ifndef TRB_H
+#define TRB_H
+
+#include <stddef.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define TRB_ABI_VERSION 1
+
+/* error codes (negative; positive values are cudaError_t) */
+#define TRB_OK 0
+#define TRB_ERR_ARG (-1)
+#define TRB_ERR_WORKSPACE (-2)
+#define TRB_ERR_UNSUPPORTED (-3)
+
+/* modes / optimisers */
+#define TRB_MODE_RIGID 0   /* params = Regressor.reg (6 | 3 floats), utils.py:313-330 */
+#define TRB_MODE_AFFINE 1  /* params = theta itself (12 | 6 floats), warpings.py:42-55 */
+#define TRB_OPT_SGD 0      /* torch.optim.SGD(lr), warpings.py:58,131,192 */
+#define TRB_OPT_ADAM 1     /* extension (north_star item 3); no reference counterpart */
+
+/* Per-pair optimiser state: TRB_STATE_FLOATS fp32 values, device resident.
+ *   [ 0..11] params        (rigid: 6|3 used, affine: 12|6 used)
+ *   [12..23] theta         theta the NEXT epoch samples with (after the last epoch:
+ *                          the reference's final_theta, warpings.py:105-109,171)
+ *   [24..35] best_theta    pre-step theta of the lowest-loss epoch (warpings.py:85-93,151-159)
+ *   [36]     best_loss     [37] last_loss
+ *   [40..51] adam m        [52..63] adam v
+ */
+#define TRB_STATE_FLOATS 64
+#define TRB_STATE_PARAMS 0
+#define TRB_STATE_THETA 12
+#define TRB_STATE_BEST_THETA 24
+#define TRB_STATE_BEST_LOSS 36
+#define TRB_STATE_LAST_LOSS 37
+#define TRB_STATE_ADAM_M 40
+#define TRB_STATE_ADAM_V 52
+
+/* Moments produced by one pass over the voxels of a pair (fp64):
+ *   [0..4]   sum t, sum w, sum t^2, sum w^2, sum t*w
+ *   [5..16]  sum J        J[r][c] = d warped / d theta[r][c]
+ *   [17..28] sum t*J      [29..40] sum w*J
+ */
+#define TRB_MOMENTS 41
+
+int trb_abi_version(void);
+const char *trb_last_error(void);
+/* number of SMs of the current device (grid sizing); <0 on error */
+int trb_sm_count(void);
+
+/* ---- rigid / affine registration ---------------------------------------- */
+
+/* Bytes of scratch (dev) needed by trb_affine_* for `n_pairs` pairs. */
+size_t trb_affine_workspace_bytes(int n_pairs);
+
+/* Fill state[.][12..23] (theta) from state[.][0..11] (params) and reset
+ * best/adam slots.  Replaces Regressor()/Theta.forward at loop entry
+ * (utils.py:287-330) and the identity bias of warpings.py:47-48,54-55. */
+int trb_affine_init_state(int ndim, int mode, float *state_dev, int n_pairs, void *stream);
+
+/* Enqueue `n_epochs` fused registration epochs for `n_pairs` independent pairs.
+ * One epoch = one kernel launch that, per pair: builds the sampling coordinates
+ * from theta on the fly, tri/bi-linearly samples `moving`, streams `target`,
+ * accumulates the loss moments and d(loss)/d(theta), and — in the last block to
+ * finish — forms loss = w_mse*MSE + w_ncc*100*(1-NCC), chains to the rigid
+ * parameters, applies the optimiser step, tracks the best theta and logs the loss.
+ * Replaces the loop bodies warpings.py:67-93 (affine) and :138-159 (rigid):
+ * F.affine_grid + F.grid_sample (:24-25), MSELoss / NCCLoss (utils.py:197-205),
+ * backward (:80,146) and SGD.step (:81,147).
+ *
+ *   xb,yb,zb   dev tables of the base coordinates per axis, linspace(-1,1,S)*(S-1)/S
+ *              (lengths W,H,D; zb ignored for ndim==2)
+ *   loss_log   dev [n_pairs][log_stride]; epoch e writes column epoch0+e
+ *   epoch0     index of the first epoch enqueued (0 starts best tracking)
+ */
+int trb_affine_optim(int ndim, int mode,
+                     const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs,
+                     int D, int H, int W,
+                     const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                     float *state_dev, float *loss_log_dev, int log_stride,
+                     int epoch0, int n_epochs,
+                     float w_mse, float w_ncc, float lr,
+                     int optimiser, float beta1, float beta2, float adam_eps,
+                     void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Sharded variant for one large volume split into z-slabs (2-D: y-slabs) across
+ * GPUs: accumulate the TRB_MOMENTS fp64 moments of output slices [s_begin,s_end)
+ * into moments_dev[n_pairs][TRB_MOMENTS] (overwritten), no update.  After the
+ * caller has all-reduced the moments, trb_affine_apply performs the update that
+ * trb_affine_optim fuses.  `n_total` = voxels of the WHOLE volume. */
+int trb_affine_moments(int ndim,
+                       const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs,
+                       int D, int H, int W, int s_begin, int s_end,
+                       const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                       const float *state_dev, double *moments_dev,
+                       void *workspace_dev, size_t workspace_bytes, void *stream);
+
+int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs,
+                     int D, int H, int W,
+                     float *state_dev, float *loss_log_dev, int log_stride, int epoch,
+                     float w_mse, float w_ncc, float lr,
+                     int optimiser, float beta1, float beta2, float adam_eps, void *stream);
+
+/* Forward warp only: out[c] = grid_sample(moving[c], affine_grid(theta)) for
+ * n_channels volumes sharing one theta (dev, 12|6 floats).
+ * Replaces get_affine_warp (warpings.py:18-26) as used by Register.__call__
+ * (torchregister.py:126-128). */
+int trb_warp_affine(int ndim, const float *moving_dev, float *out_dev, int n_channels,
+                    int D, int H, int W, const float *theta_dev,
+                    const float *xb_dev, const float *yb_dev, const float *zb_dev, void *stream);
+
+/* Vector-Jacobian product of the affine warp with respect to theta:
+ * dtheta[12|6] (fp64, dev) = sum_v gout_v * d warped_v / d theta.
+ * (autograd of warpings.py:24-25 for callers that differentiate get_affine_warp.) */
+int trb_warp_affine_vjp(int ndim, const float *moving_dev, const float *gout_dev,
+                        int D, int H, int W, const float *theta_dev,
+                        const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                        double *dtheta_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* ---- flow field ----------------------------------------------------------- */
+/* flow layout [ndim][D][H][W] fp32 in voxel units, channel i displaces spatial
+ * axis i (0 = D (3-D) or H (2-D)), the SpatialTransformer convention utils.py:350-365. */
+
+size_t trb_flow_workspace_bytes(void);
+
+/* warped[c] = SpatialTransformer(src[c], flow); replaces utils.py:350-365 as used by
+ * flow_register.deform (warpings.py:238-242) and Register.__call__ (torchregister.py:124-125). */
+int trb_warp_flow(int ndim, const float *src_dev, const float *flow_dev, float *out_dev, int n_channels,
+                  int D, int H, int W, void *stream);
+
+/* dflow = J^T gout for the warp above (autograd of utils.py:365 w.r.t. flow);
+ * used when the caller supplies its own criterion (torchregister.py:71-73). */
+int trb_warp_flow_vjp(int ndim, const float *src_dev, const float *flow_dev, const float *gout_dev,
+                      float *dflow_dev, int D, int H, int W, void *stream);
+
+/* Fused warp + similarity + gradient: loss = w_mse*MSE + w_ncc*100*(1-NCC) of
+ * (target, warp(moving, flow)) and dflow = d loss / d flow; optionally also the
+ * warped volume.  Replaces utils.py:350-365 + warpings.py:213-215 (forward of the
+ * similarity and the backward down to the flow).  loss_dev: 1 float. */
+int trb_flow_loss_grad(int ndim, const float *moving_dev, const float *target_dev, const float *flow_dev,
+                       int D, int H, int W, float w_mse, float w_ncc,
+                       float *loss_dev, float *dflow_dev, float *warped_dev_or_null,
+                       void *workspace_dev, size_t workspace_bytes, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* TRB_H */

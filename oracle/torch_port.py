@@ -182,14 +182,14 @@ def affine_like_loop(moving, target, mode, p0, lr, epochs, weights=(1.0, 0.0, 0.
         err.backward()
         if record_grads:
             grads.append(p.grad.detach().clone())
-        with torch.no_grad():
-            p -= lr * p.grad
         lv = err.item()
         losses.append(lv)
-        if best_loss is None or lv < best_loss:
+        if best_loss is None or lv < best_loss:      # pre-step theta (in affine mode theta views p)
             best_loss, best_theta = lv, theta.detach().clone()
             if keep_warped:
                 best_warped = warped.detach().clone()
+        with torch.no_grad():
+            p -= lr * p.grad
     with torch.no_grad():
         final_theta = (rigid_theta(p) if mode == "rigid" else p.view(1, nd, nd + 1)).clone()
         final_warped = affine_warp(final_theta, moving) if keep_warped else None

@@ -1,0 +1,663 @@
+// affine.cu — fused rigid/affine registration epoch for B200 (sm_100a).
+//
+// One launch per epoch.  Per pair of volumes it replaces, from the reference
+// (paths relative to /root/reference/src/TorchRegister/):
+//   F.affine_grid + F.grid_sample (align_corners=False, zeros)   warpings.py:24-25
+//   nn.MSELoss / NCCLoss.forward                                  warpings.py:37,124; utils.py:197-205
+//   error.backward() down to theta and to Regressor.reg           warpings.py:80,146; utils.py:287-310
+//   torch.optim.SGD.step, best-theta tracking, loss log           warpings.py:81-93,147-159
+// No sampling grid is materialised: coordinates are rebuilt from theta and three
+// per-axis base-coordinate tables; the warped volume is never written.
+//
+// Data layout: moving/target fp32 [D][H][W] per pair (x = W fastest).  A warp owns
+// one output row (fixed z,y), lanes run along x, so target loads are fully coalesced
+// and the 8 gathered corners of neighbouring lanes fall in the same 128-B lines for
+// near-identity transforms.  Algorithmic traffic: 8 B per voxel-warp (moving 4 +
+// target 4), everything else is O(1) per pair.
+#include "common.cuh"
+#include <math.h>
+
+namespace trb {
+
+struct AffineParams {
+    const float *moving, *target;
+    long long pair_stride;
+    int D, H, W;
+    int s_begin, s_end;          // slab of output slices (z for 3-D, y for 2-D)
+    const float *xb, *yb, *zb;   // base coordinates per axis
+    float *state;                // [n_pairs][TRB_STATE_FLOATS]
+    double *partials;            // [n_pairs][gridDim.x][TRB_MOMENTS]
+    unsigned *tickets;           // [n_pairs]
+    double *moments_out;         // unfused: [n_pairs][TRB_MOMENTS]
+    float *loss_log;
+    int log_stride, epoch;
+    float w_mse, w_ncc, lr;
+    int mode, optimiser;
+    float beta1, beta2, adam_eps;
+};
+
+// ---- Theta.forward (utils.py:287-310), fp32 like the reference ------------------
+template <int NDIM>
+__device__ void rigid_theta(const float *p, float *th)
+{
+    if (NDIM == 3) {
+        float sps, cps, sth, cth, sph, cph;
+        sincosf(p[0], &sps, &cps);
+        sincosf(p[1], &sth, &cth);
+        sincosf(p[2], &sph, &cph);
+        th[0] = cps * cth;  th[1] = sph * sps * cth - cph * sth;  th[2] = cph * sps * cth + sph * sth;
+        th[3] = 0.25f * tanhf(p[3]);
+        th[4] = cps * sth;  th[5] = sph * sps * sth + cph * cth;  th[6] = cph * sps * sth - sph * cth;
+        th[7] = 0.25f * tanhf(p[4]);
+        th[8] = -sps;       th[9] = sph * cps;                     th[10] = cph * cps;
+        th[11] = 0.25f * tanhf(p[5]);
+    } else {
+        float s, c;
+        sincosf(p[0], &s, &c);
+        th[0] = c; th[1] = -s; th[2] = p[1];
+        th[3] = s; th[4] = c;  th[5] = p[2];
+    }
+}
+
+// Jacobian-transpose product d theta -> d params of the map above.
+template <int NDIM>
+__device__ void rigid_chain(const float *p, const double *g, double *dp)
+{
+    if (NDIM == 3) {
+        double sps, cps, sth, cth, sph, cph;
+        sincos((double)p[0], &sps, &cps);
+        sincos((double)p[1], &sth, &cth);
+        sincos((double)p[2], &sph, &cph);
+        dp[0] = g[0] * (-sps * cth) + g[1] * (sph * cps * cth) + g[2] * (cph * cps * cth)
+              + g[4] * (-sps * sth) + g[5] * (sph * cps * sth) + g[6] * (cph * cps * sth)
+              - g[8] * cps - g[9] * (sph * sps) - g[10] * (cph * sps);
+        dp[1] = -g[0] * (cps * sth) - g[1] * (sph * sps * sth + cph * cth) + g[2] * (sph * cth - cph * sps * sth)
+              + g[4] * (cps * cth) + g[5] * (sph * sps * cth - cph * sth) + g[6] * (cph * sps * cth + sph * sth);
+        dp[2] = g[1] * (cph * sps * cth + sph * sth) + g[2] * (cph * sth - sph * sps * cth)
+              + g[5] * (cph * sps * sth - sph * cth) - g[6] * (sph * sps * sth + cph * cth)
+              + g[9] * (cph * cps) - g[10] * (sph * cps);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            double t = tanh((double)p[3 + k]);
+            dp[3 + k] = g[3 + 4 * k] * 0.25 * (1.0 - t * t);
+        }
+    } else {
+        double s, c;
+        sincos((double)p[0], &s, &c);
+        dp[0] = -g[0] * s - g[1] * c + g[3] * c - g[4] * s;
+        dp[1] = g[2];
+        dp[2] = g[5];
+    }
+}
+
+// ---- epilogue: moments -> loss, d theta, chain, optimiser step, bookkeeping ---------
+// Runs in ONE thread per pair (O(100) flops).  M holds the TRB_MOMENTS sums with the
+// UN-scaled interpolant derivative; the grid_sample un-normalisation factor S_r/2 is
+// applied here.
+template <int NDIM>
+__device__ void affine_epilogue(const double *M, const AffineParams &p, int pair)
+{
+    constexpr int NC = NDIM + 1, NT = NDIM * NC;
+    float *st = p.state + (size_t)pair * TRB_STATE_FLOATS;
+    const double n = (double)(NDIM == 3 ? p.D : 1) * (double)p.H * (double)p.W;
+    const LossCoef lc = loss_coefficients(n, M[0], M[1], M[2], M[3], M[4], (double)p.w_mse, (double)p.w_ncc);
+    const double scale[3] = {0.5 * p.W, 0.5 * p.H, 0.5 * p.D};
+    double dth[12];
+#pragma unroll
+    for (int r = 0; r < NDIM; ++r)
+#pragma unroll
+        for (int c = 0; c < NC; ++c) {
+            const int i = r * NC + c;
+            dth[i] = (lc.cw * M[29 + i] + lc.ct * M[17 + i] + lc.c0 * M[5 + i]) * scale[r];
+        }
+    const float loss = (float)lc.loss;
+    // best tracking on the pre-step theta (warpings.py:85-93,151-159: strictly lower)
+    if (p.epoch == 0 || loss < st[TRB_STATE_BEST_LOSS]) {
+        st[TRB_STATE_BEST_LOSS] = loss;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) st[TRB_STATE_BEST_THETA + i] = st[TRB_STATE_THETA + i];
+    }
+    st[TRB_STATE_LAST_LOSS] = loss;
+    if (p.loss_log) p.loss_log[(size_t)pair * p.log_stride + p.epoch] = loss;
+
+    double dp[12];
+    int np;
+    if (p.mode == TRB_MODE_RIGID) {
+        rigid_chain<NDIM>(st + TRB_STATE_PARAMS, dth, dp);
+        np = NDIM == 3 ? 6 : 3;
+    } else {
+#pragma unroll
+        for (int i = 0; i < NT; ++i) dp[i] = dth[i];
+        np = NT;
+    }
+    for (int i = 0; i < np; ++i) {
+        const float g = (float)dp[i];
+        float v = st[TRB_STATE_PARAMS + i];
+        if (p.optimiser == TRB_OPT_SGD) {
+            v = v - p.lr * g;                      // torch.optim.SGD, no momentum / decay
+        } else {                                   // torch.optim.Adam semantics (extension)
+            const float t = (float)(p.epoch + 1);
+            float m = st[TRB_STATE_ADAM_M + i], s = st[TRB_STATE_ADAM_V + i];
+            m = p.beta1 * m + (1.f - p.beta1) * g;
+            s = p.beta2 * s + (1.f - p.beta2) * g * g;
+            st[TRB_STATE_ADAM_M + i] = m;
+            st[TRB_STATE_ADAM_V + i] = s;
+            const float bc1 = 1.f - powf(p.beta1, t), bc2 = 1.f - powf(p.beta2, t);
+            v = v - (p.lr / bc1) * (m / (sqrtf(s) / sqrtf(bc2) + p.adam_eps));
+        }
+        st[TRB_STATE_PARAMS + i] = v;
+    }
+    if (p.mode == TRB_MODE_RIGID) {
+        float th[12];
+        rigid_theta<NDIM>(st + TRB_STATE_PARAMS, th);
+#pragma unroll
+        for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = th[i];
+    } else {
+#pragma unroll
+        for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = st[TRB_STATE_PARAMS + i];
+    }
+}
+
+// ---- the fused pass ------------------------------------------------------------------
+template <int NDIM, bool FUSED>
+__global__ void __launch_bounds__(kThreads, 2) affine_moments_kernel(const AffineParams p)
+{
+    constexpr int NC = NDIM + 1, NT = NDIM * NC;
+    const int pair = blockIdx.y;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float *__restrict__ mov = p.moving + (size_t)pair * p.pair_stride;
+    const float *__restrict__ tgt = p.target + (size_t)pair * p.pair_stride;
+    const int W = p.W, H = p.H, D = (NDIM == 3 ? p.D : 1);
+    const size_t HW = (size_t)H * W;
+
+    float th[NT];
+    {
+        const float *st = p.state + (size_t)pair * TRB_STATE_FLOATS + TRB_STATE_THETA;
+#pragma unroll
+        for (int i = 0; i < NT; ++i) th[i] = __ldcg(st + i);
+    }
+    const float hw = 0.5f * W, hh = 0.5f * H, hd = 0.5f * D;
+    // i_r(x) = a_r * xb[x] + b_r(row): affine_grid, then ((g+1)*S-1)/2 folded in
+    const float ax = th[0] * hw, ay = th[NC] * hh, az = NDIM == 3 ? th[2 * NC] * hd : 0.f;
+
+    // accumulators (k: 0 -> weight 1, 1 -> t, 2 -> w ; r: sampling coordinate)
+    float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f, s4 = 0.f;
+    float Q[3][NDIM], T1[3][NDIM], Ty[3][NDIM], Tz[3][NDIM];
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int r = 0; r < NDIM; ++r) Q[k][r] = T1[k][r] = Ty[k][r] = Tz[k][r] = 0.f;
+
+    const int rows = (p.s_end - p.s_begin) * (NDIM == 3 ? H : 1);
+    for (int row0 = blockIdx.x * kWarps; row0 < rows; row0 += gridDim.x * kWarps) {
+        const int row = row0 + warp;
+        if (row >= rows) break;
+        int z = 0, y;
+        if (NDIM == 3) { z = p.s_begin + row / H; y = row - (row / H) * H; }
+        else y = p.s_begin + row;
+        const float yv = __ldg(p.yb + y);
+        const float zv = NDIM == 3 ? __ldg(p.zb + z) : 0.f;
+        float bx, by, bz = 0.f;
+        if (NDIM == 3) {
+            bx = fmaf(th[1] * yv + th[2] * zv + th[3] + 1.f, hw, -0.5f);
+            by = fmaf(th[5] * yv + th[6] * zv + th[7] + 1.f, hh, -0.5f);
+            bz = fmaf(th[9] * yv + th[10] * zv + th[11] + 1.f, hd, -0.5f);
+        } else {
+            bx = fmaf(th[1] * yv + th[2] + 1.f, hw, -0.5f);
+            by = fmaf(th[4] * yv + th[5] + 1.f, hh, -0.5f);
+        }
+        const float *__restrict__ trow = tgt + ((size_t)z * H + y) * W;
+        float P[3][NDIM];
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int r = 0; r < NDIM; ++r) P[k][r] = 0.f;
+
+        for (int xs = 0; xs < W; xs += 32) {
+            const int xi = xs + lane;
+            const bool act = xi < W;
+            const int xc = act ? xi : W - 1;
+            const float xv = __ldg(p.xb + xc);
+            const float t = act ? ld_stream_f(trow + xc) : 0.f;
+            const float ix = fmaf(ax, xv, bx), iy = fmaf(ay, xv, by);
+            const float fx = floorf(ix), fy = floorf(iy);
+            const float tx = ix - fx, ty = iy - fy;
+            const int x0 = (int)fx, y0 = (int)fy;
+            float val, G[NDIM];
+            if (NDIM == 3) {
+                const float iz = fmaf(az, xv, bz);
+                const float fz = floorf(iz);
+                const float tz = iz - fz;
+                const int z0 = (int)fz;
+                const bool inb = (x0 >= 0) & (x0 < W - 1) & (y0 >= 0) & (y0 < H - 1) & (z0 >= 0) & (z0 < D - 1);
+                float c000, c001, c010, c011, c100, c101, c110, c111;
+                if (__all_sync(kFull, inb)) {
+                    const float *q = mov + ((size_t)z0 * H + y0) * W + x0;
+                    c000 = __ldg(q);          c001 = __ldg(q + 1);
+                    c010 = __ldg(q + W);      c011 = __ldg(q + W + 1);
+                    c100 = __ldg(q + HW);     c101 = __ldg(q + HW + 1);
+                    c110 = __ldg(q + HW + W); c111 = __ldg(q + HW + W + 1);
+                } else {
+                    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+                    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+                    const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+                    const long long o = ((long long)z0 * H + y0) * W + x0;
+                    c000 = (vz0 & vy0 & vx0) ? __ldg(mov + o) : 0.f;
+                    c001 = (vz0 & vy0 & vx1) ? __ldg(mov + o + 1) : 0.f;
+                    c010 = (vz0 & vy1 & vx0) ? __ldg(mov + o + W) : 0.f;
+                    c011 = (vz0 & vy1 & vx1) ? __ldg(mov + o + W + 1) : 0.f;
+                    c100 = (vz1 & vy0 & vx0) ? __ldg(mov + o + (long long)HW) : 0.f;
+                    c101 = (vz1 & vy0 & vx1) ? __ldg(mov + o + (long long)HW + 1) : 0.f;
+                    c110 = (vz1 & vy1 & vx0) ? __ldg(mov + o + (long long)HW + W) : 0.f;
+                    c111 = (vz1 & vy1 & vx1) ? __ldg(mov + o + (long long)HW + W + 1) : 0.f;
+                }
+                const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+                const float v00 = fmaf(tx, d00, c000), v01 = fmaf(tx, d01, c010);
+                const float v10 = fmaf(tx, d10, c100), v11 = fmaf(tx, d11, c110);
+                const float e0 = v01 - v00, e1 = v11 - v10;
+                const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
+                G[2] = w1 - w0;
+                val = fmaf(tz, G[2], w0);
+                G[1] = fmaf(tz, e1 - e0, e0);
+                const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
+                G[0] = fmaf(tz, dx1 - dx0, dx0);
+            } else {
+                const bool inb = (x0 >= 0) & (x0 < W - 1) & (y0 >= 0) & (y0 < H - 1);
+                float c00, c01, c10, c11;
+                if (__all_sync(kFull, inb)) {
+                    const float *q = mov + (size_t)y0 * W + x0;
+                    c00 = __ldg(q); c01 = __ldg(q + 1); c10 = __ldg(q + W); c11 = __ldg(q + W + 1);
+                } else {
+                    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+                    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+                    const long long o = (long long)y0 * W + x0;
+                    c00 = (vy0 & vx0) ? __ldg(mov + o) : 0.f;
+                    c01 = (vy0 & vx1) ? __ldg(mov + o + 1) : 0.f;
+                    c10 = (vy1 & vx0) ? __ldg(mov + o + W) : 0.f;
+                    c11 = (vy1 & vx1) ? __ldg(mov + o + W + 1) : 0.f;
+                }
+                const float d0 = c01 - c00, d1 = c11 - c10;
+                const float v0 = fmaf(tx, d0, c00), v1 = fmaf(tx, d1, c10);
+                G[1] = v1 - v0;
+                val = fmaf(ty, G[1], v0);
+                G[0] = fmaf(ty, d1 - d0, d0);
+            }
+            if (act) {
+                s0 += t; s1 += val;
+                s2 = fmaf(t, t, s2); s3 = fmaf(val, val, s3); s4 = fmaf(t, val, s4);
+#pragma unroll
+                for (int r = 0; r < NDIM; ++r) {
+                    const float g = G[r], tg = t * g, wg = val * g;
+                    P[0][r] += g;  P[1][r] += tg;  P[2][r] += wg;
+                    Q[0][r] = fmaf(g, xv, Q[0][r]);
+                    Q[1][r] = fmaf(tg, xv, Q[1][r]);
+                    Q[2][r] = fmaf(wg, xv, Q[2][r]);
+                }
+            }
+        }
+        // y and z are constant along the row: fold the row partials once
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+#pragma unroll
+            for (int r = 0; r < NDIM; ++r) {
+                T1[k][r] += P[k][r];
+                Ty[k][r] = fmaf(yv, P[k][r], Ty[k][r]);
+                if (NDIM == 3) Tz[k][r] = fmaf(zv, P[k][r], Tz[k][r]);
+            }
+    }
+
+    // ---- block reduction of the TRB_MOMENTS per-thread sums -------------------------------
+    __shared__ float red[kWarps][TRB_MOMENTS + 1];
+    __shared__ double fin[4][TRB_MOMENTS + 1];
+    __shared__ bool is_last;
+    float acc[TRB_MOMENTS];
+    acc[0] = s0; acc[1] = s1; acc[2] = s2; acc[3] = s3; acc[4] = s4;
+#pragma unroll
+    for (int i = 5; i < TRB_MOMENTS; ++i) acc[i] = 0.f;
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int r = 0; r < NDIM; ++r) {
+            const int b = 5 + k * 12 + r * NC;
+            acc[b + 0] = Q[k][r];
+            acc[b + 1] = Ty[k][r];
+            if (NDIM == 3) acc[b + 2] = Tz[k][r];
+            acc[b + NDIM] = T1[k][r];
+        }
+#pragma unroll
+    for (int i = 0; i < TRB_MOMENTS; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    double *mypart = p.partials + ((size_t)pair * gridDim.x + blockIdx.x) * TRB_MOMENTS;
+    if (threadIdx.x < TRB_MOMENTS) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kWarps; ++w) s += (double)red[w][threadIdx.x];
+        __stcg(mypart + threadIdx.x, s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned t = atomicAdd(p.tickets + pair, 1u);
+        is_last = (t == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    // last block of this pair: fixed-order (deterministic) fp64 reduction over blocks
+    {
+        const int v = threadIdx.x & 63, slice = threadIdx.x >> 6;
+        if (v < TRB_MOMENTS) {
+            const double *src = p.partials + (size_t)pair * gridDim.x * TRB_MOMENTS + v;
+            double a = 0.0;
+            for (int b = slice; b < (int)gridDim.x; b += 4) a += __ldcg(src + (size_t)b * TRB_MOMENTS);
+            fin[slice][v] = a;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < TRB_MOMENTS)
+        fin[0][threadIdx.x] = (fin[0][threadIdx.x] + fin[1][threadIdx.x]) + (fin[2][threadIdx.x] + fin[3][threadIdx.x]);
+    __syncthreads();
+    if (FUSED) {
+        if (threadIdx.x == 0) {
+            affine_epilogue<NDIM>(fin[0], p, pair);
+            p.tickets[pair] = 0u;
+        }
+    } else {
+        if (threadIdx.x < TRB_MOMENTS) p.moments_out[(size_t)pair * TRB_MOMENTS + threadIdx.x] = fin[0][threadIdx.x];
+        if (threadIdx.x == 0) p.tickets[pair] = 0u;
+    }
+}
+
+template <int NDIM>
+__global__ void affine_apply_kernel(const AffineParams p, const double *moments)
+{
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair < (int)p.pair_stride) affine_epilogue<NDIM>(moments + (size_t)pair * TRB_MOMENTS, p, pair);
+}
+
+template <int NDIM>
+__global__ void affine_init_state_kernel(float *state, int n_pairs, int mode)
+{
+    constexpr int NT = NDIM * (NDIM + 1);
+    const int pair = blockIdx.x * blockDim.x + threadIdx.x;
+    if (pair >= n_pairs) return;
+    float *st = state + (size_t)pair * TRB_STATE_FLOATS;
+    float th[12];
+    if (mode == TRB_MODE_RIGID) rigid_theta<NDIM>(st + TRB_STATE_PARAMS, th);
+    else
+        for (int i = 0; i < NT; ++i) th[i] = st[TRB_STATE_PARAMS + i];
+    for (int i = 0; i < NT; ++i) { st[TRB_STATE_THETA + i] = th[i]; st[TRB_STATE_BEST_THETA + i] = th[i]; }
+    st[TRB_STATE_BEST_LOSS] = 0.f;
+    st[TRB_STATE_LAST_LOSS] = 0.f;
+    for (int i = 0; i < 12; ++i) { st[TRB_STATE_ADAM_M + i] = 0.f; st[TRB_STATE_ADAM_V + i] = 0.f; }
+}
+
+// ---- forward-only warp (get_affine_warp, warpings.py:18-26) ------------------------------
+template <int NDIM>
+__global__ void __launch_bounds__(256) warp_affine_kernel(const float *__restrict__ moving, float *__restrict__ out,
+                                                           int n_channels, int D, int H, int W,
+                                                           const float *__restrict__ theta,
+                                                           const float *__restrict__ xb, const float *__restrict__ yb,
+                                                           const float *__restrict__ zb)
+{
+    constexpr int NC = NDIM + 1, NT = NDIM * NC;
+    float th[NT];
+#pragma unroll
+    for (int i = 0; i < NT; ++i) th[i] = __ldg(theta + i);
+    const size_t HW = (size_t)H * W, vol = HW * (NDIM == 3 ? D : 1);
+    const float hw = 0.5f * W, hh = 0.5f * H, hd = 0.5f * D;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        const int y = (int)((idx / W) % H);
+        const int z = (int)(idx / HW);
+        const float xv = __ldg(xb + x), yv = __ldg(yb + y);
+        if (NDIM == 3) {
+            const float zv = __ldg(zb + z);
+            const float ix = fmaf(th[0] * hw, xv, fmaf(th[1] * yv + th[2] * zv + th[3] + 1.f, hw, -0.5f));
+            const float iy = fmaf(th[4] * hh, xv, fmaf(th[5] * yv + th[6] * zv + th[7] + 1.f, hh, -0.5f));
+            const float iz = fmaf(th[8] * hd, xv, fmaf(th[9] * yv + th[10] * zv + th[11] + 1.f, hd, -0.5f));
+            const float fx = floorf(ix), fy = floorf(iy), fz = floorf(iz);
+            const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+            const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+            const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+            const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+            const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+            const long long o = ((long long)z0 * H + y0) * W + x0;
+            for (int c = 0; c < n_channels; ++c) {
+                const float *m = moving + (size_t)c * vol;
+                const float c000 = (vz0 & vy0 & vx0) ? __ldg(m + o) : 0.f;
+                const float c001 = (vz0 & vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
+                const float c010 = (vz0 & vy1 & vx0) ? __ldg(m + o + W) : 0.f;
+                const float c011 = (vz0 & vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
+                const float c100 = (vz1 & vy0 & vx0) ? __ldg(m + o + (long long)HW) : 0.f;
+                const float c101 = (vz1 & vy0 & vx1) ? __ldg(m + o + (long long)HW + 1) : 0.f;
+                const float c110 = (vz1 & vy1 & vx0) ? __ldg(m + o + (long long)HW + W) : 0.f;
+                const float c111 = (vz1 & vy1 & vx1) ? __ldg(m + o + (long long)HW + W + 1) : 0.f;
+                const float v00 = fmaf(tx, c001 - c000, c000), v01 = fmaf(tx, c011 - c010, c010);
+                const float v10 = fmaf(tx, c101 - c100, c100), v11 = fmaf(tx, c111 - c110, c110);
+                const float w0 = fmaf(ty, v01 - v00, v00), w1 = fmaf(ty, v11 - v10, v10);
+                out[(size_t)c * vol + idx] = fmaf(tz, w1 - w0, w0);
+            }
+        } else {
+            const float ix = fmaf(th[0] * hw, xv, fmaf(th[1] * yv + th[2] + 1.f, hw, -0.5f));
+            const float iy = fmaf(th[3] * hh, xv, fmaf(th[4] * yv + th[5] + 1.f, hh, -0.5f));
+            const float fx = floorf(ix), fy = floorf(iy);
+            const float tx = ix - fx, ty = iy - fy;
+            const int x0 = (int)fx, y0 = (int)fy;
+            const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+            const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+            const long long o = (long long)y0 * W + x0;
+            for (int c = 0; c < n_channels; ++c) {
+                const float *m = moving + (size_t)c * vol;
+                const float c00 = (vy0 & vx0) ? __ldg(m + o) : 0.f;
+                const float c01 = (vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
+                const float c10 = (vy1 & vx0) ? __ldg(m + o + W) : 0.f;
+                const float c11 = (vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
+                const float v0 = fmaf(tx, c01 - c00, c00), v1 = fmaf(tx, c11 - c10, c10);
+                out[(size_t)c * vol + idx] = fmaf(ty, v1 - v0, v0);
+            }
+        }
+    }
+}
+
+__global__ void vjp_extract_kernel(const double *moments, double *dtheta, int ndim, int D, int H, int W)
+{
+    const int i = threadIdx.x;
+    const int nc = ndim + 1;
+    if (i >= ndim * nc) return;
+    const int r = i / nc;
+    const double scale = r == 0 ? 0.5 * W : (r == 1 ? 0.5 * H : 0.5 * D);
+    dtheta[i] = moments[17 + i] * scale;      // sum_v gout_v * J_v (gout rides in the "target" slot)
+}
+
+// ---- host side ---------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count()
+{
+    if (g_sm_count == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    }
+    return g_sm_count;
+}
+
+constexpr int kMaxBlocksPerPair = 1024;
+
+static size_t affine_ws_bytes(int n_pairs)
+{
+    return (size_t)n_pairs * kMaxBlocksPerPair * TRB_MOMENTS * sizeof(double) + (size_t)n_pairs * 64 /*tickets, padded*/;
+}
+
+static int blocks_per_pair(int rows, int n_pairs)
+{
+    const int sms = sm_count();
+    const int groups = (rows + kWarps - 1) / kWarps;
+    // two resident CTAs per SM; whole waves across the batch
+    int per = (2 * sms + n_pairs - 1) / n_pairs;
+    if (per > groups) per = groups;
+    if (per > kMaxBlocksPerPair) per = kMaxBlocksPerPair;
+    if (per < 1) per = 1;
+    return per;
+}
+
+}  // namespace trb
+
+using namespace trb;
+
+extern "C" int trb_sm_count(void) { return sm_count(); }
+
+extern "C" size_t trb_affine_workspace_bytes(int n_pairs) { return affine_ws_bytes(n_pairs); }
+
+static int validate_common(int ndim, int n_pairs, int D, int H, int W)
+{
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3 (got %d)", ndim); return TRB_ERR_ARG; }
+    if (n_pairs < 1) { set_error("n_pairs must be >= 1"); return TRB_ERR_ARG; }
+    if (H < 1 || W < 1 || (ndim == 3 && D < 1)) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
+    if ((long long)(ndim == 3 ? D : 1) * H * W >= (1ll << 31)) { set_error("volume too large for 32-bit row indexing"); return TRB_ERR_UNSUPPORTED; }
+    return TRB_OK;
+}
+
+extern "C" int trb_affine_init_state(int ndim, int mode, float *state_dev, int n_pairs, void *stream)
+{
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
+    if (!state_dev || n_pairs < 1) { set_error("null state / n_pairs"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tb = 64, nb = (n_pairs + tb - 1) / tb;
+    if (ndim == 3) affine_init_state_kernel<3><<<nb, tb, 0, s>>>(state_dev, n_pairs, mode);
+    else affine_init_state_kernel<2><<<nb, tb, 0, s>>>(state_dev, n_pairs, mode);
+    return check_cuda(cudaGetLastError(), "affine_init_state");
+}
+
+static int fill_params(AffineParams &p, int ndim, const float *moving, const float *target, long long pair_stride,
+                       int n_pairs, int D, int H, int W, const float *xb, const float *yb, const float *zb,
+                       void *ws, size_t ws_bytes)
+{
+    int rc = validate_common(ndim, n_pairs, D, H, W);
+    if (rc) return rc;
+    if (!moving || !target || !xb || !yb || (ndim == 3 && !zb)) { set_error("null input pointer"); return TRB_ERR_ARG; }
+    if (!ws || ws_bytes < affine_ws_bytes(n_pairs)) { set_error("workspace too small: need %zu bytes", affine_ws_bytes(n_pairs)); return TRB_ERR_WORKSPACE; }
+    p.moving = moving; p.target = target; p.pair_stride = pair_stride;
+    p.D = ndim == 3 ? D : 1; p.H = H; p.W = W;
+    p.xb = xb; p.yb = yb; p.zb = zb;
+    p.partials = (double *)ws;
+    p.tickets = (unsigned *)((char *)ws + (size_t)n_pairs * kMaxBlocksPerPair * TRB_MOMENTS * sizeof(double));
+    return TRB_OK;
+}
+
+extern "C" int trb_affine_optim(int ndim, int mode, const float *moving_dev, const float *target_dev,
+                                long long pair_stride, int n_pairs, int D, int H, int W,
+                                const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                float *state_dev, float *loss_log_dev, int log_stride, int epoch0, int n_epochs,
+                                float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2,
+                                float adam_eps, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    AffineParams p{};
+    int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
+                         workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (!state_dev) { set_error("null state"); return TRB_ERR_ARG; }
+    if (mode != TRB_MODE_RIGID && mode != TRB_MODE_AFFINE) { set_error("bad mode %d", mode); return TRB_ERR_ARG; }
+    if (optimiser != TRB_OPT_SGD && optimiser != TRB_OPT_ADAM) { set_error("bad optimiser %d", optimiser); return TRB_ERR_ARG; }
+    if (loss_log_dev && epoch0 + n_epochs > log_stride) { set_error("loss log too short"); return TRB_ERR_ARG; }
+    p.s_begin = 0; p.s_end = ndim == 3 ? D : H;
+    p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride;
+    p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
+    p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rows = ndim == 3 ? D * H : H;
+    const dim3 grid(blocks_per_pair(rows, n_pairs), n_pairs);
+    for (int e = 0; e < n_epochs; ++e) {
+        p.epoch = epoch0 + e;
+        if (ndim == 3) affine_moments_kernel<3, true><<<grid, kThreads, 0, s>>>(p);
+        else affine_moments_kernel<2, true><<<grid, kThreads, 0, s>>>(p);
+    }
+    return check_cuda(cudaGetLastError(), "affine_optim");
+}
+
+extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
+                                  int n_pairs, int D, int H, int W, int s_begin, int s_end,
+                                  const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                  const float *state_dev, double *moments_dev,
+                                  void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    AffineParams p{};
+    int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
+                         workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    const int smax = ndim == 3 ? D : H;
+    if (s_begin < 0 || s_end > smax || s_begin >= s_end) { set_error("bad slab [%d,%d) of %d", s_begin, s_end, smax); return TRB_ERR_ARG; }
+    if (!state_dev || !moments_dev) { set_error("null state/moments"); return TRB_ERR_ARG; }
+    p.s_begin = s_begin; p.s_end = s_end;
+    p.state = const_cast<float *>(state_dev);
+    p.moments_out = moments_dev;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int rows = (s_end - s_begin) * (ndim == 3 ? H : 1);
+    const dim3 grid(blocks_per_pair(rows, n_pairs), n_pairs);
+    if (ndim == 3) affine_moments_kernel<3, false><<<grid, kThreads, 0, s>>>(p);
+    else affine_moments_kernel<2, false><<<grid, kThreads, 0, s>>>(p);
+    return check_cuda(cudaGetLastError(), "affine_moments");
+}
+
+extern "C" int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs, int D, int H, int W,
+                                float *state_dev, float *loss_log_dev, int log_stride, int epoch,
+                                float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2,
+                                float adam_eps, void *stream)
+{
+    int rc = validate_common(ndim, n_pairs, D, H, W);
+    if (rc) return rc;
+    if (!moments_dev || !state_dev) { set_error("null moments/state"); return TRB_ERR_ARG; }
+    if (loss_log_dev && epoch >= log_stride) { set_error("loss log too short"); return TRB_ERR_ARG; }
+    AffineParams p{};
+    p.pair_stride = n_pairs;     // apply kernel: number of pairs rides in pair_stride
+    p.D = ndim == 3 ? D : 1; p.H = H; p.W = W;
+    p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride; p.epoch = epoch;
+    p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
+    p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
+    cudaStream_t s = (cudaStream_t)stream;
+    const int tb = 32, nb = (n_pairs + tb - 1) / tb;
+    if (ndim == 3) affine_apply_kernel<3><<<nb, tb, 0, s>>>(p, moments_dev);
+    else affine_apply_kernel<2><<<nb, tb, 0, s>>>(p, moments_dev);
+    return check_cuda(cudaGetLastError(), "affine_apply");
+}
+
+extern "C" int trb_warp_affine(int ndim, const float *moving_dev, float *out_dev, int n_channels, int D, int H, int W,
+                               const float *theta_dev, const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                               void *stream)
+{
+    int rc = validate_common(ndim, 1, D, H, W);
+    if (rc) return rc;
+    if (!moving_dev || !out_dev || !theta_dev || !xb_dev || !yb_dev || (ndim == 3 && !zb_dev) || n_channels < 1) {
+        set_error("null pointer / n_channels"); return TRB_ERR_ARG;
+    }
+    const size_t vol = (size_t)(ndim == 3 ? D : 1) * H * W;
+    const int sms = sm_count();
+    size_t nb = (vol + 255) / 256;
+    if (nb > (size_t)sms * 16) nb = (size_t)sms * 16;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ndim == 3) warp_affine_kernel<3><<<(unsigned)nb, 256, 0, s>>>(moving_dev, out_dev, n_channels, D, H, W, theta_dev, xb_dev, yb_dev, zb_dev);
+    else warp_affine_kernel<2><<<(unsigned)nb, 256, 0, s>>>(moving_dev, out_dev, n_channels, 1, H, W, theta_dev, xb_dev, yb_dev, zb_dev);
+    return check_cuda(cudaGetLastError(), "warp_affine");
+}
+
+extern "C" int trb_warp_affine_vjp(int ndim, const float *moving_dev, const float *gout_dev, int D, int H, int W,
+                                   const float *theta_dev, const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                   double *dtheta_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    // Reuses the moments pass with gout in the target slot: sum_v gout_v * J_v is moment block [17..28].
+    // The unfused pass only ever reads state[TRB_STATE_THETA .. +12), so a bare theta pointer is rebased.
+    if (!dtheta_dev) { set_error("null dtheta"); return TRB_ERR_ARG; }
+    if (workspace_bytes < affine_ws_bytes(1) + TRB_MOMENTS * sizeof(double)) {
+        set_error("workspace too small: need %zu bytes", affine_ws_bytes(1) + TRB_MOMENTS * sizeof(double));
+        return TRB_ERR_WORKSPACE;
+    }
+    double *mom = (double *)((char *)workspace_dev + affine_ws_bytes(1));
+    int rc = trb_affine_moments(ndim, moving_dev, gout_dev, 0, 1, D, H, W, 0, ndim == 3 ? D : H, xb_dev, yb_dev, zb_dev,
+                                theta_dev - TRB_STATE_THETA, mom, workspace_dev, affine_ws_bytes(1), stream);
+    if (rc) return rc;
+    vjp_extract_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mom, dtheta_dev, ndim, ndim == 3 ? D : 1, H, W);
+    return check_cuda(cudaGetLastError(), "warp_affine_vjp");
+}

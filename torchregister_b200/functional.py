@@ -1,0 +1,294 @@
+"""Tensor-level wrappers over the C ABI (include/trb.h).
+
+PyTorch is used for device memory, streams and (elsewhere) torch.distributed
+only; all arithmetic of the hot path runs in libtrb_b200.so.  Every function
+requires CUDA tensors and raises otherwise — there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+STATE_FLOATS = 64
+S_PARAMS, S_THETA, S_BEST_THETA, S_BEST_LOSS, S_LAST_LOSS = 0, 12, 24, 36, 37
+MOMENTS = 41
+MODE = {"rigid": 0, "affine": 1}
+OPT = {"sgd": 0, "adam": 1}
+
+
+def _stream(device) -> int:
+    return torch.cuda.current_stream(device).cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def require_cuda(t: torch.Tensor, name: str) -> None:
+    if not isinstance(t, torch.Tensor):
+        raise TypeError("%s must be a torch.Tensor" % name)
+    if not t.is_cuda:
+        raise RuntimeError(
+            "torchregister_b200 runs on CUDA (B200, sm_100a) only; %s is on %s. "
+            "There is no CPU fallback — use the reference TorchRegister for device='cpu'." % (name, t.device))
+    if t.dtype != torch.float32:
+        raise TypeError("%s must be float32 (got %s)" % (name, t.dtype))
+
+
+def _vol_dims(t: torch.Tensor):
+    """[N, C, (D,) H, W] -> (ndim, D, H, W)."""
+    if t.dim() == 5:
+        return 3, int(t.shape[2]), int(t.shape[3]), int(t.shape[4])
+    if t.dim() == 4:
+        return 2, 1, int(t.shape[2]), int(t.shape[3])
+    raise ValueError("expected a 4-D [N,C,H,W] or 5-D [N,C,D,H,W] tensor, got shape %s" % (tuple(t.shape),))
+
+
+# --------------------------------------------------------------------------- #
+# base coordinates
+# --------------------------------------------------------------------------- #
+_TABLES = {}
+
+
+def base_coords(size: int, device) -> torch.Tensor:
+    """linspace(-1, 1, S) * (S - 1) / S — the per-axis base grid F.affine_grid builds
+    for align_corners=False (reference call site warpings.py:24).  Computed with
+    torch on the host so the values are bit-identical to the CPU reference, then
+    cached on the device: three 1-D tables replace the materialised [N,D,H,W,3] grid."""
+    key = (int(size), str(device))
+    t = _TABLES.get(key)
+    if t is None:
+        if size <= 1:
+            h = torch.zeros(max(size, 1), dtype=torch.float32)
+        else:
+            h = torch.linspace(-1, 1, size, dtype=torch.float32) * (size - 1) / size
+        t = h.to(device)
+        _TABLES[key] = t
+    return t
+
+
+# --------------------------------------------------------------------------- #
+# rigid / affine registration
+# --------------------------------------------------------------------------- #
+class AffineProblem:
+    """Device-resident state for `n_pairs` independent rigid/affine registrations
+    of equally shaped volume pairs (one fused launch per epoch covers the batch)."""
+
+    def __init__(self, moving: torch.Tensor, target: torch.Tensor, mode: str, params0: torch.Tensor,
+                 max_epochs: int):
+        require_cuda(moving, "moving")
+        require_cuda(target, "target")
+        if moving.shape != target.shape:
+            raise ValueError("moving %s and target %s shapes differ" % (tuple(moving.shape), tuple(target.shape)))
+        if moving.shape[1] != 1:
+            raise ValueError("registration expects single-channel volumes [N,1,...]; got C=%d" % moving.shape[1])
+        if mode not in MODE:
+            raise ValueError("mode must be 'rigid' or 'affine'")
+        self.lib = _lib.load()
+        self.device = moving.device
+        self.mode = mode
+        self.ndim, self.D, self.H, self.W = _vol_dims(moving)
+        self.n_pairs = int(moving.shape[0])
+        self.moving = moving.contiguous()
+        self.target = target.contiguous()
+        self.pair_stride = self.D * self.H * self.W
+        self.nt = self.ndim * (self.ndim + 1)
+        self.np = (6 if self.ndim == 3 else 3) if mode == "rigid" else self.nt
+        self.xb = base_coords(self.W, self.device)
+        self.yb = base_coords(self.H, self.device)
+        self.zb = base_coords(self.D, self.device) if self.ndim == 3 else None
+        p0 = torch.as_tensor(params0, dtype=torch.float32, device=self.device).reshape(-1, self.np)
+        if p0.shape[0] == 1 and self.n_pairs > 1:
+            p0 = p0.expand(self.n_pairs, self.np)
+        if p0.shape[0] != self.n_pairs:
+            raise ValueError("params0 must have %d rows" % self.n_pairs)
+        self.state = torch.zeros(self.n_pairs, STATE_FLOATS, dtype=torch.float32, device=self.device)
+        self.state[:, : self.np] = p0
+        self.max_epochs = int(max_epochs)
+        self.loss_log = torch.zeros(self.n_pairs, max(self.max_epochs, 1), dtype=torch.float32, device=self.device)
+        ws_bytes = int(self.lib.trb_affine_workspace_bytes(self.n_pairs))
+        self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)   # zero: tickets start at 0
+        self.epoch = 0
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_affine_init_state(self.ndim, MODE[mode], self.state.data_ptr(), self.n_pairs,
+                                                 _stream(self.device)), "affine_init_state")
+
+    def run(self, n_epochs: int, lr: float, w_mse: float, w_ncc: float, optimiser: str = "sgd",
+            betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        """Enqueue `n_epochs` fused epochs (asynchronous; no host sync)."""
+        if n_epochs <= 0:
+            return
+        if self.epoch + n_epochs > self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_affine_optim(
+                self.ndim, MODE[self.mode], self.moving.data_ptr(), self.target.data_ptr(), self.pair_stride,
+                self.n_pairs, self.D, self.H, self.W, self.xb.data_ptr(), self.yb.data_ptr(), _ptr(self.zb),
+                self.state.data_ptr(), self.loss_log.data_ptr(), self.loss_log.shape[1], self.epoch, n_epochs,
+                float(w_mse), float(w_ncc), float(lr), OPT[optimiser], float(betas[0]), float(betas[1]), float(eps),
+                self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "affine_optim")
+        self.epoch += n_epochs
+
+    # -- sharded (z-slab) form: moments -> [all-reduce by the caller] -> apply
+    def moments(self, s_begin: int, s_end: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        if out is None:
+            out = torch.empty(self.n_pairs, MOMENTS, dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_affine_moments(
+                self.ndim, self.moving.data_ptr(), self.target.data_ptr(), self.pair_stride, self.n_pairs,
+                self.D, self.H, self.W, int(s_begin), int(s_end), self.xb.data_ptr(), self.yb.data_ptr(),
+                _ptr(self.zb), self.state.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
+                self.workspace.numel(), _stream(self.device)), "affine_moments")
+        return out
+
+    def apply(self, moments: torch.Tensor, lr: float, w_mse: float, w_ncc: float, optimiser: str = "sgd",
+              betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        if self.epoch + 1 > self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_affine_apply(
+                self.ndim, MODE[self.mode], moments.data_ptr(), self.n_pairs, self.D, self.H, self.W,
+                self.state.data_ptr(), self.loss_log.data_ptr(), self.loss_log.shape[1], self.epoch,
+                float(w_mse), float(w_ncc), float(lr), OPT[optimiser], float(betas[0]), float(betas[1]), float(eps),
+                _stream(self.device)), "affine_apply")
+        self.epoch += 1
+
+    # -- results (device tensors; reading them on the host is the only sync)
+    def _theta(self, off: int) -> torch.Tensor:
+        return self.state[:, off: off + self.nt].reshape(self.n_pairs, self.ndim, self.ndim + 1).clone()
+
+    @property
+    def final_theta(self) -> torch.Tensor:
+        return self._theta(S_THETA)
+
+    @property
+    def best_theta(self) -> torch.Tensor:
+        return self._theta(S_BEST_THETA)
+
+    @property
+    def params(self) -> torch.Tensor:
+        return self.state[:, : self.np].clone()
+
+    @property
+    def losses(self) -> torch.Tensor:
+        return self.loss_log[:, : self.epoch]
+
+
+def warp_affine(theta: torch.Tensor, moving: torch.Tensor) -> torch.Tensor:
+    """out[0, c] = grid_sample(moving[0, c], affine_grid(theta)), align_corners=False,
+    zeros padding (reference get_affine_warp, warpings.py:18-26).  theta: 12|6 values."""
+    require_cuda(moving, "moving")
+    ndim, D, H, W = _vol_dims(moving)
+    if moving.shape[0] != 1:
+        raise ValueError("get_affine_warp expects N == 1 (the reference's theta is [1,%d,%d])" % (ndim, ndim + 1))
+    lib = _lib.load()
+    dev = moving.device
+    th = torch.as_tensor(theta, dtype=torch.float32, device=dev).detach().reshape(-1).contiguous()
+    if th.numel() != ndim * (ndim + 1):
+        raise ValueError("theta has %d values, expected %d" % (th.numel(), ndim * (ndim + 1)))
+    src = moving.detach().contiguous()
+    out = torch.empty_like(src)
+    xb, yb = base_coords(W, dev), base_coords(H, dev)
+    zb = base_coords(D, dev) if ndim == 3 else None
+    with torch.cuda.device(dev):
+        check(lib.trb_warp_affine(ndim, src.data_ptr(), out.data_ptr(), int(src.shape[1]), D, H, W, th.data_ptr(),
+                                  xb.data_ptr(), yb.data_ptr(), _ptr(zb), _stream(dev)), "warp_affine")
+    return out
+
+
+def warp_affine_vjp(theta: torch.Tensor, moving: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """d theta (fp64 [ndim, ndim+1]) = sum_v grad_out_v * d warped_v / d theta; single channel."""
+    require_cuda(moving, "moving")
+    require_cuda(grad_out, "grad_out")
+    ndim, D, H, W = _vol_dims(moving)
+    if moving.shape[0] != 1 or moving.shape[1] != 1:
+        raise ValueError("warp_affine_vjp expects [1,1,...]")
+    lib = _lib.load()
+    dev = moving.device
+    th = torch.as_tensor(theta, dtype=torch.float32, device=dev).detach().reshape(-1).contiguous()
+    ws_bytes = int(lib.trb_affine_workspace_bytes(1)) + MOMENTS * 8
+    ws = torch.zeros(ws_bytes, dtype=torch.uint8, device=dev)
+    out = torch.empty(ndim * (ndim + 1), dtype=torch.float64, device=dev)
+    xb, yb = base_coords(W, dev), base_coords(H, dev)
+    zb = base_coords(D, dev) if ndim == 3 else None
+    with torch.cuda.device(dev):
+        check(lib.trb_warp_affine_vjp(ndim, moving.contiguous().data_ptr(), grad_out.contiguous().data_ptr(),
+                                      D, H, W, th.data_ptr(), xb.data_ptr(), yb.data_ptr(), _ptr(zb),
+                                      out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "warp_affine_vjp")
+    return out.reshape(ndim, ndim + 1)
+
+
+# --------------------------------------------------------------------------- #
+# flow field
+# --------------------------------------------------------------------------- #
+def _check_flow(src: torch.Tensor, flow: torch.Tensor):
+    require_cuda(src, "src")
+    require_cuda(flow, "flow")
+    ndim, D, H, W = _vol_dims(src)
+    if src.shape[0] != 1 or flow.shape[0] != 1:
+        raise ValueError("flow warp expects N == 1")
+    if tuple(flow.shape[1:]) != (ndim,) + tuple(src.shape[2:]):
+        raise ValueError("flow shape %s does not match src %s" % (tuple(flow.shape), tuple(src.shape)))
+    return ndim, D, H, W
+
+
+def warp_flow(src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
+    """SpatialTransformer.forward (reference utils.py:350-365), all channels of `src`."""
+    ndim, D, H, W = _check_flow(src, flow)
+    lib = _lib.load()
+    dev = src.device
+    s, f = src.detach().contiguous(), flow.detach().contiguous()
+    out = torch.empty_like(s)
+    with torch.cuda.device(dev):
+        check(lib.trb_warp_flow(ndim, s.data_ptr(), f.data_ptr(), out.data_ptr(), int(s.shape[1]), D, H, W,
+                                _stream(dev)), "warp_flow")
+    return out
+
+
+def warp_flow_vjp(src: torch.Tensor, flow: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+    """d flow = J^T grad_out for the single-channel warp."""
+    ndim, D, H, W = _check_flow(src, flow)
+    if src.shape[1] != 1:
+        raise ValueError("warp_flow_vjp expects a single channel")
+    require_cuda(grad_out, "grad_out")
+    lib = _lib.load()
+    dev = src.device
+    s, f, g = src.detach().contiguous(), flow.detach().contiguous(), grad_out.detach().contiguous()
+    dflow = torch.empty_like(f)
+    with torch.cuda.device(dev):
+        check(lib.trb_warp_flow_vjp(ndim, s.data_ptr(), f.data_ptr(), g.data_ptr(), dflow.data_ptr(), D, H, W,
+                                    _stream(dev)), "warp_flow_vjp")
+    return dflow
+
+
+_FLOW_WS = {}
+
+
+def flow_loss_grad(moving: torch.Tensor, target: torch.Tensor, flow: torch.Tensor, w_mse: float, w_ncc: float,
+                   want_warped: bool = False):
+    """-> (loss [1] float32 dev, dflow, warped or None): fused warp + w_mse*MSE + w_ncc*100(1-NCC)
+    + gradient w.r.t. the flow (reference utils.py:350-365 + warpings.py:213-215)."""
+    ndim, D, H, W = _check_flow(moving, flow)
+    require_cuda(target, "target")
+    if moving.shape[1] != 1 or target.shape != moving.shape:
+        raise ValueError("moving/target must both be [1,1,...] of equal shape")
+    lib = _lib.load()
+    dev = moving.device
+    key = str(dev)
+    ws = _FLOW_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(lib.trb_flow_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _FLOW_WS[key] = ws
+    m, t, f = moving.detach().contiguous(), target.detach().contiguous(), flow.detach().contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    dflow = torch.empty_like(f)
+    warped = torch.empty_like(m) if want_warped else None
+    with torch.cuda.device(dev):
+        check(lib.trb_flow_loss_grad(ndim, m.data_ptr(), t.data_ptr(), f.data_ptr(), D, H, W, float(w_mse),
+                                     float(w_ncc), loss.data_ptr(), dflow.data_ptr(), _ptr(warped),
+                                     ws.data_ptr(), ws.numel(), _stream(dev)), "flow_loss_grad")
+    return loss, dflow, warped

@@ -1,0 +1,85 @@
+"""`Register` — drop-in for the reference's user API (TR/torchregister.py:11-129).
+
+Same constructor, `optim`, `__call__` and attributes; the work is done by the fused
+sm_100a kernels behind warpings.py.  CUDA only.
+"""
+from __future__ import annotations
+
+from torch import cat
+
+from .warpings import flow_register, affine_register, rigid_register, get_affine_warp
+
+
+class Register():
+    def __init__(self, mode='rigid', device='cpu', criterion=None, weight=None, grad_edges=False, debug=False):
+        '''
+        B200 registration with the reference's interface (torchregister.py:12-44).
+
+        Parameters
+        ----------
+        mode : 'rigid' | 'affine' | 'flow'. The default is 'rigid'.
+        device : device the optimisation runs on. The default 'cpu' is accepted for signature
+            compatibility, but this implementation has no CPU path: `optim` raises unless the
+            device is a CUDA device.
+        criterion, weight : as in the reference — (criterion and weight) are passed through,
+            weight alone re-weights the default [MSE, NCC, NMI] terms. NOTE the reference ignores a
+            user criterion in rigid/affine mode and uses MSE (warpings.py:38-40,125-127); so do we.
+        grad_edges, debug : as in the reference.
+        '''
+        self.criterion = criterion
+        self.weight = weight
+        self.mode = mode
+        self.warp = None if mode == 'flow' else get_affine_warp
+        self.device = device
+        self.debug = debug
+        self.theta = None
+        self.grad_edges = grad_edges
+        self.losses = None
+
+    def _check_device(self):
+        import torch
+        if torch.device(self.device).type != 'cuda':
+            raise RuntimeError(
+                "torchregister_b200.Register runs on CUDA only (got device=%r); there is no CPU fallback. "
+                "Use Register(device='cuda')." % (self.device,))
+
+    def optim(self, moving, target, lr=1E-5, max_epochs=1000, n=32, per=0.1):
+        '''
+        Optimisation loop (reference torchregister.py:46-106). Sets `self.theta` to the best
+        (lowest-loss, pre-step) theta for rigid/affine, or to the last flow field for flow.
+        '''
+        self._check_device()
+        moving = moving.to(self.device)
+        target = target.to(self.device)
+        both = self.criterion is not None and self.weight is not None
+        if self.mode == 'flow':
+            kw = dict(mode='bilinear', n=n, lr=lr, max_epochs=max_epochs)
+            if both:
+                kw.update(criterions=self.criterion, weights=self.weight)
+            elif self.weight is not None:
+                kw.update(weights=self.weight)
+            flowreg = flow_register(target.shape[2:], **kw).to(self.device)
+            flowreg.optimize(moving, target, self.device, self.debug)
+            self.theta = flowreg.flow
+            self.warp = flowreg.deform
+            self.losses = flowreg.losses
+            self._flowreg = flowreg
+        else:
+            fn = affine_register if self.mode == 'affine' else rigid_register
+            kw = dict(lr=lr, epochs=max_epochs, per=per, device=self.device, debug=self.debug,
+                      grad_edges=self.grad_edges)
+            if both:
+                kw.update(criterions=self.criterion, weights=self.weight)
+            elif self.weight is not None:
+                kw.update(weights=self.weight)
+            _, theta = fn(moving, target, **kw)
+            self.theta = theta[-1]
+
+    def __call__(self, moving):
+        '''
+        Warp `moving` [1,c,...] with the deformation found by `optim` (reference torchregister.py:108-129).
+        '''
+        moving = moving.to(self.device)
+        if self.mode == 'flow':
+            return self.warp(moving)                 # all channels in one launch
+        return self.warp(self.theta, moving)

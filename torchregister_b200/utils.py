@@ -1,0 +1,228 @@
+"""Host-side mirror of the reference's building blocks (TR/utils.py) for the hot path.
+
+Same public names and call signatures as the reference so `from utils import ...`
+style code keeps working; the arithmetic of the warp and of the similarity runs in
+libtrb_b200.so (see functional.py).  The flow network (Attention_UNet) is a dense
+conv stack outside the gather/stencil path and stays PyTorch/cuDNN, as SURVEY.md
+§8a-9 scopes it; it is re-written here (not copied) with identical parameter names
+so reference state_dicts load.
+"""
+from __future__ import annotations
+
+from math import ceil
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from . import functional as TF
+
+EPSILON = 1E-10
+
+__all__ = ["EPSILON", "NCCLoss", "SSDLoss", "norm", "padNd", "Theta", "Regressor", "SpatialTransformer",
+           "attention_grid", "Attention_UNet"]
+
+
+# --------------------------------------------------------------------------- #
+# similarity modules (API parity).  Inside Register/rigid/affine/flow the MSE and
+# NCC terms are recognised by type and evaluated by the fused CUDA kernels; the
+# nn.Module forwards below exist for users who call the criteria directly.
+# --------------------------------------------------------------------------- #
+class NCCLoss(nn.Module):
+    """Global normalised cross-correlation, loss = (1 - NCC) * alpha
+    (reference utils.py:186-205; `grad_edges` and `device` are accepted and unused there too)."""
+
+    def __init__(self, alpha=100, grad_edges=True, device='cpu'):
+        super().__init__()
+        self.NCC = None
+        self.alpha = alpha
+
+    def forward(self, y, yp):
+        a = y - torch.mean(y)
+        b = yp - torch.mean(yp)
+        self.NCC = torch.sum(a * b) / ((torch.sum(a ** 2) * torch.sum(b ** 2) + EPSILON) ** 0.5)
+        return (1 - self.NCC) * self.alpha
+
+
+class SSDLoss(nn.Module):
+    """Sum of squared differences times alpha (reference utils.py:208-221; unused by any loop)."""
+
+    def __init__(self, alpha=3):
+        super().__init__()
+        self.SSD = None
+        self.alpha = alpha
+
+    def forward(self, y, yp):
+        self.SSD = torch.sum((y - yp) ** 2)
+        return self.SSD * self.alpha
+
+
+def norm(x):
+    """Min-max normalisation (reference utils.py:262-267)."""
+    try:
+        lo = torch.min(x)
+        return (x - lo) / ((torch.max(x) - lo) + 1E-9)
+    except Exception:
+        print('WARNING: Input could not be normalized!')
+
+
+def padNd(input_, target, device='cpu', mode='constant', value=0):
+    """Centre-pad `input_` to the spatial size of `target` (reference utils.py:271-277)."""
+    dims = input_.dim() - 2
+    pads = []
+    for i in reversed(range(dims)):
+        delta = target.shape[2 + i] - input_.shape[2 + i]
+        lo = ceil(delta / 2)
+        pads += [lo, delta - lo]
+    return F.pad(input_, tuple(pads), mode=mode, value=value).to(dtype=torch.float, device=device)
+
+
+# --------------------------------------------------------------------------- #
+# rigid parametrisation (API parity; the optimisation loop evaluates it on device
+# inside the fused kernel's epilogue)
+# --------------------------------------------------------------------------- #
+class Theta(nn.Module):
+    """6 -> 12 (ZYX Euler + 0.25*tanh translation) or 3 -> 6 (reference utils.py:280-310)."""
+
+    def forward(self, x, max_translate=0.25):
+        if len(x) > 3:
+            cps, sps = torch.cos(x[0]), torch.sin(x[0])
+            cth, sth = torch.cos(x[1]), torch.sin(x[1])
+            cph, sph = torch.cos(x[2]), torch.sin(x[2])
+            t = max_translate * torch.tanh(x[3:6])
+            return torch.stack((cps * cth, sph * sps * cth - cph * sth, cph * sps * cth + sph * sth, t[0],
+                                cps * sth, sph * sps * sth + cph * cth, cph * sps * sth - sph * cth, t[1],
+                                -sps, sph * cps, cph * cps, t[2])).flatten()
+        c, s = torch.cos(x[0]), torch.sin(x[0])
+        return torch.stack((c, -s, x[1], s, c, x[2])).flatten()
+
+
+class Regressor(nn.Module):
+    """Rigid parameters, initialised with torch.rand on `device` (reference utils.py:313-330)."""
+
+    def __init__(self, moving, device):
+        super().__init__()
+        self.reg = nn.Parameter(torch.rand(6 if moving.dim() == 5 else 3, device=device), requires_grad=True)
+        self.thetas = Theta()
+
+    def forward(self):
+        theta = self.thetas(self.reg)
+        return theta.view(1, 3, 4) if theta.shape[-1] == 12 else theta.view(1, 2, 3)
+
+
+# --------------------------------------------------------------------------- #
+# flow warp
+# --------------------------------------------------------------------------- #
+class _WarpFlowFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, flow):
+        ctx.save_for_backward(src, flow)
+        return TF.warp_flow(src, flow)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        src, flow = ctx.saved_tensors
+        if src.shape[1] != 1:
+            raise NotImplementedError("gradient of the flow warp is implemented for single-channel src")
+        dflow = TF.warp_flow_vjp(src, flow, grad_out.contiguous()) if ctx.needs_input_grad[1] else None
+        return None, dflow       # no gradient to `src`: the moving image is constant on this path
+
+
+class SpatialTransformer(nn.Module):
+    """N-D spatial transformer: samples `src` at voxel index + flow (voxel units, channel i
+    displaces spatial axis i), bilinear, zeros padding (reference utils.py:333-365).
+    The identity index grid the reference keeps as a buffer is computed in the kernel."""
+
+    def __init__(self, size, mode='bilinear'):
+        super().__init__()
+        if mode != 'bilinear':
+            raise NotImplementedError("only mode='bilinear' (the mode Register uses, torchregister.py:72-79)")
+        self.mode = mode
+        self.size = tuple(int(s) for s in size)
+
+    def forward(self, src, flow):
+        return _WarpFlowFn.apply(src, flow)
+
+
+# --------------------------------------------------------------------------- #
+# flow network: PyTorch/cuDNN host code, same topology and
+# parameter names as reference utils.py:368-559
+# --------------------------------------------------------------------------- #
+def _nd(dims):
+    return (nn.Conv3d, nn.ConvTranspose3d, nn.InstanceNorm3d, nn.MaxPool3d) if dims == 3 else \
+           (nn.Conv2d, nn.ConvTranspose2d, nn.InstanceNorm2d, nn.MaxPool2d)
+
+
+class attention_grid(nn.Module):
+    """Additive attention gate with a stride-3 1x1 projection of the skip (reference utils.py:368-406)."""
+
+    def __init__(self, x_c, g_c, i_c, stride=3, mode='nearest', dims=3):
+        super().__init__()
+        conv, _, inorm, _ = _nd(dims)
+        self.input_filter = conv(x_c, i_c, kernel_size=1, stride=stride, bias=False)
+        self.gate_filter = conv(g_c, i_c, kernel_size=1, stride=1, bias=True)
+        self.psi = conv(i_c, 1, kernel_size=1, stride=1, bias=True)
+        self.bnorm = inorm(i_c)
+        self.mode = mode
+
+    def forward(self, x, g, device):
+        a, b = self.input_filter(x), self.gate_filter(g)
+        if a.shape[-1] < b.shape[-1]:
+            a = padNd(a, b, device)
+        elif a.shape[-1] > b.shape[-1]:
+            b = padNd(b, a, device)
+        w = torch.sigmoid(self.psi(F.relu(a + b)))
+        w = F.interpolate(w, size=x.shape[2:], mode=self.mode)
+        return self.bnorm(x * w), w
+
+
+class Attention_UNet(nn.Module):
+    """5-level valid-convolution attention U-Net whose 1x1 head emits the flow, followed by the
+    warp of its own input (reference utils.py:409-559).  Widths 64/n .. 1024/n."""
+
+    def __init__(self, img_size, mode='nearest', in_c=1, n=1):
+        super().__init__()
+        dims = len(img_size)
+        conv, convT, inorm, pool = _nd(dims)
+        w = [int(c / n) for c in (64, 128, 256, 512, 1024)]
+
+        def double(ci, co, up_to=None):
+            mods = [conv(ci, co, kernel_size=3), nn.ReLU(), inorm(co),
+                    conv(co, co, kernel_size=3), nn.ReLU(), inorm(co)]
+            if up_to is not None:
+                mods += [convT(co, up_to, kernel_size=2, stride=2), nn.ReLU(), inorm(up_to)]
+            return nn.Sequential(*mods)
+
+        self.layer1 = double(in_c, w[0])
+        self.skip1 = attention_grid(w[0], w[0], w[0], dims=dims)
+        self.layer2 = double(w[0], w[1])
+        self.skip2 = attention_grid(w[1], w[1], w[1], dims=dims)
+        self.layer3 = double(w[1], w[2])
+        self.skip3 = attention_grid(w[2], w[2], w[2], dims=dims)
+        self.layer4 = double(w[2], w[3])
+        self.skip4 = attention_grid(w[3], w[3], w[3], dims=dims)
+        self.layer5 = double(w[3], w[4], up_to=w[3])
+        self.layer6 = double(w[4], w[3], up_to=w[2])
+        self.layer7 = double(w[3], w[2], up_to=w[1])
+        self.layer8 = double(w[2], w[1], up_to=w[0])
+        self.layer9 = double(w[1], w[0])
+        self.out = conv(w[0], dims, kernel_size=1)
+        self.maxpool = pool(kernel_size=2, stride=2)
+        self.warp = SpatialTransformer(img_size, mode)
+
+    def flow_field(self, x, device):
+        """The network part only: x -> flow (no warp)."""
+        y1 = self.layer1(x)
+        y2 = self.layer2(self.maxpool(y1))
+        y3 = self.layer3(self.maxpool(y2))
+        y4 = self.layer4(self.maxpool(y3))
+        y = self.layer5(self.maxpool(y4))
+        for skip, enc, dec in ((self.skip4, y4, self.layer6), (self.skip3, y3, self.layer7),
+                               (self.skip2, y2, self.layer8), (self.skip1, y1, self.layer9)):
+            gated, _ = skip(enc, y, device=device)
+            y = dec(torch.cat((gated, padNd(y, gated, device=device)), dim=1))
+        return self.out(padNd(y, x, device=device))
+
+    def forward(self, x, device, out_att=False):
+        flow = self.flow_field(x, device)
+        return self.warp(x, flow), flow

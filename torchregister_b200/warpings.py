@@ -1,0 +1,219 @@
+"""Registration loops — host-side mirror of the reference's TR/warpings.py with the
+loop bodies executed by fused sm_100a kernels (one launch per epoch, no per-epoch
+host synchronisation for rigid/affine).
+
+Same function names, argument meaning, defaults and return structure as the
+reference (warpings.py:18,30,117,178) so they drop in; what differs is stated in
+each docstring.  CUDA only: there is no CPU path.
+"""
+from __future__ import annotations
+
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import functional as TF
+from .utils import Attention_UNet, NCCLoss
+
+__all__ = ["get_affine_warp", "affine_register", "rigid_register", "flow_register", "similarity_weights"]
+
+
+# --------------------------------------------------------------------------- #
+# warp
+# --------------------------------------------------------------------------- #
+class _AffineWarpFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, theta, moving):
+        ctx.save_for_backward(theta, moving)
+        return TF.warp_affine(theta, moving)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        theta, moving = ctx.saved_tensors
+        dth = None
+        if ctx.needs_input_grad[0]:
+            if moving.shape[1] != 1:
+                raise NotImplementedError("d/dtheta of get_affine_warp is implemented for single-channel input")
+            dth = TF.warp_affine_vjp(theta, moving, grad_out.contiguous()).to(theta.dtype).reshape(theta.shape)
+        return dth, None
+
+
+def get_affine_warp(theta, moving):
+    """warped = grid_sample(moving, affine_grid(theta), bilinear, zeros, align_corners=False)
+    (reference warpings.py:18-26).  theta: [1,2,3] / [1,3,4] or flat [*,6] / [*,12].
+    One fused kernel, no materialised grid; differentiable w.r.t. theta."""
+    return _AffineWarpFn.apply(theta, moving)
+
+
+# --------------------------------------------------------------------------- #
+# criterion bookkeeping
+# --------------------------------------------------------------------------- #
+def similarity_weights(criterions, weights, where: str) -> Tuple[float, float]:
+    """Map the reference's (criterions, weights) convention for the rigid/affine loops
+    (warpings.py:36-40,123-127) onto the fused kernel's (w_mse, w_ncc).
+
+      criterions is None     -> [MSE, NCC, NMI] with `weights`
+      criterions is not None -> the reference silently replaces it by [MSE], [1.]
+    The NMI term (reference utils.py:224-259) is not fused yet: weight[2] must be 0."""
+    if criterions is not None:
+        return 1.0, 0.0
+    w = list(weights)
+    if len(w) < 3:
+        raise IndexError("weights must have 3 entries (MSE, NCC, NMI) when criterions is None")
+    if w[2] != 0:
+        raise NotImplementedError(
+            "%s: the NMI/KDE similarity term (weight[2]=%g) is not part of the fused CUDA path yet "
+            "(SURVEY.md §8f-1). Pass weight=[w_mse, w_ncc, 0.] — e.g. Register(weight=[0.5, 0.5, 0.])." % (where, w[2]))
+    return float(w[0]), float(w[1])
+
+
+def _reject_edges(grad_edges):
+    if grad_edges:
+        raise NotImplementedError(
+            "grad_edges=True (Edge3D Sobel pre-filter, reference utils.py:130-183) is outside the fused path; "
+            "the reference itself raises at its default padding. Pass grad_edges=False.")
+
+
+def _affine_like(mode, moving, target, lr, epochs, weights_pair, params0, debug):
+    prob = TF.AffineProblem(moving, target, mode, params0, epochs)
+    prob.run(epochs, lr, weights_pair[0], weights_pair[1])
+    final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
+    final_warped = TF.warp_affine(final_theta, moving)
+    best_warped = TF.warp_affine(best_theta, moving)
+    if debug:
+        print('losses (first, best, last): %s' % (prob.losses[0, [0, -1]].tolist(),))
+    return prob, [final_warped, best_warped], [final_theta, best_theta]
+
+
+def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
+                    weights=[0.33, 0.33, 0.33], grad_edges=True):
+    """Affine registration by SGD on the 12 (6) entries of theta, identity start
+    (reference warpings.py:30-113).  The reference routes theta through a zero-initialised MLP
+    that is provably inert under momentum-free SGD; `per` only sizes that MLP and
+    is accepted and ignored.  Returns ([final_warped, best_warped], [final_theta, best_theta])."""
+    _reject_edges(grad_edges)
+    TF.require_cuda(moving, "moving")
+    nd = moving.dim() - 2
+    wp = similarity_weights(criterions, weights, "affine_register")
+    ident = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)
+    _, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug)
+    return warped, theta
+
+
+def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
+                   weights=[0.33, 0.33, 0.33], grad_edges=True, reg0=None):
+    """Rigid registration: SGD on (psi, theta, phi, a, b, c) / (theta, tx, ty)
+    (reference warpings.py:117-174, utils.py:287-330).  Initial parameters are drawn with
+    torch.rand on the data's device like the reference's Regressor; `reg0` (keyword-only
+    extension) injects them instead."""
+    _reject_edges(grad_edges)
+    TF.require_cuda(moving, "moving")
+    wp = similarity_weights(criterions, weights, "rigid_register")
+    npar = 6 if moving.dim() == 5 else 3
+    if reg0 is None:
+        reg0 = torch.rand(npar, device=moving.device)
+    if debug:
+        print(reg0)
+    _, warped, theta = _affine_like("rigid", moving, target, lr, epochs, wp, reg0, debug)
+    return warped, theta
+
+
+# --------------------------------------------------------------------------- #
+# flow
+# --------------------------------------------------------------------------- #
+def _split_criteria(criterions, weights):
+    """-> (w_mse, w_ncc, [(weight, module), ...] for terms the fused node does not cover)."""
+    w_mse = w_ncc = 0.0
+    other = []
+    for wt, crit in zip(weights, criterions):
+        if type(crit) is nn.MSELoss and crit.reduction == 'mean':
+            w_mse += float(wt)
+        elif isinstance(crit, NCCLoss):
+            w_ncc += float(wt) * float(crit.alpha) / 100.0
+        else:
+            other.append((wt, crit))
+    return w_mse, w_ncc, other
+
+
+class _FlowSimilarityFn(torch.autograd.Function):
+    """loss = w_mse*MSE(target, warp(moving, flow)) + w_ncc*100*(1-NCC(...)), fused with its
+    gradient w.r.t. flow (one statistics pass + one gradient pass over the volume)."""
+
+    @staticmethod
+    def forward(ctx, flow, moving, target, w_mse, w_ncc, want_warped):
+        loss, dflow, warped = TF.flow_loss_grad(moving, target, flow, w_mse, w_ncc, want_warped)
+        ctx.save_for_backward(dflow)
+        if warped is None:
+            warped = torch.empty(0, device=flow.device)
+        ctx.mark_non_differentiable(warped)
+        return loss.reshape(()), warped
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_warped):
+        (dflow,) = ctx.saved_tensors
+        return dflow * grad_loss, None, None, None, None, None
+
+
+class flow_register(nn.Module):
+    """Deformable registration: an Attention_UNet maps `moving` to a dense flow, optimised with SGD
+    on the network weights (reference warpings.py:178-242).  The U-Net stays PyTorch/cuDNN; the
+    warp, the MSE/NCC similarity and their backward down to the flow are one fused CUDA node.
+    Criteria other than nn.MSELoss / NCCLoss are honoured through the differentiable
+    SpatialTransformer (as the reference honours them in flow mode, torchregister.py:71-73)."""
+
+    def __init__(self, img_size, mode='bilinear', in_c=1, n=1,
+                 criterions=None, weights=[0.33, 0.33, 0.33], lr=1E-3, max_epochs=2000, stop_crit=1E-4):
+        super().__init__()
+        self.model = Attention_UNet(img_size, mode, in_c=in_c, n=n)
+        self.flow = None
+        self.warp = None
+        if criterions is None:
+            # reference default: [MSELoss, NCCLoss, NMILoss] (warpings.py:179)
+            if len(weights) >= 3 and weights[2] != 0:
+                raise NotImplementedError(
+                    "flow_register: the default criteria include the NMI/KDE term (weight[2]=%g), which is not "
+                    "part of the CUDA path yet (SURVEY.md §8f-1). Pass weights=[w_mse, w_ncc, 0.] or explicit "
+                    "criterions=[nn.MSELoss(), NCCLoss()]." % weights[2])
+            criterions = [nn.MSELoss(), NCCLoss()]
+            weights = list(weights)[:2]
+        self.criterions, self.weights = criterions, weights
+        self.lr, self.max_epochs, self.stop_crit = lr, max_epochs, stop_crit
+        self.optimizer = torch.optim.SGD(self.model.parameters(), lr)
+        self.losses = []
+
+    def forward(self, x, device):
+        y, self.flow = self.model(x, device)
+        return y
+
+    def optimize(self, moving, target, device, debug=True, grad_edges=False):
+        _reject_edges(grad_edges)
+        TF.require_cuda(moving, "moving")
+        w_mse, w_ncc, other = _split_criteria(self.criterions, self.weights)
+        self.losses = []
+        message = 'Reached max epochs'
+        self.train()
+        for eps in range(self.max_epochs):
+            self.optimizer.zero_grad()
+            flow = self.model.flow_field(moving, device)
+            self.flow = flow
+            if other:
+                y = self.model.warp(moving, flow)
+                error = sum(wt * crit(target, y) for wt, crit in other)
+                if w_mse or w_ncc:
+                    error = error + _FlowSimilarityFn.apply(flow, moving, target, w_mse, w_ncc, False)[0]
+            else:
+                error, _ = _FlowSimilarityFn.apply(flow, moving, target, w_mse, w_ncc, False)
+            error.backward()
+            self.optimizer.step()
+            self.warp = self.model.warp
+            self.losses.append(error.item())
+            if self.losses[-1] <= self.stop_crit:
+                message = 'Converged to %f' % self.stop_crit
+                break
+        if debug:
+            print('Optimization ended with status: %s' % message)
+
+    def deform(self, x):
+        """Warp `x` with the flow of the last forward pass (reference warpings.py:238-242)."""
+        return TF.warp_flow(x, self.flow.detach())
