@@ -1,0 +1,208 @@
+"""GPU (B200): the CUDA path, called through the C ABI (libtrb_b200.so via ctypes), against
+(a) the golden vectors recorded from the unmodified reference and (b) the CPU oracle on seeded
+inputs, plus size-independent properties at BASELINE.json's full sizes."""
+import numpy as np
+import pytest
+import torch
+
+from conftest import load_golden
+from test_oracle_golden import AFFINE_LIKE, LATTICE_RTOL, _loss_ok, _p0
+
+pytestmark = pytest.mark.gpu
+
+DEV = "cuda:0"
+
+
+def _tf():
+    import torchregister_b200.functional as TF
+    return TF
+
+
+def _run_problem(g, name):
+    TF = _tf()
+    mov, tgt = torch.from_numpy(g["moving"]).to(DEV), torch.from_numpy(g["target"]).to(DEV)
+    nd = mov.dim() - 2
+    w = g["weights"]
+    prob = TF.AffineProblem(mov, tgt, str(g["mode"]), _p0(g, nd).to(DEV), int(g["epochs"]))
+    prob.run(int(g["epochs"]), float(g["lr"]), float(w[0]), float(w[1]))
+    return prob, mov, nd
+
+
+@pytest.mark.parametrize("name", AFFINE_LIKE)
+def test_affine_like_vs_reference_golden(name):
+    TF = _tf()
+    g = load_golden(name)
+    prob, mov, nd = _run_problem(g, name)
+    losses = prob.losses[0].cpu().numpy()
+    rtol = LATTICE_RTOL if str(g["mode"]) == "affine" else 1e-4
+    ok, worst = _loss_ok(losses, g["losses"], g["losses_f64"], rtol)
+    assert ok, "per-epoch loss outside tolerance (worst ratio %.2f)\n%s\n%s" % (worst, losses, g["losses"])
+    ref_final = g["final_theta_f64"].reshape(nd, nd + 1)
+    ref_best = g["best_theta_f64"].reshape(nd, nd + 1)
+    tol = max(1e-4 * np.abs(ref_final).max(), 2 * np.abs(g["final_theta"].reshape(nd, nd + 1) - ref_final).max())
+    assert np.abs(prob.final_theta[0].cpu().numpy() - ref_final).max() <= tol
+    assert np.abs(prob.best_theta[0].cpu().numpy() - ref_best).max() <= tol
+    # warped output within 1e-5 absolute at the reference's own final theta
+    th = torch.from_numpy(g["final_theta"]).to(DEV)
+    warped = TF.warp_affine(th, mov).cpu().numpy()
+    assert np.abs(warped - g["final_warped"]).max() < 1e-5
+
+
+@pytest.mark.parametrize("name", ["flownode3d", "flownode2d", "flownode3d_mse"])
+def test_flow_node_vs_reference_golden(name):
+    TF = _tf()
+    g = load_golden(name)
+    mov, tgt, flow = (torch.from_numpy(g[k]).to(DEV) for k in ("moving", "target", "flow"))
+    w = g["weights"]
+    loss, dflow, warped = TF.flow_loss_grad(mov, tgt, flow, float(w[0]), float(w[1]), want_warped=True)
+    assert abs(loss.item() - float(g["loss_f64"])) <= 1e-4 * abs(float(g["loss_f64"]))
+    assert np.abs(warped.cpu().numpy() - g["warped"]).max() < 1e-5
+    scale = np.abs(g["dflow_f64"]).max()
+    # the reference's own fp32 run is this far from its fp64 run: we must not be further than 2x that or 1e-4
+    ref_gap = np.abs(g["dflow"] - g["dflow_f64"]).max()
+    assert np.abs(dflow.cpu().numpy() - g["dflow_f64"]).max() <= max(1e-4 * scale, 2 * ref_gap)
+    out = TF.warp_flow(mov, flow).cpu().numpy()
+    assert np.abs(out - g["warped"]).max() < 1e-5
+    vjp = TF.warp_flow_vjp(mov, flow, torch.from_numpy(g["cot"]).to(DEV)).cpu().numpy()
+    vgap = np.abs(g["vjp"] - g["vjp_f64"]).max()
+    assert np.abs(vjp - g["vjp_f64"]).max() <= max(1e-4 * np.abs(g["vjp_f64"]).max(), 2 * vgap)
+
+
+@pytest.mark.parametrize("name", ["api_rigid3d", "api_affine2d"])
+def test_register_api_vs_reference_golden(name):
+    import torchregister_b200 as tr
+    g = load_golden(name)
+    mode = str(g["mode"])
+    reg = tr.Register(mode=mode, device=DEV, weight=list(g["weights"]))
+    mov, tgt = torch.from_numpy(g["moving"]), torch.from_numpy(g["target"])
+    reg.optim(mov, tgt, lr=float(g["lr"]), max_epochs=int(g["epochs"]), reg0=torch.from_numpy(g["p0"]) if mode == "rigid" else None)
+    assert tuple(reg.theta.shape) == tuple(g["theta"].shape)
+    assert np.abs(reg.theta.cpu().numpy() - g["theta"]).max() <= 5e-5
+    out = reg(torch.from_numpy(g["call_in"])).cpu().numpy()
+    assert out.shape == g["call_out"].shape
+    # the multi-channel warp at OUR theta differs from the reference's by the theta difference only
+    out_ref_theta = tr.get_affine_warp(torch.from_numpy(g["theta"]).to(DEV), torch.from_numpy(g["call_in"]).to(DEV))
+    assert np.abs(out_ref_theta.cpu().numpy() - g["call_out"]).max() < 1e-5
+    assert np.abs(out - g["call_out"]).max() < 1e-4
+
+
+@pytest.mark.parametrize("shape,mode,weights", [((40, 36, 44), "rigid", (0.0, 1.0)), ((40, 36, 44), "affine", (0.5, 0.5)),
+                                                ((96, 80), "rigid", (1.0, 0.0)), ((33, 47, 65), "rigid", (0.3, 0.7))])
+def test_step_terms_vs_c_oracle(shape, mode, weights):
+    """One step at a generic (off-lattice) theta: loss and parameter update against the plain-C oracle."""
+    TF = _tf()
+    from oracle import c_oracle as co
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair(shape, "rigid")
+    nd = len(shape)
+    if mode == "rigid":
+        p0 = np.array([0.05, -0.03, 0.04, 0.1, -0.08, 0.05][: 6 if nd == 3 else 3], np.float32)
+    else:
+        p0 = (np.eye(nd, nd + 1) + 0.01 * np.random.default_rng(0).standard_normal((nd, nd + 1))).astype(np.float32).ravel()
+    lr = 1e-3
+    ref = co.affine_loop(mov.numpy(), tgt.numpy(), mode, p0, lr, 3, weights[0], weights[1])
+    ref64 = co.affine_loop(mov.double().numpy(), tgt.double().numpy(), mode, p0.astype(np.float64), lr, 3, weights[0], weights[1])
+    prob = TF.AffineProblem(mov.to(DEV), tgt.to(DEV), mode, torch.from_numpy(p0).to(DEV), 3)
+    prob.run(3, lr, weights[0], weights[1])
+    ok, worst = _loss_ok(prob.losses[0].cpu().numpy(), ref["losses"], ref64["losses"])
+    assert ok, worst
+    assert np.abs(prob.final_theta[0].cpu().numpy() - ref64["final_theta"]).max() <= 1e-4 * np.abs(ref64["final_theta"]).max()
+    dpar_ref = ref64["final_params"] - p0
+    dpar = prob.params[0].cpu().numpy().astype(np.float64) - p0
+    assert np.abs(dpar - dpar_ref).max() <= 2e-3 * np.abs(dpar_ref).max() + 1e-7   # the 3-step update itself
+
+
+def test_zero_padding_large_rotation():
+    """Reference-style torch.rand start (angles up to 1 rad): most samples leave the volume."""
+    TF = _tf()
+    from oracle import c_oracle as co
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((30, 34, 38), "rigid")
+    p0 = np.array([0.9, 0.7, 0.8, 0.6, 0.9, 0.3], np.float32)
+    ref64 = co.affine_loop(mov.double().numpy(), tgt.double().numpy(), "rigid", p0.astype(np.float64), 1e-4, 4, 0.5, 0.5)
+    ref32 = co.affine_loop(mov.numpy(), tgt.numpy(), "rigid", p0, 1e-4, 4, 0.5, 0.5)
+    prob = TF.AffineProblem(mov.to(DEV), tgt.to(DEV), "rigid", torch.from_numpy(p0).to(DEV), 4)
+    prob.run(4, 1e-4, 0.5, 0.5)
+    ok, worst = _loss_ok(prob.losses[0].cpu().numpy(), ref32["losses"], ref64["losses"])
+    assert ok, worst
+    th = prob.final_theta[0]
+    warped = TF.warp_affine(th, mov.to(DEV)).cpu().numpy()[0, 0]
+    assert np.abs(warped - co.warp_affine(mov.numpy(), th.cpu().numpy())).max() < 1e-5
+
+
+def test_batch_equals_singles_and_is_deterministic():
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    shape = (24, 40, 56)
+    pairs = [make_pair(shape, "rigid", seed=100 + i) for i in range(5)]
+    mov = torch.cat([p[0] for p in pairs]).to(DEV)
+    tgt = torch.cat([p[1] for p in pairs]).to(DEV)
+    p0 = torch.tensor([[0.02 * (i + 1), -0.01, 0.03, 0.05, -0.05, 0.02] for i in range(5)], device=DEV)
+    def run(m, t, p):
+        prob = TF.AffineProblem(m, t, "rigid", p, 6)
+        prob.run(6, 1e-3, 0.5, 0.5)
+        return prob.losses.clone(), prob.final_theta, prob.best_theta
+    a = run(mov, tgt, p0)
+    b = run(mov, tgt, p0)
+    for x, y in zip(a, b):
+        assert torch.equal(x, y), "not bit-reproducible"
+    for i in range(5):
+        s = run(mov[i:i + 1], tgt[i:i + 1], p0[i:i + 1])
+        assert torch.allclose(s[0][0], a[0][i], rtol=2e-6, atol=0)
+        assert torch.allclose(s[1][0], a[1][i], rtol=0, atol=2e-7)
+
+
+def test_slab_moments_sum_to_fused_epoch():
+    """z-slab form (moments -> sum over slabs -> apply) reproduces the fused epoch."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    shape = (36, 40, 48)
+    mov, tgt = (t.to(DEV) for t in make_pair(shape, "affine"))
+    p0 = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02], device=DEV)
+    fused = TF.AffineProblem(mov, tgt, "rigid", p0, 3)
+    fused.run(3, 1e-3, 0.5, 0.5)
+    sh = TF.AffineProblem(mov, tgt, "rigid", p0, 3)
+    for _ in range(3):
+        parts = [sh.moments(a, b) for a, b in ((0, 10), (10, 19), (19, 36))]
+        sh.apply(parts[0] + parts[1] + parts[2], 1e-3, 0.5, 0.5)
+    assert torch.allclose(sh.losses, fused.losses, rtol=1e-6)
+    assert torch.allclose(sh.final_theta, fused.final_theta, atol=1e-7)
+
+
+def test_get_affine_warp_autograd():
+    import torchregister_b200 as tr
+    from oracle import torch_port as tp
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((20, 24, 28), "rigid")
+    th0 = torch.tensor([[1.02, 0.03, -0.02, 0.05], [-0.04, 0.97, 0.01, -0.03], [0.02, -0.01, 1.01, 0.02]])
+    th = th0.clone().to(DEV).requires_grad_(True)
+    out = tr.get_affine_warp(th.view(1, 3, 4), mov.to(DEV))
+    ((out - tgt.to(DEV)) ** 2).mean().backward()
+    thr = th0.clone().double().requires_grad_(True)
+    ((tp.affine_warp(thr.view(1, 3, 4), mov.double()) - tgt.double()) ** 2).mean().backward()
+    assert np.abs(th.grad.cpu().numpy() - thr.grad.numpy()).max() <= 1e-4 * np.abs(thr.grad.numpy()).max()
+
+
+@pytest.mark.parametrize("shape", [(192, 192, 160)])
+def test_full_size_properties(shape):
+    """BASELINE.json config sizes: properties that need no oracle run.
+    (1) identity theta reproduces the volume; (2) moving == target gives loss ~ 0 and a ~zero update;
+    (3) the loss decreases from a perturbed start; (4) translation by exactly one voxel shifts the volume."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    mov, tgt = (t.to(DEV) for t in make_pair(shape, "rigid", device=DEV))
+    ident = torch.eye(3, 4, device=DEV)
+    assert (TF.warp_affine(ident, mov) - mov).abs().max().item() < 2e-5
+    prob = TF.AffineProblem(mov, mov.clone(), "affine", ident.reshape(1, -1), 2)
+    prob.run(2, 1e-5, 0.5, 0.5)
+    assert abs(prob.losses[0, 0].item()) < 1e-3
+    shift = ident.clone()
+    shift[0, 3] = 2.0 / shape[2]                      # +1 voxel along x
+    out = TF.warp_affine(shift, mov)
+    assert (out[..., :-1] - mov[..., 1:]).abs().max().item() < 2e-5
+    assert out[..., -1].abs().max().item() < 1e-6 + mov[..., -1].abs().max().item()
+    p0 = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02], device=DEV)
+    prob = TF.AffineProblem(mov, tgt, "rigid", p0, 30)
+    prob.run(30, 1e-3, 0.0, 1.0)
+    L = prob.losses[0].cpu().numpy()
+    assert np.all(np.isfinite(L)) and L[-1] < L[0]

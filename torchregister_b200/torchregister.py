@@ -43,10 +43,11 @@ class Register():
                 "torchregister_b200.Register runs on CUDA only (got device=%r); there is no CPU fallback. "
                 "Use Register(device='cuda')." % (self.device,))
 
-    def optim(self, moving, target, lr=1E-5, max_epochs=1000, n=32, per=0.1):
+    def optim(self, moving, target, lr=1E-5, max_epochs=1000, n=32, per=0.1, *, reg0=None):
         '''
         Optimisation loop (reference torchregister.py:46-106). Sets `self.theta` to the best
         (lowest-loss, pre-step) theta for rigid/affine, or to the last flow field for flow.
+        `reg0` (keyword-only extension): initial rigid parameters instead of the torch.rand draw.
         '''
         self._check_device()
         moving = moving.to(self.device)
@@ -66,14 +67,18 @@ class Register():
             self._flowreg = flowreg
         else:
             fn = affine_register if self.mode == 'affine' else rigid_register
+            probs = []
             kw = dict(lr=lr, epochs=max_epochs, per=per, device=self.device, debug=self.debug,
-                      grad_edges=self.grad_edges)
+                      grad_edges=self.grad_edges, _want_warped=False, _problem_out=probs)
             if both:
                 kw.update(criterions=self.criterion, weights=self.weight)
             elif self.weight is not None:
                 kw.update(weights=self.weight)
+            if reg0 is not None and self.mode == 'rigid':
+                kw.update(reg0=reg0)
             _, theta = fn(moving, target, **kw)
             self.theta = theta[-1]
+            self.losses = probs[0].losses[0]          # device tensor: per-epoch loss log (harmless superset)
 
     def __call__(self, moving):
         '''

@@ -72,8 +72,8 @@ def padNd(input_, target, device='cpu', mode='constant', value=0):
     pads = []
     for i in reversed(range(dims)):
         delta = target.shape[2 + i] - input_.shape[2 + i]
-        lo = ceil(delta / 2)
-        pads += [lo, delta - lo]
+        hi = ceil(delta / 2)             # the reference puts the larger half AFTER the data
+        pads += [delta - hi, hi]
     return F.pad(input_, tuple(pads), mode=mode, value=value).to(dtype=torch.float, device=device)
 
 

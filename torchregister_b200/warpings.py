@@ -75,19 +75,21 @@ def _reject_edges(grad_edges):
             "the reference itself raises at its default padding. Pass grad_edges=False.")
 
 
-def _affine_like(mode, moving, target, lr, epochs, weights_pair, params0, debug):
+def _affine_like(mode, moving, target, lr, epochs, weights_pair, params0, debug, want_warped=True):
     prob = TF.AffineProblem(moving, target, mode, params0, epochs)
     prob.run(epochs, lr, weights_pair[0], weights_pair[1])
     final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
-    final_warped = TF.warp_affine(final_theta, moving)
-    best_warped = TF.warp_affine(best_theta, moving)
+    # the reference keeps the warped volumes of the final and best epochs; we never write them during
+    # the loop and re-create them here only when the caller wants them (Register.optim does not)
+    final_warped = TF.warp_affine(final_theta, moving) if want_warped else None
+    best_warped = TF.warp_affine(best_theta, moving) if want_warped else None
     if debug:
         print('losses (first, best, last): %s' % (prob.losses[0, [0, -1]].tolist(),))
     return prob, [final_warped, best_warped], [final_theta, best_theta]
 
 
 def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
-                    weights=[0.33, 0.33, 0.33], grad_edges=True):
+                    weights=[0.33, 0.33, 0.33], grad_edges=True, *, _want_warped=True, _problem_out=None):
     """Affine registration by SGD on the 12 (6) entries of theta, identity start
     (reference warpings.py:30-113).  The reference routes theta through a zero-initialised MLP
     that is provably inert under momentum-free SGD; `per` only sizes that MLP and
@@ -97,12 +99,14 @@ def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu',
     nd = moving.dim() - 2
     wp = similarity_weights(criterions, weights, "affine_register")
     ident = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)
-    _, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug)
+    prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug, _want_warped)
+    if _problem_out is not None:
+        _problem_out.append(prob)
     return warped, theta
 
 
 def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
-                   weights=[0.33, 0.33, 0.33], grad_edges=True, reg0=None):
+                   weights=[0.33, 0.33, 0.33], grad_edges=True, *, reg0=None, _want_warped=True, _problem_out=None):
     """Rigid registration: SGD on (psi, theta, phi, a, b, c) / (theta, tx, ty)
     (reference warpings.py:117-174, utils.py:287-330).  Initial parameters are drawn with
     torch.rand on the data's device like the reference's Regressor; `reg0` (keyword-only
@@ -115,7 +119,9 @@ def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', 
         reg0 = torch.rand(npar, device=moving.device)
     if debug:
         print(reg0)
-    _, warped, theta = _affine_like("rigid", moving, target, lr, epochs, wp, reg0, debug)
+    prob, warped, theta = _affine_like("rigid", moving, target, lr, epochs, wp, reg0, debug, _want_warped)
+    if _problem_out is not None:
+        _problem_out.append(prob)
     return warped, theta
 
 
