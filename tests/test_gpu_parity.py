@@ -206,3 +206,78 @@ def test_full_size_properties(shape):
     prob.run(30, 1e-3, 0.0, 1.0)
     L = prob.losses[0].cpu().numpy()
     assert np.all(np.isfinite(L)) and L[-1] < L[0]
+
+
+# --------------------------------------------------------------------------------------------
+# TMA-staged 3-D kernel (affine_tma.cu) — needs W % 4 == 0, W >= 32, H >= 16
+# --------------------------------------------------------------------------------------------
+def _run(TF, mov, tgt, mode, p0, epochs, lr, w, path):
+    TF.set_kernel_path(path)
+    try:
+        prob = TF.AffineProblem(mov, tgt, mode, p0, epochs)
+        prob.run(epochs, lr, w[0], w[1])
+        torch.cuda.synchronize()
+        return prob.losses.clone(), prob.final_theta, prob.best_theta, prob.params
+    finally:
+        TF.set_kernel_path("auto")
+
+
+TMA_CASES = [
+    # shape, mode, params, weights  (non-multiples of the 32x16x8 tile, odd D, tiny D included)
+    ((40, 36, 44), "rigid", [0.05, -0.03, 0.04, 0.1, -0.08, 0.05], (0.0, 1.0)),
+    ((33, 47, 64), "rigid", [0.02, -0.01, 0.03, 0.05, -0.05, 0.02], (0.3, 0.7)),
+    ((8, 16, 32), "affine", None, (1.0, 0.0)),
+    ((19, 50, 100), "affine", None, (0.5, 0.5)),
+    ((64, 64, 64), "rigid", [0.9, 0.7, 0.8, 0.6, 0.9, 0.3], (0.5, 0.5)),      # large rotation: fallback tiles
+    ((48, 48, 48), "rigid", [0.12, -0.1, 0.15, 0.2, -0.1, 0.1], (0.5, 0.5)),   # ~8 deg: mixed fit / fallback
+]
+
+
+@pytest.mark.parametrize("shape,mode,params,weights", TMA_CASES)
+def test_tma_kernel_vs_direct_kernel_and_oracle(shape, mode, params, weights):
+    TF = _tf()
+    from oracle import c_oracle as co
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair(shape, "rigid")
+    if mode == "affine":
+        p0 = (np.eye(3, 4) + 0.01 * np.random.default_rng(1).standard_normal((3, 4))).astype(np.float32).ravel()
+    else:
+        p0 = np.asarray(params, np.float32)
+    m, t, p = mov.to(DEV), tgt.to(DEV), torch.from_numpy(p0).to(DEV)
+    a = _run(TF, m, t, mode, p, 4, 1e-3, weights, "auto")
+    d = _run(TF, m, t, mode, p, 4, 1e-3, weights, "direct")
+    ref64 = co.affine_loop(mov.double().numpy(), tgt.double().numpy(), mode, p0.astype(np.float64), 1e-3, 4, weights[0], weights[1])
+    ref32 = co.affine_loop(mov.numpy(), tgt.numpy(), mode, p0, 1e-3, 4, weights[0], weights[1])
+    for got, name in ((a, "tma"), (d, "direct")):
+        ok, worst = _loss_ok(got[0][0].cpu().numpy(), ref32["losses"], ref64["losses"])
+        assert ok, "%s: loss ratio %.2f: %s vs %s" % (name, worst, got[0][0].cpu().numpy(), ref64["losses"])
+        assert np.abs(got[1][0].cpu().numpy() - ref64["final_theta"]).max() <= 1e-4 * np.abs(ref64["final_theta"]).max(), name
+        dpar_ref = ref64["final_params"] - p0
+        dpar = got[3][0].cpu().numpy().astype(np.float64) - p0
+        assert np.abs(dpar - dpar_ref).max() <= 2e-3 * np.abs(dpar_ref).max() + 1e-7, name
+    assert torch.allclose(a[0], d[0], rtol=1e-4)
+
+
+def test_tma_kernel_batch_and_slabs():
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    shape = (24, 48, 64)
+    pairs = [make_pair(shape, "rigid", seed=200 + i) for i in range(11)]
+    mov = torch.cat([p[0] for p in pairs]).to(DEV)
+    tgt = torch.cat([p[1] for p in pairs]).to(DEV)
+    p0 = torch.tensor([[0.01 * (i + 1), -0.01, 0.03, 0.05, -0.05, 0.02] for i in range(11)], device=DEV)
+    a = _run(TF, mov, tgt, "rigid", p0, 5, 1e-3, (0.5, 0.5), "auto")
+    b = _run(TF, mov, tgt, "rigid", p0, 5, 1e-3, (0.5, 0.5), "auto")
+    d = _run(TF, mov, tgt, "rigid", p0, 5, 1e-3, (0.5, 0.5), "direct")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]), "TMA path not bit-reproducible"
+    assert torch.allclose(a[0], d[0], rtol=1e-4)
+    assert torch.allclose(a[1], d[1], atol=2e-6)
+    # z-slab form through the TMA kernel
+    fused = TF.AffineProblem(mov[:1], tgt[:1], "rigid", p0[:1], 3)
+    fused.run(3, 1e-3, 0.5, 0.5)
+    sh = TF.AffineProblem(mov[:1], tgt[:1], "rigid", p0[:1], 3)
+    for _ in range(3):
+        parts = [sh.moments(lo, hi) for lo, hi in ((0, 7), (7, 16), (16, 24))]
+        sh.apply(parts[0] + parts[1] + parts[2], 1e-3, 0.5, 0.5)
+    assert torch.allclose(sh.losses, fused.losses, rtol=1e-5)
+    assert torch.allclose(sh.final_theta, fused.final_theta, atol=1e-6)

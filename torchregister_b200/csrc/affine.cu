@@ -15,148 +15,10 @@
 // near-identity transforms.  Algorithmic traffic: 8 B per voxel-warp (moving 4 +
 // target 4), everything else is O(1) per pair.
 #include "common.cuh"
+#include "affine_shared.cuh"
 #include <math.h>
 
 namespace trb {
-
-struct AffineParams {
-    const float *moving, *target;
-    long long pair_stride;
-    int D, H, W;
-    int s_begin, s_end;          // slab of output slices (z for 3-D, y for 2-D)
-    const float *xb, *yb, *zb;   // base coordinates per axis
-    float *state;                // [n_pairs][TRB_STATE_FLOATS]
-    double *partials;            // [n_pairs][gridDim.x][TRB_MOMENTS]
-    unsigned *tickets;           // [n_pairs]
-    double *moments_out;         // unfused: [n_pairs][TRB_MOMENTS]
-    float *loss_log;
-    int log_stride, epoch;
-    float w_mse, w_ncc, lr;
-    int mode, optimiser;
-    float beta1, beta2, adam_eps;
-};
-
-// ---- Theta.forward (utils.py:287-310), fp32 like the reference ------------------
-template <int NDIM>
-__device__ void rigid_theta(const float *p, float *th)
-{
-    if (NDIM == 3) {
-        float sps, cps, sth, cth, sph, cph;
-        sincosf(p[0], &sps, &cps);
-        sincosf(p[1], &sth, &cth);
-        sincosf(p[2], &sph, &cph);
-        th[0] = cps * cth;  th[1] = sph * sps * cth - cph * sth;  th[2] = cph * sps * cth + sph * sth;
-        th[3] = 0.25f * tanhf(p[3]);
-        th[4] = cps * sth;  th[5] = sph * sps * sth + cph * cth;  th[6] = cph * sps * sth - sph * cth;
-        th[7] = 0.25f * tanhf(p[4]);
-        th[8] = -sps;       th[9] = sph * cps;                     th[10] = cph * cps;
-        th[11] = 0.25f * tanhf(p[5]);
-    } else {
-        float s, c;
-        sincosf(p[0], &s, &c);
-        th[0] = c; th[1] = -s; th[2] = p[1];
-        th[3] = s; th[4] = c;  th[5] = p[2];
-    }
-}
-
-// Jacobian-transpose product d theta -> d params of the map above.
-template <int NDIM>
-__device__ void rigid_chain(const float *p, const double *g, double *dp)
-{
-    if (NDIM == 3) {
-        double sps, cps, sth, cth, sph, cph;
-        sincos((double)p[0], &sps, &cps);
-        sincos((double)p[1], &sth, &cth);
-        sincos((double)p[2], &sph, &cph);
-        dp[0] = g[0] * (-sps * cth) + g[1] * (sph * cps * cth) + g[2] * (cph * cps * cth)
-              + g[4] * (-sps * sth) + g[5] * (sph * cps * sth) + g[6] * (cph * cps * sth)
-              - g[8] * cps - g[9] * (sph * sps) - g[10] * (cph * sps);
-        dp[1] = -g[0] * (cps * sth) - g[1] * (sph * sps * sth + cph * cth) + g[2] * (sph * cth - cph * sps * sth)
-              + g[4] * (cps * cth) + g[5] * (sph * sps * cth - cph * sth) + g[6] * (cph * sps * cth + sph * sth);
-        dp[2] = g[1] * (cph * sps * cth + sph * sth) + g[2] * (cph * sth - sph * sps * cth)
-              + g[5] * (cph * sps * sth - sph * cth) - g[6] * (sph * sps * sth + cph * cth)
-              + g[9] * (cph * cps) - g[10] * (sph * cps);
-#pragma unroll
-        for (int k = 0; k < 3; ++k) {
-            double t = tanh((double)p[3 + k]);
-            dp[3 + k] = g[3 + 4 * k] * 0.25 * (1.0 - t * t);
-        }
-    } else {
-        double s, c;
-        sincos((double)p[0], &s, &c);
-        dp[0] = -g[0] * s - g[1] * c + g[3] * c - g[4] * s;
-        dp[1] = g[2];
-        dp[2] = g[5];
-    }
-}
-
-// ---- epilogue: moments -> loss, d theta, chain, optimiser step, bookkeeping ---------
-// Runs in ONE thread per pair (O(100) flops).  M holds the TRB_MOMENTS sums with the
-// UN-scaled interpolant derivative; the grid_sample un-normalisation factor S_r/2 is
-// applied here.
-template <int NDIM>
-__device__ void affine_epilogue(const double *M, const AffineParams &p, int pair)
-{
-    constexpr int NC = NDIM + 1, NT = NDIM * NC;
-    float *st = p.state + (size_t)pair * TRB_STATE_FLOATS;
-    const double n = (double)(NDIM == 3 ? p.D : 1) * (double)p.H * (double)p.W;
-    const LossCoef lc = loss_coefficients(n, M[0], M[1], M[2], M[3], M[4], (double)p.w_mse, (double)p.w_ncc);
-    const double scale[3] = {0.5 * p.W, 0.5 * p.H, 0.5 * p.D};
-    double dth[12];
-#pragma unroll
-    for (int r = 0; r < NDIM; ++r)
-#pragma unroll
-        for (int c = 0; c < NC; ++c) {
-            const int i = r * NC + c;
-            dth[i] = (lc.cw * M[29 + i] + lc.ct * M[17 + i] + lc.c0 * M[5 + i]) * scale[r];
-        }
-    const float loss = (float)lc.loss;
-    // best tracking on the pre-step theta (warpings.py:85-93,151-159: strictly lower)
-    if (p.epoch == 0 || loss < st[TRB_STATE_BEST_LOSS]) {
-        st[TRB_STATE_BEST_LOSS] = loss;
-#pragma unroll
-        for (int i = 0; i < NT; ++i) st[TRB_STATE_BEST_THETA + i] = st[TRB_STATE_THETA + i];
-    }
-    st[TRB_STATE_LAST_LOSS] = loss;
-    if (p.loss_log) p.loss_log[(size_t)pair * p.log_stride + p.epoch] = loss;
-
-    double dp[12];
-    int np;
-    if (p.mode == TRB_MODE_RIGID) {
-        rigid_chain<NDIM>(st + TRB_STATE_PARAMS, dth, dp);
-        np = NDIM == 3 ? 6 : 3;
-    } else {
-#pragma unroll
-        for (int i = 0; i < NT; ++i) dp[i] = dth[i];
-        np = NT;
-    }
-    for (int i = 0; i < np; ++i) {
-        const float g = (float)dp[i];
-        float v = st[TRB_STATE_PARAMS + i];
-        if (p.optimiser == TRB_OPT_SGD) {
-            v = v - p.lr * g;                      // torch.optim.SGD, no momentum / decay
-        } else {                                   // torch.optim.Adam semantics (extension)
-            const float t = (float)(p.epoch + 1);
-            float m = st[TRB_STATE_ADAM_M + i], s = st[TRB_STATE_ADAM_V + i];
-            m = p.beta1 * m + (1.f - p.beta1) * g;
-            s = p.beta2 * s + (1.f - p.beta2) * g * g;
-            st[TRB_STATE_ADAM_M + i] = m;
-            st[TRB_STATE_ADAM_V + i] = s;
-            const float bc1 = 1.f - powf(p.beta1, t), bc2 = 1.f - powf(p.beta2, t);
-            v = v - (p.lr / bc1) * (m / (sqrtf(s) / sqrtf(bc2) + p.adam_eps));
-        }
-        st[TRB_STATE_PARAMS + i] = v;
-    }
-    if (p.mode == TRB_MODE_RIGID) {
-        float th[12];
-        rigid_theta<NDIM>(st + TRB_STATE_PARAMS, th);
-#pragma unroll
-        for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = th[i];
-    } else {
-#pragma unroll
-        for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = st[TRB_STATE_PARAMS + i];
-    }
-}
 
 // ---- the fused pass ------------------------------------------------------------------
 template <int NDIM, bool FUSED>
@@ -306,10 +168,7 @@ __global__ void __launch_bounds__(kThreads, 2) affine_moments_kernel(const Affin
             }
     }
 
-    // ---- block reduction of the TRB_MOMENTS per-thread sums -------------------------------
-    __shared__ float red[kWarps][TRB_MOMENTS + 1];
-    __shared__ double fin[4][TRB_MOMENTS + 1];
-    __shared__ bool is_last;
+    // ---- CTA reduction + last-CTA epilogue ---------------------------------------------------
     float acc[TRB_MOMENTS];
     acc[0] = s0; acc[1] = s1; acc[2] = s2; acc[3] = s3; acc[4] = s4;
 #pragma unroll
@@ -324,51 +183,7 @@ __global__ void __launch_bounds__(kThreads, 2) affine_moments_kernel(const Affin
             if (NDIM == 3) acc[b + 2] = Tz[k][r];
             acc[b + NDIM] = T1[k][r];
         }
-#pragma unroll
-    for (int i = 0; i < TRB_MOMENTS; ++i) {
-        const float v = warp_sum(acc[i]);
-        if (lane == 0) red[warp][i] = v;
-    }
-    __syncthreads();
-    double *mypart = p.partials + ((size_t)pair * gridDim.x + blockIdx.x) * TRB_MOMENTS;
-    if (threadIdx.x < TRB_MOMENTS) {
-        double s = 0.0;
-#pragma unroll
-        for (int w = 0; w < kWarps; ++w) s += (double)red[w][threadIdx.x];
-        __stcg(mypart + threadIdx.x, s);
-    }
-    __threadfence();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        const unsigned t = atomicAdd(p.tickets + pair, 1u);
-        is_last = (t == gridDim.x - 1);
-    }
-    __syncthreads();
-    if (!is_last) return;
-    __threadfence();
-    // last block of this pair: fixed-order (deterministic) fp64 reduction over blocks
-    {
-        const int v = threadIdx.x & 63, slice = threadIdx.x >> 6;
-        if (v < TRB_MOMENTS) {
-            const double *src = p.partials + (size_t)pair * gridDim.x * TRB_MOMENTS + v;
-            double a = 0.0;
-            for (int b = slice; b < (int)gridDim.x; b += 4) a += __ldcg(src + (size_t)b * TRB_MOMENTS);
-            fin[slice][v] = a;
-        }
-    }
-    __syncthreads();
-    if (threadIdx.x < TRB_MOMENTS)
-        fin[0][threadIdx.x] = (fin[0][threadIdx.x] + fin[1][threadIdx.x]) + (fin[2][threadIdx.x] + fin[3][threadIdx.x]);
-    __syncthreads();
-    if (FUSED) {
-        if (threadIdx.x == 0) {
-            affine_epilogue<NDIM>(fin[0], p, pair);
-            p.tickets[pair] = 0u;
-        }
-    } else {
-        if (threadIdx.x < TRB_MOMENTS) p.moments_out[(size_t)pair * TRB_MOMENTS + threadIdx.x] = fin[0][threadIdx.x];
-        if (threadIdx.x == 0) p.tickets[pair] = 0u;
-    }
+    reduce_and_finish<NDIM, FUSED, kWarps>(acc, p, pair, blockIdx.x, gridDim.x, 0, gridDim.x, 0, threadIdx.x);
 }
 
 template <int NDIM>
@@ -475,6 +290,7 @@ __global__ void vjp_extract_kernel(const double *moments, double *dtheta, int nd
 
 // ---- host side ---------------------------------------------------------------------------
 static int g_sm_count = 0;
+static bool g_force_direct = false;   // test hook: trb_set_kernel_path(1) pins the non-TMA kernel
 static int sm_count()
 {
     if (g_sm_count == 0) {
@@ -485,7 +301,7 @@ static int sm_count()
     return g_sm_count;
 }
 
-constexpr int kMaxBlocksPerPair = 1024;
+constexpr int kMaxBlocksPerPair = kMaxSlots;
 
 static size_t affine_ws_bytes(int n_pairs)
 {
@@ -509,6 +325,13 @@ static int blocks_per_pair(int rows, int n_pairs)
 using namespace trb;
 
 extern "C" int trb_sm_count(void) { return sm_count(); }
+
+extern "C" int trb_set_kernel_path(int path)
+{
+    if (path != 0 && path != 1) { set_error("path must be 0 (auto) or 1 (direct)"); return TRB_ERR_ARG; }
+    g_force_direct = (path == 1);
+    return TRB_OK;
+}
 
 extern "C" size_t trb_affine_workspace_bytes(int n_pairs) { return affine_ws_bytes(n_pairs); }
 
@@ -568,6 +391,8 @@ extern "C" int trb_affine_optim(int ndim, int mode, const float *moving_dev, con
     p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs))
+        return launch_affine3d_tma(p, n_pairs, true, epoch0, n_epochs, s);
     const int rows = ndim == 3 ? D * H : H;
     const dim3 grid(blocks_per_pair(rows, n_pairs), n_pairs);
     for (int e = 0; e < n_epochs; ++e) {
@@ -595,6 +420,8 @@ extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float
     p.state = const_cast<float *>(state_dev);
     p.moments_out = moments_dev;
     cudaStream_t s = (cudaStream_t)stream;
+    if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs))
+        return launch_affine3d_tma(p, n_pairs, false, 0, 1, s);
     const int rows = (s_end - s_begin) * (ndim == 3 ? H : 1);
     const dim3 grid(blocks_per_pair(rows, n_pairs), n_pairs);
     if (ndim == 3) affine_moments_kernel<3, false><<<grid, kThreads, 0, s>>>(p);
