@@ -165,8 +165,8 @@ def test_slab_moments_sum_to_fused_epoch():
     for _ in range(3):
         parts = [sh.moments(a, b) for a, b in ((0, 10), (10, 19), (19, 36))]
         sh.apply(parts[0] + parts[1] + parts[2], 1e-3, 0.5, 0.5)
-    assert torch.allclose(sh.losses, fused.losses, rtol=1e-6)
-    assert torch.allclose(sh.final_theta, fused.final_theta, atol=1e-7)
+    assert torch.allclose(sh.losses, fused.losses, rtol=1e-5)      # other fp32 summation order
+    assert torch.allclose(sh.final_theta, fused.final_theta, atol=1e-6)
 
 
 def test_get_affine_warp_autograd():

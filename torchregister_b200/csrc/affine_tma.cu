@@ -249,7 +249,9 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                         const float hi = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.02f;
                         // keep the float->int conversions defined for wild thetas
                         const float loc = fminf(fmaxf(lo, -1.0e6f), 1.0e6f), hic = fminf(fmaxf(hi, -1.0e6f), 1.0e6f);
-                        o[r] = (int)floorf(loc);
+                        // TMA needs the box start 16-byte aligned along x (tools/tma_probe.cu: an unaligned
+                        // innermost coordinate raises an illegal-instruction fault); y and z are free
+                        o[r] = r == 0 ? 4 * (int)floorf(loc * 0.25f) : (int)floorf(loc);
                         fits = fits && ((int)floorf(hic) + 1 <= o[r] + B[r] - 1);
                     }
                     // the fp32 index trick needs |x + BX*y + BX*BY*z| < 2^22
