@@ -47,7 +47,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OUT_DIR, exist_ok=True)
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc wrapper without OpenMP specs; nvcc only needs g++
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-ccbin", shutil.which("g++") or "g++", "-o", LIB_PATH] + \
+    extra = ["-DTRB_TIMING"] if os.environ.get("TRB_TIMING") else []
+    cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-ccbin", shutil.which("g++") or "g++", "-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
     log = res.stdout + res.stderr

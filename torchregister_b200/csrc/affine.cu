@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 2) affine_moments_kernel(const Affin
             if (NDIM == 3) acc[b + 2] = Tz[k][r];
             acc[b + NDIM] = T1[k][r];
         }
-    reduce_and_finish<NDIM, FUSED, kWarps>(acc, p, pair, blockIdx.x, gridDim.x, 0, gridDim.x, 0, threadIdx.x);
+    reduce_and_finish<NDIM, FUSED, kWarps>(acc, p, pair, blockIdx.x, gridDim.x, 0, gridDim.x, threadIdx.x);
 }
 
 template <int NDIM>
@@ -305,7 +305,7 @@ constexpr int kMaxBlocksPerPair = kMaxSlots;
 
 static size_t affine_ws_bytes(int n_pairs)
 {
-    return (size_t)n_pairs * kMaxBlocksPerPair * TRB_MOMENTS * sizeof(double) + (size_t)n_pairs * 64 /*tickets, padded*/;
+    return (size_t)n_pairs * kMaxBlocksPerPair * TRB_MOMENTS * sizeof(double) + (size_t)n_pairs * kTicketStride * sizeof(unsigned);
 }
 
 static int blocks_per_pair(int rows, int n_pairs)

@@ -7,6 +7,7 @@
 
 namespace trb {
 
+constexpr int kTicketStride = 128;  // unsigned counters per pair in the workspace (direct kernel uses [127])
 constexpr int kMaxSlots = 1024;      // partial-sum slots per pair in the workspace (>= CTAs contributing to a pair)
 
 struct AffineParams;
@@ -93,6 +94,15 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
 {
     constexpr int NC = NDIM + 1, NT = NDIM * NC;
     float *st = p.state + (size_t)pair * TRB_STATE_FLOATS;
+    // read everything first (independent loads, one round trip), compute, then write
+    float par[12], th_cur[12], am[12], av[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { par[i] = __ldcg(st + TRB_STATE_PARAMS + i); th_cur[i] = __ldcg(st + TRB_STATE_THETA + i); }
+    const float best_prev = __ldcg(st + TRB_STATE_BEST_LOSS);
+    if (p.optimiser != TRB_OPT_SGD) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { am[i] = __ldcg(st + TRB_STATE_ADAM_M + i); av[i] = __ldcg(st + TRB_STATE_ADAM_V + i); }
+    }
     const double n = (double)(NDIM == 3 ? p.D : 1) * (double)p.H * (double)p.W;
     const LossCoef lc = loss_coefficients(n, M[0], M[1], M[2], M[3], M[4], (double)p.w_mse, (double)p.w_ncc);
     const double scale[3] = {0.5 * p.W, 0.5 * p.H, 0.5 * p.D};
@@ -106,10 +116,10 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
         }
     const float loss = (float)lc.loss;
     // best tracking on the pre-step theta (warpings.py:85-93,151-159: strictly lower)
-    if (p.epoch == 0 || loss < st[TRB_STATE_BEST_LOSS]) {
+    if (p.epoch == 0 || loss < best_prev) {
         st[TRB_STATE_BEST_LOSS] = loss;
 #pragma unroll
-        for (int i = 0; i < NT; ++i) st[TRB_STATE_BEST_THETA + i] = st[TRB_STATE_THETA + i];
+        for (int i = 0; i < NT; ++i) st[TRB_STATE_BEST_THETA + i] = th_cur[i];
     }
     st[TRB_STATE_LAST_LOSS] = loss;
     if (p.loss_log) p.loss_log[(size_t)pair * p.log_stride + p.epoch] = loss;
@@ -117,116 +127,116 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
     double dp[12];
     int np;
     if (p.mode == TRB_MODE_RIGID) {
-        rigid_chain<NDIM>(st + TRB_STATE_PARAMS, dth, dp);
+        rigid_chain<NDIM>(par, dth, dp);
         np = NDIM == 3 ? 6 : 3;
     } else {
 #pragma unroll
         for (int i = 0; i < NT; ++i) dp[i] = dth[i];
         np = NT;
     }
-    for (int i = 0; i < np; ++i) {
-        const float g = (float)dp[i];
-        float v = st[TRB_STATE_PARAMS + i];
-        if (p.optimiser == TRB_OPT_SGD) {
-            v = v - p.lr * g;                      // torch.optim.SGD, no momentum / decay
-        } else {                                   // torch.optim.Adam semantics (extension)
-            const float t = (float)(p.epoch + 1);
-            float m = st[TRB_STATE_ADAM_M + i], s = st[TRB_STATE_ADAM_V + i];
-            m = p.beta1 * m + (1.f - p.beta1) * g;
-            s = p.beta2 * s + (1.f - p.beta2) * g * g;
-            st[TRB_STATE_ADAM_M + i] = m;
-            st[TRB_STATE_ADAM_V + i] = s;
-            const float bc1 = 1.f - powf(p.beta1, t), bc2 = 1.f - powf(p.beta2, t);
-            v = v - (p.lr / bc1) * (m / (sqrtf(s) / sqrtf(bc2) + p.adam_eps));
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        if (i < np) {
+            const float g = (float)dp[i];
+            float v = par[i];
+            if (p.optimiser == TRB_OPT_SGD) {
+                v = v - p.lr * g;                      // torch.optim.SGD, no momentum / decay
+            } else {                                   // torch.optim.Adam semantics (extension)
+                const float t = (float)(p.epoch + 1);
+                float m = am[i], s = av[i];
+                m = p.beta1 * m + (1.f - p.beta1) * g;
+                s = p.beta2 * s + (1.f - p.beta2) * g * g;
+                st[TRB_STATE_ADAM_M + i] = m;
+                st[TRB_STATE_ADAM_V + i] = s;
+                const float bc1 = 1.f - powf(p.beta1, t), bc2 = 1.f - powf(p.beta2, t);
+                v = v - (p.lr / bc1) * (m / (sqrtf(s) / sqrtf(bc2) + p.adam_eps));
+            }
+            par[i] = v;
+            st[TRB_STATE_PARAMS + i] = v;
         }
-        st[TRB_STATE_PARAMS + i] = v;
     }
     if (p.mode == TRB_MODE_RIGID) {
         float th[12];
-        rigid_theta<NDIM>(st + TRB_STATE_PARAMS, th);
+        rigid_theta<NDIM>(par, th);
 #pragma unroll
         for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = th[i];
     } else {
 #pragma unroll
-        for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = st[TRB_STATE_PARAMS + i];
+        for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = par[i];
     }
 }
 
-
-// ---- CTA reduction of the TRB_MOMENTS per-thread sums, grid-level finish -----------------------
-// Every participating thread passes its 41 partial sums.  The CTA total is written (fp64) to
-// partials[pair][slot]; the last CTA to arrive for this pair (atomic ticket) adds up the `count`
-// contributing slots first_slot, first_slot+1, ... (mod n_slots) in that fixed order — so the result
-// is bit-reproducible — and runs the epilogue (FUSED) or publishes the moments (sharded form).
-// bar_id 0: the whole CTA participates (__syncthreads); otherwise a named barrier over NWARPS warps.
-template <int NWARPS>
-__device__ __forceinline__ void cta_bar(int bar_id)
-{
-    if (bar_id == 0) __syncthreads();
-    else asm volatile("bar.sync %0, %1;" ::"r"(bar_id), "r"(NWARPS * 32) : "memory");
-}
-
+// second half of the CTA reduction: `red` holds one row of TRB_MOMENTS warp totals per warp
+// (row stride `ld` floats).  Must be called by all NWARPS*32 threads of the CTA after a barrier.
 template <int NDIM, bool FUSED, int NWARPS>
-__device__ void reduce_and_finish(float (&acc)[TRB_MOMENTS], const AffineParams &p, int pair, int slot, int n_slots,
-                                  int first_slot, int count, int bar_id, int tid)
+__device__ void finish_from_warp_sums(const float *red, int ld, const AffineParams &p, int pair, int slot, int n_slots,
+                                      int first_slot, int count, int tid)
 {
     constexpr int kSlices = NWARPS * 32 / 64;
-    __shared__ float red[NWARPS][TRB_MOMENTS + 1];
     __shared__ double fin[kSlices][TRB_MOMENTS + 1];
     __shared__ int is_last;
-    const int lane = tid & 31, warp = tid >> 5;
-    cta_bar<NWARPS>(bar_id);               // previous use of the scratch is over
-#pragma unroll
-    for (int i = 0; i < TRB_MOMENTS; ++i) {
-        const float v = warp_sum(acc[i]);
-        if (lane == 0) red[warp][i] = v;
-    }
-    cta_bar<NWARPS>(bar_id);
     if (tid < TRB_MOMENTS) {
         double s = 0.0;
 #pragma unroll
-        for (int w = 0; w < NWARPS; ++w) s += (double)red[w][tid];
+        for (int w = 0; w < NWARPS; ++w) s += (double)red[w * ld + tid];
         __stcg(p.partials + ((size_t)pair * n_slots + slot) * TRB_MOMENTS + tid, s);
     }
     __threadfence();
-    cta_bar<NWARPS>(bar_id);
+    __syncthreads();
     if (tid == 0) {
-        const unsigned t = atomicAdd(p.tickets + pair, 1u);
+        const unsigned t = atomicAdd(p.tickets + (size_t)pair * kTicketStride + 127, 1u);
         is_last = (t == (unsigned)count - 1u) ? 1 : 0;
     }
-    cta_bar<NWARPS>(bar_id);
+    __syncthreads();
     if (!is_last) return;
     __threadfence();
     {
         const int v = tid & 63, slice = tid >> 6;
         if (v < TRB_MOMENTS) {
-            const double *src = p.partials + (size_t)pair * n_slots * TRB_MOMENTS + v;
+            double *src = p.partials + (size_t)pair * n_slots * TRB_MOMENTS + v;
             double a = 0.0;
             for (int j = slice; j < count; j += kSlices) {
                 int sl = first_slot + j;
                 if (sl >= n_slots) sl -= n_slots;
                 a += __ldcg(src + (size_t)sl * TRB_MOMENTS);
+                __stcg(src + (size_t)sl * TRB_MOMENTS, 0.0);      // leave the workspace zeroed (the TMA kernel relies on it)
             }
             fin[slice][v] = a;
         }
     }
-    cta_bar<NWARPS>(bar_id);
+    __syncthreads();
     if (tid < TRB_MOMENTS) {
         double a = 0.0;
 #pragma unroll
         for (int sidx = 0; sidx < kSlices; ++sidx) a += fin[sidx][tid];
         fin[0][tid] = a;
     }
-    cta_bar<NWARPS>(bar_id);
+    __syncthreads();
     if (FUSED) {
         if (tid == 0) {
             affine_epilogue<NDIM>(fin[0], p, pair);
-            p.tickets[pair] = 0u;
+            p.tickets[(size_t)pair * kTicketStride + 127] = 0u;
         }
     } else {
         if (tid < TRB_MOMENTS) p.moments_out[(size_t)pair * TRB_MOMENTS + tid] = fin[0][tid];
-        if (tid == 0) p.tickets[pair] = 0u;
+        if (tid == 0) p.tickets[(size_t)pair * kTicketStride + 127] = 0u;
     }
+}
+
+template <int NDIM, bool FUSED, int NWARPS>
+__device__ void reduce_and_finish(float (&acc)[TRB_MOMENTS], const AffineParams &p, int pair, int slot, int n_slots,
+                                  int first_slot, int count, int tid)
+{
+    __shared__ float red[NWARPS][TRB_MOMENTS + 1];
+    const int lane = tid & 31, warp = tid >> 5;
+    __syncthreads();               // previous use of the scratch is over
+#pragma unroll
+    for (int i = 0; i < TRB_MOMENTS; ++i) {
+        const float v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    finish_from_warp_sums<NDIM, FUSED, NWARPS>(&red[0][0], TRB_MOMENTS + 1, p, pair, slot, n_slots, first_slot, count, tid);
 }
 
 }  // namespace trb

@@ -3,13 +3,15 @@
 // Same contract as affine_moments_kernel<3,*> in affine.cu (reference call sites listed there),
 // re-organised around what bounds it on B200: 8 B/voxel of HBM traffic against ~60 fp32
 // pipe operations per voxel.  Design:
-//   * persistent CTAs (one per SM): 16 consumer warps + 1 producer warp;
+//   * persistent CTAs (one per SM) of 16 warps; there is no dedicated producer warp: the LAST warp
+//     to finish a tile (shared-memory arrival counter) computes and issues the TMA loads that
+//     refill that stage, so no warp ever waits for a slot to drain;
 //   * work unit = a z-run of ZC output tiles of 32x16x8 voxels; lane <-> x, warp <-> y, so a
 //     thread keeps its x and y base coordinates for the whole unit and steps along z;
 //   * the producer maps each output tile through theta, takes the bounding box of its source
 //     footprint and, if it fits the fixed TMA box (BX x BY x BZ incl. halo), fetches that box of the
 //     moving volume and the target tile with two cp.async.bulk.tensor loads into a 4-stage smem
-//     ring (mbarrier full/empty).  TMA's out-of-bounds zero fill IS grid_sample's zeros padding.
+//     ring (mbarrier "full" per stage).  TMA's out-of-bounds zero fill IS grid_sample's zeros padding.
 //     Tiles whose footprint does not fit (large rotations) are gathered from global memory with
 //     explicit bounds checks instead — same arithmetic, slower, always correct;
 //   * consumers process two voxels (z, z+1) per thread with packed f32x2 arithmetic
@@ -28,9 +30,9 @@ namespace trb {
 
 constexpr int TX = 32, TY = 16, TZ = 8;          // output tile (voxels)
 constexpr int kConsumerWarps = TY;               // warp <-> y row of the tile
-constexpr int kTmaThreads = (kConsumerWarps + 1) * 32;
+constexpr int kTmaThreads = kConsumerWarps * 32;
 constexpr float kMagic = 12582912.f;             // 1.5 * 2^23
-constexpr int kMagicBits = 0x4B400000;
+constexpr float kIdxScale = 1.f / 4194304.f;     // 2^-22
 
 // ---- PTX helpers ---------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -68,13 +70,23 @@ __device__ __forceinline__ void tma_load_4d(void *dst, const CUtensorMap *map, u
 __device__ __forceinline__ float2 f2(float a) { return make_float2(a, a); }
 __device__ __forceinline__ float2 sub2(float2 a, float2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
 
+#ifdef TRB_TIMING
+__device__ unsigned long long g_dbg[1024 * 16];
+__device__ __forceinline__ unsigned long long gtime() { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); return t; }
+#define TRB_T(slot) do { if (lane == 0) atomicMax(&g_dbg[blockIdx.x * 16 + (slot)], gtime()); } while (0)
+#define TRB_TD(slot, t0) do { if (lane == 0) atomicMax(&g_dbg[blockIdx.x * 16 + (slot)], gtime() - (t0)); } while (0)
+#else
+#define TRB_T(slot) do { } while (0)
+#define TRB_TD(slot, t0) do { } while (0)
+#endif
+
 struct TmaParams {
     AffineParams a;
     int n_pairs;
     int tiles_x, tiles_y, tiles_z;     // output tiles per axis
-    int zc;                            // tiles per unit (z-run)
-    int units_per_col;                 // ceil(tiles_z / zc)
-    int n_units;                       // n_pairs * tiles_y * tiles_x * units_per_col
+    int cols_per_pair;                 // tiles_x * tiles_y
+    int full_rounds;                   // rounds in which every CTA owns one whole column
+    long long tail_tiles;              // tiles of the remaining columns, cut into one span per CTA
 };
 
 struct TileMeta { int ox, oy, oz, fits; };
@@ -103,23 +115,52 @@ struct SmemLayout {
     static constexpr int kStageBytes = ((kBoxFloats + kTgtFloats) * 4 + 127) / 128 * 128;
 };
 
-// one pair of voxels (same x,y; z and z+1).  SECOND=false masks the second voxel (odd tail).
-template <int BX, int BY, bool SECOND>
-__device__ __forceinline__ void pair_step(const float *__restrict__ box, float2 Mrel, float2 ix, float2 iy, float2 iz,
-                                          float2 t, float2 zf, float2 (&s)[5], float2 (&P)[3][3], float2 (&Q)[3][3])
+
+template <int OFF>
+__device__ __forceinline__ float lds_f(uint32_t addr)
 {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1+%2];" : "=f"(v) : "r"(addr), "n"(OFF));
+    return v;
+}
+__device__ __forceinline__ float lds_f_dyn(uint32_t addr)
+{
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+    return v;
+}
+
+struct Acc {
+    float2 s[5];        // sum t, w, t^2, w^2, t*w            (two partial streams: voxel a / voxel b)
+    float2 P[3][3];     // sum k*G_r,        k in {1, t, w}
+    float2 Q[3][3];     // sum k*G_r*z
+};
+
+// one pair of voxels (same x,y; z and z+1).  box_m: smem byte address of the staged box.
+// SECOND=false masks voxel b.
+template <int BX, int BY, bool SECOND>
+__device__ __forceinline__ void pair_step(uint32_t box_m, float Mrel, float2 ix, float2 iy, float2 iz,
+                                          float2 t, float2 zf, Acc &A)
+{
+    // floor() = round-down add of 1.5*2^23 (FADD.RM) and subtracting it again; FRND on the XU pipe was
+    // tried instead (it frees 6 packed fp32 ops per pair) but its latency lengthened the dependent
+    // chain and the step got 11% slower (profiles/r01_notes.md)
     const float2 M = f2(kMagic), nM = f2(-kMagic);
     const float2 flx = __fadd2_rd(ix, M), fly = __fadd2_rd(iy, M), flz = __fadd2_rd(iz, M);
     const float2 fx = __fadd2_rn(flx, nM), fy = __fadd2_rn(fly, nM), fz = __fadd2_rn(flz, nM);
     const float2 tx = sub2(ix, fx), ty = sub2(iy, fy), tz = sub2(iz, fz);
-    const float2 fidx = __ffma2_rn(f2((float)(BX * BY)), fz, __ffma2_rn(f2((float)BX), fy, fx));
-    const float2 tb = __fadd2_rn(fidx, Mrel);
-    const float *qa = box + (__float_as_int(tb.x) - kMagicBits);
-    const float *qb = box + (__float_as_int(tb.y) - kMagicBits);
-    float2 c000 = make_float2(qa[0], qb[0]), c001 = make_float2(qa[1], qb[1]);
-    float2 c010 = make_float2(qa[BX], qb[BX]), c011 = make_float2(qa[BX + 1], qb[BX + 1]);
-    float2 c100 = make_float2(qa[BX * BY], qb[BX * BY]), c101 = make_float2(qa[BX * BY + 1], qb[BX * BY + 1]);
-    float2 c110 = make_float2(qa[BX * BY + BX], qb[BX * BY + BX]), c111 = make_float2(qa[BX * BY + BX + 1], qb[BX * BY + BX + 1]);
+    // box-relative linear index, formed in fp32 and scaled by 2^-22 onto [2, 4): exact, and the bit
+    // pattern is 0x40000000 + index, so (bits << 2) IS the byte offset (the 0x4 wraps away)
+    const float2 tb = __ffma2_rn(f2(kIdxScale * (float)(BX * BY)), fz,
+                                 __ffma2_rn(f2(kIdxScale * (float)BX), fy, __ffma2_rn(f2(kIdxScale), fx, f2(Mrel))));
+    const uint32_t qa = box_m + ((uint32_t)__float_as_int(tb.x) << 2);
+    const uint32_t qb = box_m + ((uint32_t)__float_as_int(tb.y) << 2);
+    constexpr int SY = BX * 4, SZ = BX * BY * 4;
+    const float2 c000 = make_float2(lds_f<0>(qa), lds_f<0>(qb)), c001 = make_float2(lds_f<4>(qa), lds_f<4>(qb));
+    const float2 c010 = make_float2(lds_f<SY>(qa), lds_f<SY>(qb)), c011 = make_float2(lds_f<SY + 4>(qa), lds_f<SY + 4>(qb));
+    const float2 c100 = make_float2(lds_f<SZ>(qa), lds_f<SZ>(qb)), c101 = make_float2(lds_f<SZ + 4>(qa), lds_f<SZ + 4>(qb));
+    const float2 c110 = make_float2(lds_f<SZ + SY>(qa), lds_f<SZ + SY>(qb));
+    const float2 c111 = make_float2(lds_f<SZ + SY + 4>(qa), lds_f<SZ + SY + 4>(qb));
     const float2 d00 = sub2(c001, c000), d01 = sub2(c011, c010), d10 = sub2(c101, c100), d11 = sub2(c111, c110);
     const float2 v00 = __ffma2_rn(tx, d00, c000), v01 = __ffma2_rn(tx, d01, c010);
     const float2 v10 = __ffma2_rn(tx, d10, c100), v11 = __ffma2_rn(tx, d11, c110);
@@ -137,26 +178,26 @@ __device__ __forceinline__ void pair_step(const float *__restrict__ box, float2 
 #pragma unroll
         for (int r = 0; r < 3; ++r) G[r] = __fmul2_rn(G[r], m);
     }
-    s[0] = __fadd2_rn(s[0], t);
-    s[1] = __fadd2_rn(s[1], val);
-    s[2] = __ffma2_rn(t, t, s[2]);
-    s[3] = __ffma2_rn(val, val, s[3]);
-    s[4] = __ffma2_rn(t, val, s[4]);
+    A.s[0] = __fadd2_rn(A.s[0], t);
+    A.s[1] = __fadd2_rn(A.s[1], val);
+    A.s[2] = __ffma2_rn(t, t, A.s[2]);
+    A.s[3] = __ffma2_rn(val, val, A.s[3]);
+    A.s[4] = __ffma2_rn(t, val, A.s[4]);
     const float2 tzf = __fmul2_rn(t, zf), wzf = __fmul2_rn(val, zf);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        P[0][r] = __fadd2_rn(P[0][r], G[r]);
-        P[1][r] = __ffma2_rn(t, G[r], P[1][r]);
-        P[2][r] = __ffma2_rn(val, G[r], P[2][r]);
-        Q[0][r] = __ffma2_rn(zf, G[r], Q[0][r]);
-        Q[1][r] = __ffma2_rn(tzf, G[r], Q[1][r]);
-        Q[2][r] = __ffma2_rn(wzf, G[r], Q[2][r]);
+        A.P[0][r] = __fadd2_rn(A.P[0][r], G[r]);
+        A.P[1][r] = __ffma2_rn(t, G[r], A.P[1][r]);
+        A.P[2][r] = __ffma2_rn(val, G[r], A.P[2][r]);
+        A.Q[0][r] = __ffma2_rn(zf, G[r], A.Q[0][r]);
+        A.Q[1][r] = __ffma2_rn(tzf, G[r], A.Q[1][r]);
+        A.Q[2][r] = __ffma2_rn(wzf, G[r], A.Q[2][r]);
     }
 }
 
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
 __device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
-                                             float t, float zf, float2 (&s)[5], float2 (&P)[3][3], float2 (&Q)[3][3])
+                                             float t, float zf, Acc &A)
 {
     ix = fminf(fmaxf(ix, -4.f), (float)W + 4.f);        // keeps the magic-number floor in range
     iy = fminf(fmaxf(iy, -4.f), (float)H + 4.f);
@@ -180,13 +221,264 @@ __device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int 
     G[2] = w1 - w0;
     const float val = fmaf(tz, G[2], w0);
     G[1] = fmaf(tz, e1 - e0, e0);
-    G[0] = fmaf(tz, fmaf(ty, d11 - d10, d10) - fmaf(ty, d01 - d00, d00), fmaf(ty, d01 - d00, d00));
-    s[0].x += t; s[1].x += val; s[2].x = fmaf(t, t, s[2].x); s[3].x = fmaf(val, val, s[3].x); s[4].x = fmaf(t, val, s[4].x);
+    const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
+    G[0] = fmaf(tz, dx1 - dx0, dx0);
+    A.s[0].x += t; A.s[1].x += val;
+    A.s[2].x = fmaf(t, t, A.s[2].x); A.s[3].x = fmaf(val, val, A.s[3].x); A.s[4].x = fmaf(t, val, A.s[4].x);
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
         const float g = G[r], tg = t * g, wg = val * g;
-        P[0][r].x += g; P[1][r].x += tg; P[2][r].x += wg;
-        Q[0][r].x = fmaf(zf, g, Q[0][r].x); Q[1][r].x = fmaf(zf, tg, Q[1][r].x); Q[2][r].x = fmaf(zf, wg, Q[2][r].x);
+        A.P[0][r].x += g; A.P[1][r].x += tg; A.P[2][r].x += wg;
+        A.Q[0][r].x = fmaf(zf, g, A.Q[0][r].x); A.Q[1][r].x = fmaf(zf, tg, A.Q[1][r].x); A.Q[2][r].x = fmaf(zf, wg, A.Q[2][r].x);
+    }
+}
+
+// Work decomposition.  A COLUMN is the full z-run of tiles at one (pair, y-tile, x-tile).  Columns are
+// numbered (pair, y, x) with x fastest and dealt out cyclically: in round r CTA b owns column r*G + b, so
+// at any moment the G CTAs sit on G x/y-adjacent columns at about the same z and the halo one CTA needs
+// was just fetched by its neighbour (L2 hit); a thread keeps its (x, y) for a whole column (one fold of
+// its sums per ~200 voxels).  The columns left after the last full round are cut into contiguous tile
+// spans (z fastest), one per CTA, so every SM stays busy to within one tile.
+struct TileIter {
+    int phase;                   // 0: full-column rounds, 1: tail span, 2: done
+    int r;                       // round
+    long long tt, tt_end;        // tail tile index / end of this CTA's tail span
+    int cg, tz_i;                // global column index, z-tile
+};
+__device__ __forceinline__ void iter_enter_tail(TileIter &it, const TmaParams &p, int b, int G)
+{
+    it.tt = p.tail_tiles * (long long)b / G;
+    it.tt_end = p.tail_tiles * (long long)(b + 1) / G;
+    if (it.tt >= it.tt_end) { it.phase = 2; return; }
+    it.phase = 1;
+    const int c = (int)(it.tt / p.tiles_z);
+    it.cg = p.full_rounds * G + c;
+    it.tz_i = (int)(it.tt - (long long)c * p.tiles_z);
+}
+__device__ __forceinline__ void iter_begin(TileIter &it, const TmaParams &p, int b, int G)
+{
+    it.r = 0; it.tt = it.tt_end = 0; it.tz_i = 0;
+    if (p.full_rounds > 0) { it.phase = 0; it.cg = b; }
+    else iter_enter_tail(it, p, b, G);
+}
+__device__ __forceinline__ bool iter_next(TileIter &it, const TmaParams &p, int b, int G)     // true: column changed / done
+{
+    if (it.phase == 0) {
+        if (++it.tz_i < p.tiles_z) return false;
+        it.tz_i = 0;
+        if (++it.r < p.full_rounds) it.cg = it.r * G + b;
+        else iter_enter_tail(it, p, b, G);
+        return true;
+    }
+    if (++it.tt >= it.tt_end) { it.phase = 2; return true; }
+    if (++it.tz_i < p.tiles_z) return false;
+    it.tz_i = 0;
+    ++it.cg;
+    return true;
+}
+
+constexpr int kMaxTmaPairs = 1024;       // pairs per launch of the TMA kernel (touched-pair bitmask)
+constexpr int kMaxCachedPairs = 64;     // coordinate maps kept in smem (12 floats per pair)
+
+__device__ __forceinline__ Coef load_coef(const float *coef_s, const TmaParams &p, int pair)
+{
+    Coef k;
+    if (p.n_pairs <= kMaxCachedPairs) {
+        const float *c = coef_s + pair * 12;
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) k.A[r][j] = c[r * 4 + j];
+            k.C[r] = c[r * 4 + 3];
+        }
+    } else {
+        const float *st = p.a.state + (size_t)pair * TRB_STATE_FLOATS + TRB_STATE_THETA;
+        float th[12];
+#pragma unroll
+        for (int i = 0; i < 12; ++i) th[i] = __ldcg(st + i);
+        k = make_coef(th, p.a.D, p.a.H, p.a.W);
+    }
+    return k;
+}
+
+// Map the tile through theta, decide whether its source footprint fits the TMA box, publish the
+// box origin and start the loads for `stage`.  Executed by ONE lane.
+template <int BX, int BY, int BZ>
+__device__ __forceinline__ void issue_tile(const TileIter &t, const TmaParams &p, const float *coef_s, unsigned char *stg,
+                                           uint64_t *full, TileMeta *meta, const CUtensorMap *map_mov,
+                                           const CUtensorMap *map_tgt, float inv_d2, float zoff)
+{
+    using L = SmemLayout<BX, BY, BZ>;
+    const int W = p.a.W, H = p.a.H;
+    const int pair = t.cg / p.cols_per_pair;
+    const int col = t.cg - pair * p.cols_per_pair;
+    const Coef k = load_coef(coef_s, p, pair);
+    const int ty_i = col / p.tiles_x;
+    const int x0 = (col - ty_i * p.tiles_x) * TX, y0 = ty_i * TY;
+    const float xa = __ldg(p.a.xb + x0), xe = __ldg(p.a.xb + min(x0 + TX - 1, W - 1));
+    const float ya = __ldg(p.a.yb + y0), ye = __ldg(p.a.yb + min(y0 + TY - 1, H - 1));
+    const int z0 = p.a.s_begin + t.tz_i * TZ;
+    const float za = fmaf(inv_d2, (float)z0, zoff), ze = fmaf(inv_d2, (float)min(z0 + TZ - 1, p.a.s_end - 1), zoff);
+    int o[3];
+    bool fits = true;
+    const int B[3] = {BX, BY, BZ};
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float base = k.A[r][0] * xa + k.A[r][1] * ya + k.A[r][2] * za + k.C[r];
+        const float dx = k.A[r][0] * (xe - xa), dy = k.A[r][1] * (ye - ya), dz = k.A[r][2] * (ze - za);
+        const float lo = base + fminf(dx, 0.f) + fminf(dy, 0.f) + fminf(dz, 0.f) - 0.02f;
+        const float hi = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.02f;
+        // keep the float->int conversions defined for wild thetas
+        const float loc = fminf(fmaxf(lo, -1.0e6f), 1.0e6f), hic = fminf(fmaxf(hi, -1.0e6f), 1.0e6f);
+        // TMA needs the box start 16-byte aligned along x (tools/tma_probe.cu: an unaligned innermost
+        // coordinate raises an illegal-instruction fault); y and z are free
+        o[r] = r == 0 ? 4 * (int)floorf(loc * 0.25f) : (int)floorf(loc);
+        fits = fits && ((int)floorf(hic) + 1 <= o[r] + B[r] - 1);
+    }
+    // the fp32 index trick needs |x + BX*y + BX*BY*z| < 2^21
+    fits = fits && (fabsf((float)o[0]) + BX * fabsf((float)o[1]) + (float)(BX * BY) * fabsf((float)o[2]) < 1.9e6f);
+    TileMeta m;
+    m.ox = o[0]; m.oy = o[1]; m.oz = o[2]; m.fits = fits ? 1 : 0;
+    *meta = m;
+    const unsigned tgt_bytes = L::kTgtFloats * 4, box_bytes = L::kBoxFloats * 4;
+    mbar_arrive_expect_tx(full, fits ? (tgt_bytes + box_bytes) : tgt_bytes);
+    if (fits) tma_load_4d(stg, map_mov, full, o[0], o[1], o[2], pair);
+    tma_load_4d(stg + L::kBoxFloats * 4, map_tgt, full, x0, y0, z0, pair);
+}
+
+// sum 41 per-lane values over the warp.  The first 32 are reduced "transposed" (recursive halving:
+// 31 shuffles instead of 160); lane l ends up holding the warp total of value l.
+__device__ __forceinline__ void warp_reduce_moments(const float (&acc)[TRB_MOMENTS], float *dst /*[41] smem*/, int lane)
+{
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = acc[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, off);
+        }
+    }
+    dst[lane] = v[0];
+#pragma unroll
+    for (int i = 32; i < TRB_MOMENTS; ++i) {
+        const float r = warp_sum(acc[i]);
+        if (lane == 0) dst[i] = r;
+    }
+}
+
+constexpr int kRedLd = TRB_MOMENTS + 3;
+
+// ---- grid-level reduction of the per-CTA partial sums -------------------------------------------------
+// Every CTA owns slot blockIdx.x of every pair (zeros for pairs it never touches).  CTAs are grouped by 16;
+// the CTA that completes a (pair, group) ticket adds the group's 16 slots in index order into the group
+// slot — this happens DURING the launch, off the critical path.  The last CTA to finish all its tiles then
+// only has ceil(G/16) group slots per pair to add (fixed order) before the epilogue, so the serial tail of
+// a launch is a few microseconds however many SMs contributed.  All orders are fixed => bit-reproducible.
+constexpr int kGroup = 16;
+constexpr int kTicketsPerPair = 128;          // [0..63] group tickets; [126] CTAs-done (pair 0); [127] direct kernel
+
+__device__ __forceinline__ double *slot_ptr(const TmaParams &p, int pair, int slot)
+{
+    return p.a.partials + ((size_t)pair * kMaxSlots + slot) * TRB_MOMENTS;
+}
+
+// add slots [s0, s1) of `pair` in index order; lane l returns moments l (x) and l+32 (y, valid for l < 9)
+__device__ __forceinline__ double2 warp_fold_slots(const TmaParams &p, int pair, int s0, int s1, int lane)
+{
+    const int v1 = min(lane + 32, TRB_MOMENTS - 1);
+    double r0 = 0.0, r1 = 0.0;
+    for (int b0 = s0; b0 < s1; b0 += kGroup) {
+        // issue all 32 loads of the pass before touching any result: written as `acc += __ldcg(...)` the
+        // compiler emitted load-pair / add / load-pair / add with two registers, i.e. one L2 round trip per
+        // slot (tools/_lat microbenchmark: 6.4k cycles for 16 slots)
+        double x0[kGroup], x1[kGroup];
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {
+            const double *row = slot_ptr(p, pair, (b0 + j < s1) ? b0 + j : s0);
+            asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(x0[j]) : "l"(row + lane));
+            asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(x1[j]) : "l"(row + v1));
+        }
+#pragma unroll
+        for (int j = 0; j < kGroup; ++j) {              // index order
+            const bool ok = b0 + j < s1;
+            r0 += ok ? x0[j] : 0.0;
+            r1 += ok ? x1[j] : 0.0;
+        }
+    }
+    return make_double2(r0, r1);
+}
+
+// one warp: CTA blockIdx.x has deposited its slot of `pair`; arrive on the group ticket, fold if last
+__device__ void warp_arrive_group(const TmaParams &p, int pair, int G, int lane)
+{
+    __threadfence();
+    __syncwarp();
+    const int g = blockIdx.x / kGroup;
+    const int gsize = min(kGroup, G - g * kGroup);
+    unsigned *tk = p.a.tickets + (size_t)pair * kTicketsPerPair + g;
+    unsigned t = 0;
+    if (lane == 0) t = atomicAdd(tk, 1u);
+    t = __shfl_sync(kFull, t, 0);
+    if (t != (unsigned)gsize - 1u) return;
+    __threadfence();
+    const double2 r = warp_fold_slots(p, pair, g * kGroup, g * kGroup + gsize, lane);
+    double *dst = slot_ptr(p, pair, G + g);
+    __stcg(dst + lane, r.x);
+    if (lane + 32 < TRB_MOMENTS) __stcg(dst + lane + 32, r.y);
+    if (lane == 0) *tk = 0u;
+    __threadfence();
+}
+
+// Warp-level hand-over of a pair's sums (no CTA barrier: warps never wait for each other).  Each warp
+// deposits its 41 totals in red[warp]; the LAST warp of the CTA to arrive adds the 16 rows in fixed
+// order, writes the CTA partial (fp64) to its slot and arrives on the group ticket.
+__device__ void warp_publish_pair(const float (&acc)[TRB_MOMENTS], float *red /*[16][kRedLd]*/, unsigned *cnt,
+                                  const TmaParams &p, int pair, int G, int warp, int lane)
+{
+    warp_reduce_moments(acc, red + warp * kRedLd, lane);
+    __syncwarp();
+    unsigned old = 0;
+    if (lane == 0)
+        asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
+    old = __shfl_sync(kFull, old, 0);
+    if (old != kConsumerWarps - 1) return;
+    if (lane == 0) *cnt = 0u;
+    double *mine = slot_ptr(p, pair, blockIdx.x);
+    for (int v = lane; v < TRB_MOMENTS; v += 32) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kConsumerWarps; ++w) s += (double)red[w * kRedLd + v];
+        __stcg(mine + v, s);
+    }
+    warp_arrive_group(p, pair, G, lane);
+}
+
+// Run by the LAST CTA to complete its tiles (all 16 warps): per pair, add the group slots in index order
+// and run the epilogue (FUSED) or publish the moments.  Pairs are spread over the warps.
+template <bool FUSED>
+__device__ void final_phase(const TmaParams &p, double *fin_s /*[16][TRB_MOMENTS + 1] smem*/, int G, int warp, int lane)
+{
+    constexpr int LD = TRB_MOMENTS + 1;
+    const int n_groups = (G + kGroup - 1) / kGroup;
+    for (int pair = warp; pair < p.n_pairs; pair += kConsumerWarps) {
+        const double2 r = warp_fold_slots(p, pair, G, G + n_groups, lane);
+        double *row = fin_s + warp * LD;
+        row[lane] = r.x;
+        if (lane + 32 < TRB_MOMENTS) row[lane + 32] = r.y;
+        __syncwarp();
+        TRB_T(5);
+        if (FUSED) {
+            if (lane == 0) affine_epilogue<3>(row, p.a, pair);
+        } else {
+            for (int v = lane; v < TRB_MOMENTS; v += 32) p.a.moments_out[(size_t)pair * TRB_MOMENTS + v] = row[v];
+        }
+        __syncwarp();
+        TRB_T(6);
     }
 }
 
@@ -197,198 +489,228 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
     using L = SmemLayout<BX, BY, BZ>;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     uint64_t *full_bar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)NSTAGE * L::kStageBytes);
-    uint64_t *empty_bar = full_bar + NSTAGE;
-    TileMeta *meta = reinterpret_cast<TileMeta *>(empty_bar + NSTAGE);
+    unsigned *done_cnt = reinterpret_cast<unsigned *>(full_bar + NSTAGE);
+    TileMeta *meta = reinterpret_cast<TileMeta *>(done_cnt + NSTAGE);
+    __shared__ __align__(16) float red[2][kConsumerWarps * kRedLd];     // double-buffered by the parity of the flush count;
+                                                                         // re-used (as doubles) by final_phase
+    __shared__ unsigned pair_cnt[2];
+    __shared__ float coef_s[kMaxCachedPairs * 12];
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int W = p.a.W, H = p.a.H, D = p.a.D;
-
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar + i, 1); mbar_init(empty_bar + i, kConsumerWarps); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-
-    const int units_per_pair = p.tiles_y * p.tiles_x * p.units_per_col;
-    const int G = gridDim.x;
+    const int G = gridDim.x, b = blockIdx.x;
     const float inv_d2 = 2.f / (float)D, zoff = 1.f / (float)D - 1.f;      // zv(z) = (2z+1)/D - 1
 
-    if (warp == kConsumerWarps) {
-        // ===================== producer: one lane walks the same unit/tile sequence ==========
-        if (lane == 0) {
-            int it = 0;
-            for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-                const int pair = u / units_per_pair;
-                int rem = u - pair * units_per_pair;
-                const int zc_i = rem / (p.tiles_y * p.tiles_x);
-                rem -= zc_i * (p.tiles_y * p.tiles_x);
-                const int ty_i = rem / p.tiles_x, tx_i = rem - ty_i * p.tiles_x;
-                const int x0 = tx_i * TX, y0 = ty_i * TY;
-                const float *st = p.a.state + (size_t)pair * TRB_STATE_FLOATS + TRB_STATE_THETA;
-                float th[12];
-#pragma unroll
-                for (int i = 0; i < 12; ++i) th[i] = __ldcg(st + i);
-                const Coef k = make_coef(th, D, H, W);
-                const float xa = __ldg(p.a.xb + x0), xe = __ldg(p.a.xb + min(x0 + TX - 1, W - 1));
-                const float ya = __ldg(p.a.yb + y0), ye = __ldg(p.a.yb + min(y0 + TY - 1, H - 1));
-                const int t_begin = zc_i * p.zc, t_end = min(t_begin + p.zc, p.tiles_z);
-                for (int tz_i = t_begin; tz_i < t_end; ++tz_i, ++it) {
-                    const int stage = it % NSTAGE;
-                    const unsigned phase = (unsigned)(it / NSTAGE) & 1u;
-                    mbar_wait(empty_bar + stage, phase ^ 1u);
-                    const int z0 = p.a.s_begin + tz_i * TZ;
-                    const float za = fmaf(inv_d2, (float)z0, zoff), ze = fmaf(inv_d2, (float)min(z0 + TZ - 1, p.a.s_end - 1), zoff);
-                    int o[3];
-                    bool fits = true;
-                    const int B[3] = {BX, BY, BZ};
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float base = k.A[r][0] * xa + k.A[r][1] * ya + k.A[r][2] * za + k.C[r];
-                        const float dx = k.A[r][0] * (xe - xa), dy = k.A[r][1] * (ye - ya), dz = k.A[r][2] * (ze - za);
-                        const float lo = base + fminf(dx, 0.f) + fminf(dy, 0.f) + fminf(dz, 0.f) - 0.02f;
-                        const float hi = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.02f;
-                        // keep the float->int conversions defined for wild thetas
-                        const float loc = fminf(fmaxf(lo, -1.0e6f), 1.0e6f), hic = fminf(fmaxf(hi, -1.0e6f), 1.0e6f);
-                        // TMA needs the box start 16-byte aligned along x (tools/tma_probe.cu: an unaligned
-                        // innermost coordinate raises an illegal-instruction fault); y and z are free
-                        o[r] = r == 0 ? 4 * (int)floorf(loc * 0.25f) : (int)floorf(loc);
-                        fits = fits && ((int)floorf(hic) + 1 <= o[r] + B[r] - 1);
-                    }
-                    // the fp32 index trick needs |x + BX*y + BX*BY*z| < 2^22
-                    fits = fits && (fabsf((float)o[0]) + BX * fabsf((float)o[1]) + (float)(BX * BY) * fabsf((float)o[2]) < 3.0e6f);
-                    TileMeta m;
-                    m.ox = o[0]; m.oy = o[1]; m.oz = o[2]; m.fits = fits ? 1 : 0;
-                    meta[stage] = m;
-                    unsigned char *stg = smem_raw + (size_t)stage * L::kStageBytes;
-                    const unsigned tgt_bytes = L::kTgtFloats * 4, box_bytes = L::kBoxFloats * 4;
-                    mbar_arrive_expect_tx(full_bar + stage, fits ? (tgt_bytes + box_bytes) : tgt_bytes);
-                    if (fits) tma_load_4d(stg, &map_mov, full_bar + stage, o[0], o[1], o[2], pair);
-                    tma_load_4d(stg + L::kBoxFloats * 4, &map_tgt, full_bar + stage, x0, y0, z0, pair);
-                }
-            }
-        }
-    } else {
-        // ===================== consumers ======================================================
-        // per-pair accumulators of this thread, folded with its x,y,z base coordinates
-        float S[5], T1[3][3], Tx[3][3], Ty[3][3], Tz[3][3];
-        auto zero_totals = [&]() {
-#pragma unroll
-            for (int i = 0; i < 5; ++i) S[i] = 0.f;
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) T1[kk][r] = Tx[kk][r] = Ty[kk][r] = Tz[kk][r] = 0.f;
-        };
-        // a CTA's units are pair-major, so it finishes one pair before touching the next: hand the
-        // pair's CTA total to the grid-level reduction when the pair changes
-        auto flush_pair = [&](int pr) {
-            float acc[TRB_MOMENTS];
-#pragma unroll
-            for (int i = 0; i < 5; ++i) acc[i] = S[i];
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) {
-                    const int b = 5 + kk * 12 + r * 4;
-                    acc[b + 0] = Tx[kk][r]; acc[b + 1] = Ty[kk][r]; acc[b + 2] = Tz[kk][r]; acc[b + 3] = T1[kk][r];
-                }
-            const int count = min(G, units_per_pair);
-            const int first = (int)(((long long)pr * units_per_pair) % G);
-            reduce_and_finish<3, FUSED, kConsumerWarps>(acc, p.a, pr, blockIdx.x, G, first, count, 1, threadIdx.x);
-        };
-        zero_totals();
-        int cur_pair = -1;
-        int it = 0;
-        for (int u = blockIdx.x; u < p.n_units; u += gridDim.x) {
-            const int pair = u / units_per_pair;
-            if (pair != cur_pair) {
-                if (cur_pair >= 0) { flush_pair(cur_pair); zero_totals(); }
-                cur_pair = pair;
-            }
-            int rem = u - pair * units_per_pair;
-            const int zc_i = rem / (p.tiles_y * p.tiles_x);
-            rem -= zc_i * (p.tiles_y * p.tiles_x);
-            const int ty_i = rem / p.tiles_x, tx_i = rem - ty_i * p.tiles_x;
-            const int x = tx_i * TX + lane, y = ty_i * TY + warp;
-            const bool valid = (x < W) && (y < H);
-            const float *st = p.a.state + (size_t)pair * TRB_STATE_FLOATS + TRB_STATE_THETA;
+    // coordinate maps of all pairs -> smem (theta was written by the previous epoch's epilogue)
+    if (p.n_pairs <= kMaxCachedPairs) {
+        for (int pr = threadIdx.x; pr < p.n_pairs; pr += kTmaThreads) {
+            const float *st = p.a.state + (size_t)pr * TRB_STATE_FLOATS + TRB_STATE_THETA;
             float th[12];
 #pragma unroll
             for (int i = 0; i < 12; ++i) th[i] = __ldcg(st + i);
             const Coef k = make_coef(th, D, H, W);
-            const float xv = __ldg(p.a.xb + min(x, W - 1)), yv = __ldg(p.a.yb + min(y, H - 1));
-            float pxy[3], sz[3];
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) coef_s[pr * 12 + r * 4 + j] = k.A[r][j];
+                coef_s[pr * 12 + r * 4 + 3] = k.C[r];
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        pair_cnt[0] = pair_cnt[1] = 0u;
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar + i, 1); done_cnt[i] = 0u; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    TRB_T(0);
+    TileIter cur, ahead;
+    iter_begin(cur, p, b, G);
+    ahead = cur;
+    // pairs this CTA never touches still owe their (zero) slot to the grid reduction: settle that now,
+    // off the critical path.  Thread 0 walks the work list (a few columns) to mark the touched pairs.
+    __shared__ unsigned touched[kMaxTmaPairs / 32];
+    for (int i = threadIdx.x; i < kMaxTmaPairs / 32; i += kTmaThreads) touched[i] = 0u;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int r = 0; r < p.full_rounds; ++r) {
+            const int pr = (r * G + b) / p.cols_per_pair;
+            touched[pr >> 5] |= 1u << (pr & 31);
+        }
+        const long long t0 = p.tail_tiles * (long long)b / G, t1 = p.tail_tiles * (long long)(b + 1) / G;
+        if (t1 > t0) {
+            const int c0 = p.full_rounds * G + (int)(t0 / p.tiles_z), c1 = p.full_rounds * G + (int)((t1 - 1) / p.tiles_z);
+            for (int pr = c0 / p.cols_per_pair; pr <= c1 / p.cols_per_pair; ++pr) touched[pr >> 5] |= 1u << (pr & 31);
+        }
+    }
+    __syncthreads();
+    for (int pr = warp; pr < p.n_pairs; pr += kConsumerWarps) {
+        if (touched[pr >> 5] & (1u << (pr & 31))) continue;
+        double *mine = slot_ptr(p, pr, b);
+        for (int v = lane; v < TRB_MOMENTS; v += 32) __stcg(mine + v, 0.0);
+        warp_arrive_group(p, pr, G, lane);
+    }
+    if (threadIdx.x == 0) {                     // prologue: fill the ring
+        TileIter t = cur;
+        for (int i = 0; i < NSTAGE && t.phase != 2; ++i) {
+            issue_tile<BX, BY, BZ>(t, p, coef_s, smem_raw + (size_t)i * L::kStageBytes, full_bar + i, meta + i, &map_mov, &map_tgt, inv_d2, zoff);
+            iter_next(t, p, b, G);
+        }
+    }
+    for (int i = 0; i < NSTAGE && ahead.phase != 2; ++i) iter_next(ahead, p, b, G);   // ahead = cur + NSTAGE tiles
+
+    // per-pair totals of this thread, folded with its x,y,z base coordinates.  Touched once per column
+    // only: kept in local memory (volatile) so the 41 values do not occupy registers in the hot loop.
+    float Tmem[TRB_MOMENTS];
+    volatile float *T = Tmem;
+#pragma unroll
+    for (int i = 0; i < TRB_MOMENTS; ++i) T[i] = 0.f;
+    int n_flush = 0;
+
+    int it = 0;
+    while (cur.phase != 2) {
+        // ---- column setup: this thread's x, y and the coordinate map of the pair ------------------------
+        const int pair = cur.cg / p.cols_per_pair;
+        const int col = cur.cg - pair * p.cols_per_pair;
+        const int ty_i = col / p.tiles_x;
+        const int x = (col - ty_i * p.tiles_x) * TX + lane, y = ty_i * TY + warp;
+        const bool valid = (x < W) && (y < H);
+        const float xv = __ldg(p.a.xb + min(x, W - 1)), yv = __ldg(p.a.yb + min(y, H - 1));
+        float pxy[3], sz[3];
+        {
+            const Coef k = load_coef(coef_s, p, pair);
 #pragma unroll
             for (int r = 0; r < 3; ++r) {
                 pxy[r] = fmaf(k.A[r][0], xv, fmaf(k.A[r][1], yv, fmaf(k.A[r][2], zoff, k.C[r])));
                 sz[r] = k.A[r][2] * inv_d2;
             }
-            const float *__restrict__ mov = p.a.moving + (size_t)pair * p.a.pair_stride;
-            float2 s[5], P[3][3], Q[3][3];
+        }
+        const float *__restrict__ mov = p.a.moving + (size_t)pair * p.a.pair_stride;
+        Acc A;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) s[i] = f2(0.f);
+        for (int i = 0; i < 5; ++i) A.s[i] = f2(0.f);
 #pragma unroll
-            for (int kk = 0; kk < 3; ++kk)
+        for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
-                for (int r = 0; r < 3; ++r) P[kk][r] = Q[kk][r] = f2(0.f);
+            for (int r = 0; r < 3; ++r) A.P[kk][r] = A.Q[kk][r] = f2(0.f);
 
-            const int t_begin = zc_i * p.zc, t_end = min(t_begin + p.zc, p.tiles_z);
-            for (int tz_i = t_begin; tz_i < t_end; ++tz_i, ++it) {
-                const int stage = it % NSTAGE;
-                const unsigned phase = (unsigned)(it / NSTAGE) & 1u;
-                mbar_wait(full_bar + stage, phase);
-                const TileMeta m = meta[stage];
-                const float *box = reinterpret_cast<const float *>(smem_raw + (size_t)stage * L::kStageBytes);
-                const float *tg = box + L::kBoxFloats + warp * TX + lane;
-                const int z0 = p.a.s_begin + tz_i * TZ;
-                const int nz = min(TZ, p.a.s_end - z0);
-                if (valid) {
-                    if (m.fits) {
-                        const float2 Mrel = f2(kMagic - (float)(m.ox + BX * m.oy + BX * BY * m.oz));
-#pragma unroll 2
-                        for (int zz = 0; zz < nz; zz += 2) {
-                            const bool second = zz + 1 < nz;
-                            const float zf0 = (float)(z0 + zz);
-                            const float2 zf = make_float2(zf0, second ? zf0 + 1.f : zf0);
+        bool col_done = false;
+        while (!col_done) {
+            const int stage = it % NSTAGE;
+            const unsigned phase = (unsigned)(it / NSTAGE) & 1u;
+            mbar_wait(full_bar + stage, phase);
+            const TileMeta m = meta[stage];
+            unsigned char *stg = smem_raw + (size_t)stage * L::kStageBytes;
+            const uint32_t box_addr = smem_u32(stg);
+            const uint32_t tg = box_addr + L::kBoxFloats * 4 + (uint32_t)(warp * TX + lane) * 4u;
+            const int z0 = p.a.s_begin + cur.tz_i * TZ;
+            const int nz = min(TZ, p.a.s_end - z0);
+            if (valid) {
+                if (m.fits) {
+                    // index magic: 2.0 + rel * 2^-22 has bit pattern 0x40000000 + rel, and (bits << 2) wraps to 4*rel
+                    const float Mrel = 2.f - kIdxScale * (float)(m.ox + BX * m.oy + BX * BY * m.oz);
+                    const float zf0 = (float)z0;
+                    if (nz == TZ) {
+                        float2 zf = make_float2(zf0, zf0 + 1.f);
+#pragma unroll
+                        for (int j = 0; j < TZ / 2; ++j) {
                             const float2 ix = __ffma2_rn(f2(sz[0]), zf, f2(pxy[0]));
                             const float2 iy = __ffma2_rn(f2(sz[1]), zf, f2(pxy[1]));
                             const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
-                            const float2 t = make_float2(tg[zz * (TX * TY)], tg[(second ? zz + 1 : zz) * (TX * TY)]);
-                            if (second) pair_step<BX, BY, true>(box, Mrel, ix, iy, iz, t, zf, s, P, Q);
-                            else pair_step<BX, BY, false>(box, Mrel, ix, iy, iz, t, zf, s, P, Q);
+                            float2 t;
+                            switch (j) {      // immediates: the target tile advances TX*TY*4 bytes per z
+                            case 0: t = make_float2(lds_f<0 * TX * TY * 4>(tg), lds_f<1 * TX * TY * 4>(tg)); break;
+                            case 1: t = make_float2(lds_f<2 * TX * TY * 4>(tg), lds_f<3 * TX * TY * 4>(tg)); break;
+                            case 2: t = make_float2(lds_f<4 * TX * TY * 4>(tg), lds_f<5 * TX * TY * 4>(tg)); break;
+                            default: t = make_float2(lds_f<6 * TX * TY * 4>(tg), lds_f<7 * TX * TY * 4>(tg)); break;
+                            }
+                            pair_step<BX, BY, true>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            zf = __fadd2_rn(zf, f2(2.f));
                         }
                     } else {
-                        for (int zz = 0; zz < nz; ++zz) {
-                            const float zf = (float)(z0 + zz);
-                            voxel_direct(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
-                                         tg[zz * (TX * TY)], zf, s, P, Q);
+                        for (int zz = 0; zz < nz; zz += 2) {
+                            const bool second = zz + 1 < nz;
+                            const float za = zf0 + (float)zz;
+                            const float2 zf = make_float2(za, second ? za + 1.f : za);
+                            const float2 ix = __ffma2_rn(f2(sz[0]), zf, f2(pxy[0]));
+                            const float2 iy = __ffma2_rn(f2(sz[1]), zf, f2(pxy[1]));
+                            const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
+                            const float2 t = make_float2(lds_f_dyn(tg + zz * (TX * TY * 4)),
+                                                         lds_f_dyn(tg + (second ? zz + 1 : zz) * (TX * TY * 4)));
+                            if (second) pair_step<BX, BY, true>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            else pair_step<BX, BY, false>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                         }
                     }
-                }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(empty_bar + stage);
-            }
-            // fold the unit's sums with this thread's base coordinates (x, y constant over the unit)
-            if (valid) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) S[i] += s[i].x + s[i].y;
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                    for (int r = 0; r < 3; ++r) {
-                        const float pp = P[kk][r].x + P[kk][r].y, qq = Q[kk][r].x + Q[kk][r].y;
-                        T1[kk][r] += pp;
-                        Tx[kk][r] = fmaf(xv, pp, Tx[kk][r]);
-                        Ty[kk][r] = fmaf(yv, pp, Ty[kk][r]);
-                        Tz[kk][r] += fmaf(inv_d2, qq, zoff * pp);
+                } else {
+                    for (int zz = 0; zz < nz; ++zz) {
+                        const float zf = (float)(z0 + zz);
+                        voxel_direct(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
+                                     lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
                     }
+                }
             }
+            // ---- release the stage; the last warp to finish refills it with the tile NSTAGE ahead --------
+            __syncwarp();
+            if (lane == 0) {
+                unsigned old;
+                asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(done_cnt + stage)) : "memory");
+                if (old == kConsumerWarps - 1) {
+                    done_cnt[stage] = 0u;
+                    if (ahead.phase != 2)
+                        issue_tile<BX, BY, BZ>(ahead, p, coef_s, stg, full_bar + stage, meta + stage, &map_mov, &map_tgt, inv_d2, zoff);
+                }
+            }
+            ++it;
+            if (ahead.phase != 2) iter_next(ahead, p, b, G);
+            col_done = iter_next(cur, p, b, G);
         }
-        if (cur_pair >= 0) flush_pair(cur_pair);
+
+        // ---- fold the column's sums with this thread's base coordinates (x, y constant over the column) --
+        if (valid) {
+#pragma unroll
+            for (int i = 0; i < 5; ++i) T[i] += A.s[i].x + A.s[i].y;
+#pragma unroll
+            for (int kk = 0; kk < 3; ++kk)
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    const float pp = A.P[kk][r].x + A.P[kk][r].y, qq = A.Q[kk][r].x + A.Q[kk][r].y;
+                    const int bi = 5 + kk * 12 + r * 4;
+                    T[bi + 0] = fmaf(xv, pp, T[bi + 0]);
+                    T[bi + 1] = fmaf(yv, pp, T[bi + 1]);
+                    T[bi + 2] += fmaf(inv_d2, qq, zoff * pp);
+                    T[bi + 3] += pp;
+                }
+        }
+        // ---- pair finished (for this CTA): hand its totals to the grid-level reduction ----------------
+        if (cur.phase == 2 || cur.cg / p.cols_per_pair != pair) {
+            float acc[TRB_MOMENTS];
+#pragma unroll
+            for (int i = 0; i < TRB_MOMENTS; ++i) { acc[i] = T[i]; T[i] = 0.f; }
+            // a warp can be at most one flush ahead of the slowest warp of its CTA (the TMA ring holds fewer
+            // tiles than a pair has), so two scratch buffers alternate safely
+            warp_publish_pair(acc, red[n_flush & 1], pair_cnt + (n_flush & 1), p, pair, G, warp, lane);
+            ++n_flush;
+        }
     }
-
+    TRB_T(1);
+    // ---- the last CTA to get here finishes every pair ------------------------------------------------
+    __shared__ int is_last_cta;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        const unsigned done = atomicAdd(p.a.tickets + 126, 1u);
+        is_last_cta = (done == (unsigned)G - 1u) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!is_last_cta) return;
+    TRB_T(3);
+    __threadfence();
+    TRB_T(4);
+    final_phase<FUSED>(p, reinterpret_cast<double *>(&red[0][0]), G, warp, lane);
+    if (threadIdx.x == 0) p.a.tickets[126] = 0u;
+    TRB_T(2);
 }
-
 
 // ---- host side ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -435,8 +757,13 @@ bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs)
     if (a.W % 4 != 0 || a.W < TX || a.H < TY || (a.s_end - a.s_begin) < 1) return false;
     if (((uintptr_t)a.moving & 15) || ((uintptr_t)a.target & 15)) return false;
     if (n_pairs > 1 && (a.pair_stride % 4 != 0)) return false;
+    if (n_pairs > kMaxTmaPairs) return false;
     // fp32 index trick range: |x + BX*y + BX*BY*z| < 2^22 with some headroom
-    if ((double)a.W + (double)kBX * a.H + (double)kBX * kBY * a.D > 2.9e6) return false;
+    if ((double)a.W + (double)kBX * a.H + (double)kBX * kBY * a.D > 1.8e6) return false;
+    {   // the pair-parity double buffer assumes a pair spans more tiles than the ring holds
+        const long long tpp = (long long)((a.W + TX - 1) / TX) * ((a.H + TY - 1) / TY) * ((a.s_end - a.s_begin + TZ - 1) / TZ);
+        if (n_pairs > 1 && tpp < 4 * kStages) return false;   // (tiles per pair; chunks only group them)
+    }
     return encode_fn() != nullptr;
 }
 
@@ -458,19 +785,14 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const long long cols = (long long)n_pairs * p.tiles_x * p.tiles_y;
-    // units of zc tiles along z: aim for >= 8 units per CTA so the static round-robin balances
-    long long zc = cols * p.tiles_z / ((long long)sms * 8);
-    if (zc < 1) zc = 1;
-    if (zc > p.tiles_z) zc = p.tiles_z;
-    p.zc = (int)zc;
-    p.units_per_col = (p.tiles_z + p.zc - 1) / p.zc;
-    const long long n_units = cols * p.units_per_col;
-    if (n_units > 0x7fffffffLL) { set_error("too many work units"); return TRB_ERR_UNSUPPORTED; }
-    p.n_units = (int)n_units;
-    int grid = sms;
-    if (grid > p.n_units) grid = p.n_units;
-    if (grid > kMaxSlots) grid = kMaxSlots;
+    p.cols_per_pair = p.tiles_x * p.tiles_y;
+    const long long total_cols = (long long)n_pairs * p.cols_per_pair;
+    long long grid_ll = sms;
+    if (grid_ll > total_cols * p.tiles_z) grid_ll = total_cols * p.tiles_z;
+    if (grid_ll > kMaxSlots - 64) grid_ll = kMaxSlots - 64;       // slots G.. hold the group sums
+    const int grid = (int)grid_ll;
+    p.full_rounds = (int)(total_cols / grid);
+    p.tail_tiles = (total_cols - (long long)p.full_rounds * grid) * p.tiles_z;
     const size_t smem = (size_t)kStages * L::kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * sizeof(TileMeta);
     auto kf = affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true>;
     auto ku = affine3d_tma_kernel<kBX, kBY, kBZ, kStages, false>;
@@ -490,3 +812,7 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
 }
 
 }  // namespace trb
+#ifdef TRB_TIMING
+extern "C" int trb_debug_read(unsigned long long *out, int n) { return (int)cudaMemcpyFromSymbol(out, trb::g_dbg, sizeof(unsigned long long) * n); }
+extern "C" int trb_debug_clear() { static unsigned long long z[1024 * 16]; return (int)cudaMemcpyToSymbol(trb::g_dbg, z, sizeof(z)); }
+#endif
