@@ -77,7 +77,7 @@ def flow_warp(src: torch.Tensor, flow: torch.Tensor) -> torch.Tensor:
     displaces spatial axis i; normalise, reverse channel order, sample with
     align_corners=True."""
     shape = flow.shape[2:]
-    vecs = [torch.arange(0, s, dtype=torch.float32) for s in shape]
+    vecs = [torch.arange(0, s, dtype=torch.float32, device=flow.device) for s in shape]
     ident = torch.stack(torch.meshgrid(*vecs, indexing="ij"))[None].to(flow.dtype)
     locs = ident + flow
     comps = []

@@ -191,7 +191,34 @@ def case_register_api(name, shape, mode, weights, lr, epochs, seed):
          call_in=two.numpy(), call_out=out.numpy())
 
 
+def case_flow_register(name, shape, n, lr, epochs, w_mse, w_ncc):
+    """reference flow_register (U-Net -> flow -> warp -> MSE+NCC -> SGD on the U-Net), 2-D so it runs in
+    seconds on CPU; the initial state_dict is stored so both sides start from the same weights."""
+    import warnings
+    mov, tgt = make_pair(shape, "flow")
+    # seed 5: seed 0 gives a network whose first block is dead (all-zero after ReLU) on this input, so the
+    # flow is amplified rounding noise — useless as a pin
+    torch.manual_seed(5)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        fr = rw.flow_register(shape, mode='bilinear', n=n, lr=lr, max_epochs=epochs,
+                              criterions=[nn.MSELoss(), ru.NCCLoss()], weights=[w_mse, w_ncc])
+        sd0 = {k: v.clone() for k, v in fr.state_dict().items() if not k.endswith('warp.grid')}
+        _quiet(fr.optimize, mov, tgt, 'cpu', True)
+        losses = ref_shim.last_losses()
+        deformed = fr.deform(mov).detach()
+    out = dict(moving=mov.numpy(), target=tgt.numpy(), lr=np.float64(lr), epochs=np.int64(epochs), n=np.int64(n),
+               weights=np.asarray([w_mse, w_ncc, 0.0]), losses=np.asarray(losses, np.float64),
+               flow=fr.flow.detach().numpy().copy(), deformed=deformed.numpy().copy())
+    for k, v in sd0.items():
+        out["sd::" + k] = v.numpy()
+    save(name, **out)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "flowreg":
+        case_flow_register("flowreg2d", (160, 168), 32, 1e-3, 3, 0.5, 0.5)
+        return
     case_2d_stub_equivalence()
     p3 = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02])
     p2 = torch.tensor([0.03, 0.02, -0.01])
@@ -221,6 +248,7 @@ def main():
     # public API
     case_register_api("api_rigid3d", S3, "rigid", [0.0, 1.0, 0.0], 1e-4, 6, seed=3)
     case_register_api("api_affine2d", S2, "affine", [0.5, 0.5, 0.0], 1e-4, 6, seed=3)
+    case_flow_register("flowreg2d", (160, 168), 32, 1e-3, 3, 0.5, 0.5)
 
 
 if __name__ == "__main__":

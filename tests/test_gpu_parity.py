@@ -281,3 +281,81 @@ def test_tma_kernel_batch_and_slabs():
         sh.apply(parts[0] + parts[1] + parts[2], 1e-3, 0.5, 0.5)
     assert torch.allclose(sh.losses, fused.losses, rtol=1e-5)
     assert torch.allclose(sh.final_theta, fused.final_theta, atol=1e-6)
+
+
+# --------------------------------------------------------------------------------------------
+# flow mode: PyTorch U-Net + fused warp/similarity/gradient node
+# --------------------------------------------------------------------------------------------
+def _flow_register_vs_device_oracle(criterions, weights, loss_fn, epochs=3):
+    """flow_register on the GPU against the SAME loop built from the reference's torch ops on the same device
+    (what the reference runs for device='cuda').  The reference's U-Net is ill-conditioned on flat backgrounds
+    (InstanceNorm of near-constant channels: a 1e-6 input perturbation moves the flow by 1e-2 voxels, measured),
+    so CPU-recorded goldens cannot pin a GPU run; they pin the CPU oracle (test_flow_register_port_matches_reference)."""
+    import torchregister_b200 as tr
+    from test_oracle_golden import _flowreg_state, cpu_flow_loop
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = load_golden("flowreg2d")
+    mov, tgt = torch.from_numpy(g["moving"]), torch.from_numpy(g["target"])
+    ref_losses, ref_flow, ref_sd, ref_flows = cpu_flow_loop(mov, tgt, _flowreg_state(g), int(g["n"]), 1e-3, epochs, loss_fn, device=DEV)
+    fr = tr.flow_register(tuple(mov.shape[2:]), mode="bilinear", n=int(g["n"]), lr=1e-3, max_epochs=1,
+                          criterions=criterions, weights=weights)
+    fr.load_state_dict(_flowreg_state(g), strict=True)
+    fr = fr.to(DEV)
+    # epoch 0: identical network and weights on both sides -> identical flow; loss and the parameter
+    # update differ only through our warp/similarity/gradient node
+    fr.optimize(mov.to(DEV), tgt.to(DEV), DEV, debug=False)
+    assert abs(fr.losses[0] - ref_losses[0]) <= 1e-4 * abs(ref_losses[0]), (fr.losses, ref_losses)   # torch fp32 NCC reductions
+    assert torch.equal(fr.flow.detach(), ref_flows[0])
+    sd = fr.state_dict()
+    _, _, sd1, _ = cpu_flow_loop(mov, tgt, _flowreg_state(g), int(g["n"]), 1e-3, 1, loss_fn, device=DEV)
+    num = den = 0.0
+    worst = 0.0
+    for k, v in sd1.items():
+        d_ref = (v - _flowreg_state(g)["model." + k].to(DEV)).double()
+        d_got = (sd["model." + k] - _flowreg_state(g)["model." + k].to(DEV)).double()
+        num += ((d_got - d_ref) ** 2).sum().item()
+        den += (d_ref ** 2).sum().item()
+        if d_ref.abs().max().item() > 0:
+            worst = max(worst, ((d_got - d_ref).abs().max() / d_ref.abs().max()).item())
+    rel = (num / den) ** 0.5
+    # the U-Net backward amplifies the ~1e-6 relative differences between our dflow and torch's (ill-conditioned
+    # InstanceNorm, see above): aggregate step error 1e-3, worst single tensor a few 1e-3 (measured 5.7e-3)
+    assert rel <= 3e-3 and worst <= 3e-2, "parameter step vs device oracle: L2 %.2e, worst tensor %.2e" % (rel, worst)
+    return fr
+
+
+def test_flow_register_fused_node_vs_device_oracle():
+    import torch.nn as nn
+    import torchregister_b200 as tr
+    from oracle import torch_port as tp
+    fr = _flow_register_vs_device_oracle([nn.MSELoss(), tr.NCCLoss()], [0.5, 0.5],
+                                         lambda t, y: tp.weighted_loss(t, y, (0.5, 0.5, 0.0)))
+    g = load_golden("flowreg2d")
+    exact = tr.functional.warp_flow(torch.from_numpy(g["moving"]).to(DEV), torch.from_numpy(g["flow"]).to(DEV)).cpu().numpy()
+    assert np.abs(exact - g["deformed"]).max() < 1e-5      # deform() at the REFERENCE's recorded flow
+    assert tuple(fr.deform(torch.from_numpy(g["moving"]).to(DEV)).shape) == g["deformed"].shape
+
+
+def test_flow_register_user_criterion_route():
+    """A criterion the fused node does not know (L1) goes through the differentiable SpatialTransformer
+    (trb_warp_flow + trb_warp_flow_vjp), as the reference honours user criteria in flow mode."""
+    import torch.nn as nn
+    _flow_register_vs_device_oracle([nn.L1Loss(), nn.MSELoss()], [0.7, 0.3],
+                                    lambda t, y: 0.7 * nn.L1Loss()(t, y) + 0.3 * nn.MSELoss()(t, y))
+
+
+def test_register_flow_mode_api():
+    import torch.nn as nn
+    import torchregister_b200 as tr
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((160, 160), "flow")
+    torch.manual_seed(0)
+    reg = tr.Register(mode="flow", device=DEV, criterion=[nn.MSELoss(), tr.NCCLoss()], weight=[0.5, 0.5])
+    reg.optim(mov, tgt, lr=1e-3, max_epochs=2, n=32)
+    assert tuple(reg.theta.shape) == (1, 2, 160, 160)
+    two = torch.cat([mov, 0.5 * tgt], dim=1)
+    out = reg(two)
+    assert tuple(out.shape) == (1, 2, 160, 160) and torch.isfinite(out).all()
+    with pytest.raises(NotImplementedError, match="NMI"):
+        tr.Register(mode="flow", device=DEV).optim(mov, tgt, max_epochs=1)

@@ -143,3 +143,39 @@ def test_base_coordinate_tables_match_torch():
     vol = np.random.default_rng(0).random((6, 5, 7)).astype(np.float32)
     out = co.warp_affine(vol, np.eye(3, 4, dtype=np.float32))
     assert np.abs(out - vol).max() < 2e-5
+
+
+def _flowreg_state(g):
+    return {k[4:]: torch.from_numpy(v) for k, v in g.items() if k.startswith("sd::")}
+
+
+def cpu_flow_loop(mov, tgt, sd, n, lr, epochs, loss_fn, device="cpu"):
+    """Oracle for reference flow_register.optimize (warpings.py:198-233): the U-Net mirror (bit-equal to the
+    reference's on CPU, test_unet_matches_reference_when_available) + the torch-port warp + SGD.  With
+    device='cuda' it is what the reference executes for device='cuda' (same torch ops on that device)."""
+    import torchregister_b200 as tr
+    mov, tgt = mov.to(device), tgt.to(device)
+    net = tr.Attention_UNet(tuple(mov.shape[2:]), "bilinear", in_c=1, n=n)
+    net.load_state_dict({k[len("model."):]: v for k, v in sd.items()}, strict=True)     # keys are flow_register's
+    net = net.to(device)
+    opt = torch.optim.SGD(net.parameters(), lr)
+    losses, flows = [], []
+    for _ in range(epochs):
+        opt.zero_grad()
+        flow = net.flow_field(mov, device)
+        err = loss_fn(tgt, tp.flow_warp(mov, flow))
+        err.backward()
+        opt.step()
+        losses.append(err.item())
+        flows.append(flow.detach().clone())
+    return losses, flows[-1], {k: v.detach().clone() for k, v in net.state_dict().items()}, flows
+
+
+def test_flow_register_port_matches_reference():
+    g = load_golden("flowreg2d")
+    mov, tgt = torch.from_numpy(g["moving"]), torch.from_numpy(g["target"])
+    w = g["weights"]
+    losses, flow, _, _ = cpu_flow_loop(mov, tgt, _flowreg_state(g), int(g["n"]), float(g["lr"]), int(g["epochs"]),
+                                       lambda t, y: tp.weighted_loss(t, y, (w[0], w[1], 0.0)))
+    assert _rel(losses, g["losses"]) < 1e-5
+    assert np.abs(flow.numpy() - g["flow"]).max() <= 1e-5 * np.abs(g["flow"]).max()
