@@ -41,6 +41,16 @@ METRIC = "voxel-warps/s fwd+bwd"
 UNIT = "voxel-warps/s"
 
 
+def _traffic():
+    """DRAM bytes per launch of the dominant kernel from the committed ncu capture (profiles/)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            t = json.load(f)
+        return float(t["dram_bytes_read"] + t["dram_bytes_write"]), t["source"]
+    except Exception:
+        return None, None
+
+
 def _peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     try:
@@ -265,6 +275,7 @@ def main():
         return
 
     peak, peak_src = _peaks()
+    traffic, traffic_src = _traffic()
     kernel_s = ms * 1e-3 / K
     achieved = BYTES_PER_VOXEL_WARP * PAIRS_PER_GPU * vox / kernel_s / 1e9
     line = {
@@ -278,7 +289,8 @@ def main():
                         % (er, ea, PAIRS_PER_GPU, n_e2e)},
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": None, "peak_source": peak_src, "kernel": "affine_moments_kernel<3,true>",
+                     "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
+                     "kernel": "trb::affine3d_tma_kernel<40,20,12,4,true> (csrc/affine_tma.cu)",
                      "algorithmic_bytes_per_launch": BYTES_PER_VOXEL_WARP * PAIRS_PER_GPU * vox,
                      "kernel_us": kernel_s * 1e6,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
