@@ -171,6 +171,32 @@ int trb_flow_loss_grad(int ndim, const float *moving_dev, const float *target_de
                        float *loss_dev, float *dflow_dev, float *warped_dev_or_null,
                        void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ---- EXTENSION: direct per-voxel flow optimisation (north_star items 2b/3) ---------------------
+ * No counterpart in the reference (it optimises U-Net weights, warpings.py:178-233, and has no smoothness
+ * term).  One epoch = trb_flow_direct_stats -> [all-reduce of the 6 moments when sharded] ->
+ * trb_flow_direct_update.  loss = w_mse*MSE + w_ncc*100*(1-NCC) + lambda * smooth,
+ * smooth = mean over axes of mean((forward difference of every flow channel)^2).
+ * Slab form (one volume sharded over GPUs by z): target/flow/adam arrays hold slices [z_off, z_off+Ds),
+ * `moving` is the whole volume, halo_lo/halo_hi are the neighbouring ranks' flow slices z_off-1 and
+ * z_off+Ds ([ndim][H][W]; NULL at the volume boundary).  A single GPU passes z_off=0, Ds=D, no halos.
+ * moments6: sum t, sum w, sum t^2, sum w^2, sum t*w, smooth (fp64, overwritten by stats). */
+size_t trb_flow_direct_workspace_bytes(void);
+
+int trb_flow_direct_stats(int ndim, const float *moving_dev, const float *target_slab_dev, const float *flow_slab_dev,
+                          const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                          float smooth_lambda, double *moments6_dev, void *workspace_dev, size_t workspace_bytes,
+                          void *stream);
+
+/* flow_out = optimiser(flow_in, d loss / d flow); out of place (the smoothness stencil reads neighbours).
+ * optimiser TRB_OPT_SGD or TRB_OPT_ADAM (torch.optim.Adam semantics; adam_m/v slab-shaped, step_index 1-based).
+ * loss_log_dev[epoch] receives the loss of flow_in (may be NULL). */
+int trb_flow_direct_update(int ndim, const float *moving_dev, const float *target_slab_dev,
+                           const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                           const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                           const double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                           int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                           float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

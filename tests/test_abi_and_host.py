@@ -82,7 +82,10 @@ def test_register_signature_matches_reference():
     import inspect
     import torchregister_b200 as tr
     sig = inspect.signature(tr.Register.__init__)
-    assert list(sig.parameters)[1:] == ["mode", "device", "criterion", "weight", "grad_edges", "debug"]
+    assert list(sig.parameters)[1:7] == ["mode", "device", "criterion", "weight", "grad_edges", "debug"]
+    extras = list(sig.parameters.values())[7:]
+    assert all(p.kind is inspect.Parameter.KEYWORD_ONLY for p in extras)      # extensions never shift positions
+    assert sig.parameters["flow_param"].default == "unet" and sig.parameters["optm"].default == "SGD"
     assert sig.parameters["mode"].default == "rigid" and sig.parameters["device"].default == "cpu"
     osig = inspect.signature(tr.Register.optim)
     names = list(osig.parameters)[1:7]

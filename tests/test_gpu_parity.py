@@ -359,3 +359,64 @@ def test_register_flow_mode_api():
     assert tuple(out.shape) == (1, 2, 160, 160) and torch.isfinite(out).all()
     with pytest.raises(NotImplementedError, match="NMI"):
         tr.Register(mode="flow", device=DEV).optim(mov, tgt, max_epochs=1)
+
+
+# --------------------------------------------------------------------------------------------
+# EXTENSION: direct per-voxel flow (oracle: oracle/torch_port.direct_flow_loop, parity unpinned by the reference)
+# --------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("shape,opt,smooth,weights", [((20, 24, 28), "sgd", 0.0, (1.0, 0.0)), ((20, 24, 28), "sgd", 5.0, (0.5, 0.5)),
+                                                      ((20, 24, 28), "adam", 5.0, (0.5, 0.5)), ((40, 48), "adam", 2.0, (0.0, 1.0))])
+def test_direct_flow_vs_torch_restatement(shape, opt, smooth, weights):
+    TF = _tf()
+    from oracle import torch_port as tp
+    from torchregister_b200.synth import make_pair, smooth_flow
+    mov, tgt = make_pair(shape, "flow")
+    flow0 = 0.3 * smooth_flow(shape, 1.0)          # off-lattice start (see DESIGN.md on lattice starts)
+    lr = 0.5 if opt == "sgd" else 0.05
+    epochs = 5
+    ref = tp.direct_flow_loop(mov.double(), tgt.double(), lr, epochs, (weights[0], weights[1], 0.0), smooth, opt, flow0=flow0.double())
+    ref32 = tp.direct_flow_loop(mov, tgt, lr, epochs, (weights[0], weights[1], 0.0), smooth, opt, flow0=flow0)
+    prob = TF.DirectFlowProblem(mov.to(DEV), tgt.to(DEV), epochs, flow0=flow0, optimiser=opt)
+    prob.run(epochs, lr, weights[0], weights[1], smooth)
+    ok, worst = _loss_ok(prob.losses.cpu().numpy(), ref32["losses"], ref["losses"])
+    assert ok, (worst, prob.losses.cpu().numpy(), ref["losses"])
+    d = (prob.flow.cpu().double() - ref["flow"]).abs().max().item()
+    step = (ref["flow"] - flow0.double()).abs().max().item()
+    gap32 = (ref32["flow"].double() - ref["flow"]).abs().max().item()
+    assert d <= max(1e-4 * step, 2 * gap32), (d, step, gap32)
+
+
+def test_direct_flow_slabs_equal_whole_volume():
+    """The slab form with explicit halos (what ShardedDirectFlow drives across GPUs) on one GPU."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair, smooth_flow
+    shape = (18, 20, 24)
+    mov, tgt = (t.to(DEV) for t in make_pair(shape, "flow"))
+    flow0 = (0.3 * smooth_flow(shape, 1.0)).to(DEV)
+    whole = TF.DirectFlowProblem(mov, tgt, 3, flow0=flow0, optimiser="adam")
+    whole.run(3, 0.05, 0.5, 0.5, 4.0)
+    cuts = [(0, 7), (7, 12), (12, 18)]
+    slabs = [TF.DirectFlowProblem(mov, tgt[:, :, a:b].contiguous(), 3, z_off=a, flow0=flow0[:, :, a:b].contiguous(), optimiser="adam")
+             for a, b in cuts]
+    for _ in range(3):
+        bounds = [s.boundary_slices() for s in slabs]
+        halos = [(bounds[i - 1][1] if i > 0 else None, bounds[i + 1][0] if i < len(slabs) - 1 else None) for i in range(len(slabs))]
+        total = sum(s.stats(4.0, *halos[i]).clone() for i, s in enumerate(slabs))
+        for i, s in enumerate(slabs):
+            s.moments.copy_(total)
+            s.update(0.05, 0.5, 0.5, 4.0, *halos[i])
+    got = torch.cat([s.flow for s in slabs], dim=2)
+    assert torch.allclose(got, whole.flow, atol=1e-6)
+    assert torch.allclose(slabs[0].losses, whole.losses, rtol=1e-6)
+
+
+def test_register_direct_flow_extension():
+    import torchregister_b200 as tr
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((24, 28, 32), "flow")
+    reg = tr.Register(mode="flow", device=DEV, weight=[0.5, 0.5, 0.0], flow_param="direct", smooth=2.0, optm="ADAM")
+    reg.optim(mov, tgt, lr=0.05, max_epochs=30)
+    assert tuple(reg.theta.shape) == (1, 3, 24, 28, 32)
+    assert reg.losses[-1] < reg.losses[0]
+    out = reg(torch.cat([mov, mov], 1))
+    assert tuple(out.shape) == (1, 2, 24, 28, 32)

@@ -1,0 +1,327 @@
+// flow_direct.cu — EXTENSION (north_star items 2b/3; BASELINE configs[2] "direct" variant and configs[4]):
+// direct per-voxel flow optimisation.  The reference optimises the weights of a U-Net whose output is the
+// flow (warpings.py:178-233); there is no per-voxel flow optimiser and no smoothness term in it, so this
+// path has no reference counterpart — its oracle is oracle/torch_port.py:direct_flow_loop, assembled from
+// the reference's own SpatialTransformer (utils.py:350-365) + MSE/NCC (utils.py:197-205) + torch SGD/Adam +
+// a VoxelMorph-style smoothness penalty (mean over axes of the mean squared forward difference).
+//
+// One epoch = two streaming passes over a z-slab of the volume:
+//   stats : warp(moving, flow) -> 5 similarity moments + the smoothness sum            (20 B/voxel + halo)
+//   update: same sample + derivative, dL/dflow = (cw*w + ct*t + c0)*G + lambda*stencil, SGD or Adam,
+//           written out of place (32 B/voxel SGD, 80 B/voxel Adam)
+// Between the passes the caller all-reduces the 6 moments when the volume is sharded over GPUs
+// (parallel.ShardedDirectFlow); on one GPU trb_flow_direct_epoch chains both.
+// Layout of a slab: flow/adam [ndim][Ds][H][W], target [Ds][H][W] hold slices [z_off, z_off+Ds) of the
+// volume; `moving` is the full [D][H][W] volume; halo_lo / halo_hi are the neighbour ranks' flow slices
+// z_off-1 and z_off+Ds ([ndim][H][W]) or NULL at the volume boundary.
+#include "common.cuh"
+
+namespace trb {
+
+struct DirectParams {
+    const float *moving, *target, *flow_in, *halo_lo, *halo_hi;
+    float *flow_out, *adam_m, *adam_v, *loss_log;
+    int D, H, W, z_off, Ds;
+    double *moments;        // [6]
+    double *partials;       // [blocks][6]
+    unsigned *ticket;
+    float w_mse, w_ncc, lambda, lr;
+    int optimiser, step, epoch;
+    float beta1, beta2, eps;
+};
+
+__device__ __forceinline__ float dflow_pos(int S, int i, float f)
+{
+    const float loc = (float)i + f;
+    const float nrm = 2.f * (__fdiv_rn(loc, (float)(S - 1)) - 0.5f);
+    return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.f), 0.5f), (float)(S - 1));
+}
+
+template <int NDIM>
+__device__ __forceinline__ void sample3(const float *__restrict__ m, int D, int H, int W, float px, float py, float pz,
+                                        float &val, float (&g)[3])
+{
+    const float fx = floorf(px), fy = floorf(py);
+    const float tx = px - fx, ty = py - fy;
+    const int x0 = (int)fx, y0 = (int)fy;
+    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    if (NDIM == 3) {
+        const float fz = floorf(pz);
+        const float tz = pz - fz;
+        const int z0 = (int)fz;
+        const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+        const long long HW = (long long)H * W, o = ((long long)z0 * H + y0) * W + x0;
+        const float c000 = (vz0 & vy0 & vx0) ? __ldg(m + o) : 0.f, c001 = (vz0 & vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
+        const float c010 = (vz0 & vy1 & vx0) ? __ldg(m + o + W) : 0.f, c011 = (vz0 & vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
+        const float c100 = (vz1 & vy0 & vx0) ? __ldg(m + o + HW) : 0.f, c101 = (vz1 & vy0 & vx1) ? __ldg(m + o + HW + 1) : 0.f;
+        const float c110 = (vz1 & vy1 & vx0) ? __ldg(m + o + HW + W) : 0.f, c111 = (vz1 & vy1 & vx1) ? __ldg(m + o + HW + W + 1) : 0.f;
+        const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+        const float v00 = fmaf(tx, d00, c000), v01 = fmaf(tx, d01, c010), v10 = fmaf(tx, d10, c100), v11 = fmaf(tx, d11, c110);
+        const float e0 = v01 - v00, e1 = v11 - v10;
+        const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
+        g[2] = w1 - w0;
+        val = fmaf(tz, g[2], w0);
+        g[1] = fmaf(tz, e1 - e0, e0);
+        const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
+        g[0] = fmaf(tz, dx1 - dx0, dx0);
+    } else {
+        const long long o = (long long)y0 * W + x0;
+        const float c00 = (vy0 & vx0) ? __ldg(m + o) : 0.f, c01 = (vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
+        const float c10 = (vy1 & vx0) ? __ldg(m + o + W) : 0.f, c11 = (vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
+        const float d0 = c01 - c00, d1 = c11 - c10;
+        const float v0 = fmaf(tx, d0, c00), v1 = fmaf(tx, d1, c10);
+        g[1] = v1 - v0;
+        val = fmaf(ty, g[1], v0);
+        g[0] = fmaf(ty, d1 - d0, d0);
+        g[2] = 0.f;
+    }
+}
+
+// flow value of channel c at slab-local (zl, y, x) with zl in [-1, Ds] resolved through the halos
+template <int NDIM>
+__device__ __forceinline__ float flow_at(const DirectParams &p, int c, int zl, int y, int x)
+{
+    const size_t HW = (size_t)p.H * p.W;
+    if (NDIM == 3) {
+        if (zl < 0) return __ldg(p.halo_lo + (size_t)c * HW + (size_t)y * p.W + x);
+        if (zl >= p.Ds) return __ldg(p.halo_hi + (size_t)c * HW + (size_t)y * p.W + x);
+        return __ldg(p.flow_in + ((size_t)c * p.Ds + zl) * HW + (size_t)y * p.W + x);
+    }
+    return __ldg(p.flow_in + (size_t)c * HW + (size_t)y * p.W + x);
+}
+
+// weight of one squared forward difference along axis a in  mean_axes( mean(diff^2) )
+template <int NDIM>
+__device__ __forceinline__ float smooth_weight(const DirectParams &p, int a)
+{
+    const double dims[3] = {(double)p.W, (double)p.H, (double)(NDIM == 3 ? p.D : 1)};
+    double n = (double)NDIM;                   // channels
+    for (int k = 0; k < NDIM; ++k) n *= (k == a) ? dims[k] - 1.0 : dims[k];
+    return (float)(1.0 / (n * NDIM));
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectParams p)
+{
+    const int W = p.W, H = p.H, D = NDIM == 3 ? p.D : 1, Ds = NDIM == 3 ? p.Ds : 1;
+    const size_t HW = (size_t)H * W, slab = HW * Ds;
+    const float wx = smooth_weight<NDIM>(p, 0), wy = smooth_weight<NDIM>(p, 1), wz = NDIM == 3 ? smooth_weight<NDIM>(p, 2) : 0.f;
+    double acc[6] = {0, 0, 0, 0, 0, 0};
+    float s[6] = {0, 0, 0, 0, 0, 0};
+    int cnt = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < slab; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        const size_t q = idx / W;
+        const int y = (int)(q % H), zl = (int)(q / H), z = p.z_off + zl;
+        float f[3] = {0.f, 0.f, 0.f};          // f[c]: channel c displaces spatial axis c (0 = D|H first axis)
+#pragma unroll
+        for (int c = 0; c < NDIM; ++c) f[c] = ld_stream_f(p.flow_in + (size_t)c * slab + idx);
+        float px, py, pz = 0.f;
+        if (NDIM == 3) { pz = dflow_pos(D, z, f[0]); py = dflow_pos(H, y, f[1]); px = dflow_pos(W, x, f[2]); }
+        else { py = dflow_pos(H, y, f[0]); px = dflow_pos(W, x, f[1]); }
+        float val, g[3];
+        sample3<NDIM>(p.moving, D, H, W, px, py, pz, val, g);
+        const float t = ld_stream_f(p.target + idx);
+        s[0] += t; s[1] += val;
+        s[2] = fmaf(t, t, s[2]); s[3] = fmaf(val, val, s[3]); s[4] = fmaf(t, val, s[4]);
+        if (p.lambda != 0.f) {
+            float sm = 0.f;
+#pragma unroll
+            for (int c = 0; c < NDIM; ++c) {
+                if (x + 1 < W) { const float d = flow_at<NDIM>(p, c, zl, y, x + 1) - f[c]; sm = fmaf(wx * d, d, sm); }
+                if (y + 1 < H) { const float d = flow_at<NDIM>(p, c, zl, y + 1, x) - f[c]; sm = fmaf(wy * d, d, sm); }
+                if (NDIM == 3 && z + 1 < D) { const float d = flow_at<NDIM>(p, c, zl + 1, y, x) - f[c]; sm = fmaf(wz * d, d, sm); }
+            }
+            s[5] += sm;
+        }
+        if (++cnt == 64) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) { acc[i] += (double)s[i]; s[i] = 0.f; }
+            cnt = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < 6; ++i) acc[i] += (double)s[i];
+    __shared__ double red[8][6];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum(acc[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        __stcg(p.partials + (size_t)blockIdx.x * 6 + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < 6) {
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(p.partials + (size_t)b * 6 + warp);
+        v = warp_sum(v);
+        if (lane == 0) p.moments[warp] = v;
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+template <int NDIM>
+__global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectParams p)
+{
+    const int W = p.W, H = p.H, D = NDIM == 3 ? p.D : 1, Ds = NDIM == 3 ? p.Ds : 1;
+    const size_t HW = (size_t)H * W, slab = HW * Ds;
+    __shared__ float coef[3];
+    if (threadIdx.x == 0) {
+        const double n = (double)D * H * W;
+        const LossCoef lc = loss_coefficients(n, p.moments[0], p.moments[1], p.moments[2], p.moments[3], p.moments[4],
+                                              (double)p.w_mse, (double)p.w_ncc);
+        coef[0] = (float)lc.cw; coef[1] = (float)lc.ct; coef[2] = (float)lc.c0;
+        if (blockIdx.x == 0 && p.loss_log) p.loss_log[p.epoch] = (float)(lc.loss + (double)p.lambda * p.moments[5]);
+    }
+    __syncthreads();
+    const float cw = coef[0], ct = coef[1], c0 = coef[2];
+    const float sw[3] = {2.f * p.lambda * smooth_weight<NDIM>(p, 0), 2.f * p.lambda * smooth_weight<NDIM>(p, 1),
+                         NDIM == 3 ? 2.f * p.lambda * smooth_weight<NDIM>(p, 2) : 0.f};
+    float bc1 = 1.f, bc2s = 1.f;
+    if (p.optimiser == TRB_OPT_ADAM) {
+        bc1 = 1.f - powf(p.beta1, (float)p.step);
+        bc2s = sqrtf(1.f - powf(p.beta2, (float)p.step));
+    }
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < slab; idx += (size_t)gridDim.x * blockDim.x) {
+        const int x = (int)(idx % W);
+        const size_t q = idx / W;
+        const int y = (int)(q % H), zl = (int)(q / H), z = p.z_off + zl;
+        float f[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < NDIM; ++c) f[c] = ld_stream_f(p.flow_in + (size_t)c * slab + idx);
+        float px, py, pz = 0.f;
+        if (NDIM == 3) { pz = dflow_pos(D, z, f[0]); py = dflow_pos(H, y, f[1]); px = dflow_pos(W, x, f[2]); }
+        else { py = dflow_pos(H, y, f[0]); px = dflow_pos(W, x, f[1]); }
+        float val, g[3];
+        sample3<NDIM>(p.moving, D, H, W, px, py, pz, val, g);
+        const float t = ld_stream_f(p.target + idx);
+        const float r = fmaf(cw, val, fmaf(ct, t, c0));
+#pragma unroll
+        for (int c = 0; c < NDIM; ++c) {
+            float gr = r * g[NDIM - 1 - c];          // channel c <-> sampling coordinate NDIM-1-c
+            if (p.lambda != 0.f) {
+                float st = 0.f;
+                if (x + 1 < W) st -= sw[0] * (flow_at<NDIM>(p, c, zl, y, x + 1) - f[c]);
+                if (x > 0) st += sw[0] * (f[c] - flow_at<NDIM>(p, c, zl, y, x - 1));
+                if (y + 1 < H) st -= sw[1] * (flow_at<NDIM>(p, c, zl, y + 1, x) - f[c]);
+                if (y > 0) st += sw[1] * (f[c] - flow_at<NDIM>(p, c, zl, y - 1, x));
+                if (NDIM == 3) {
+                    if (z + 1 < D) st -= sw[2] * (flow_at<NDIM>(p, c, zl + 1, y, x) - f[c]);
+                    if (z > 0) st += sw[2] * (f[c] - flow_at<NDIM>(p, c, zl - 1, y, x));
+                }
+                gr += st;
+            }
+            const size_t o = (size_t)c * slab + idx;
+            float nv;
+            if (p.optimiser == TRB_OPT_SGD) {
+                nv = f[c] - p.lr * gr;
+            } else {
+                float m = p.adam_m[o], v = p.adam_v[o];
+                m = p.beta1 * m + (1.f - p.beta1) * gr;
+                v = p.beta2 * v + (1.f - p.beta2) * gr * gr;
+                p.adam_m[o] = m; p.adam_v[o] = v;
+                nv = f[c] - (p.lr / bc1) * (m / (sqrtf(v) / bc2s + p.eps));
+            }
+            p.flow_out[o] = nv;
+        }
+    }
+}
+
+constexpr int kDirectMaxBlocks = 4096;
+
+static unsigned direct_grid(size_t n)
+{
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    size_t nb = (n + 255) / 256;
+    const size_t cap = (size_t)sms * 8;
+    if (nb > cap) nb = cap;
+    if (nb > kDirectMaxBlocks) nb = kDirectMaxBlocks;
+    return (unsigned)(nb < 1 ? 1 : nb);
+}
+
+static int fill_direct(DirectParams &p, int ndim, const float *moving, const float *target, const float *flow_in,
+                       const float *halo_lo, const float *halo_hi, int D, int H, int W, int z_off, int Ds,
+                       double *moments, void *ws, size_t ws_bytes)
+{
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
+    if (H < 2 || W < 2 || (ndim == 3 && D < 2)) { set_error("flow needs every axis >= 2"); return TRB_ERR_ARG; }
+    if (!moving || !target || !flow_in || !moments) { set_error("null pointer"); return TRB_ERR_ARG; }
+    if (ndim == 3 && (z_off < 0 || Ds < 1 || z_off + Ds > D)) { set_error("bad slab [%d,%d) of %d", z_off, z_off + Ds, D); return TRB_ERR_ARG; }
+    if (ndim == 3 && ((z_off > 0 && !halo_lo) || (z_off + Ds < D && !halo_hi))) { set_error("interior slab needs both halos"); return TRB_ERR_ARG; }
+    if (!ws || ws_bytes < (size_t)(kDirectMaxBlocks * 6 + 2) * sizeof(double)) { set_error("workspace too small"); return TRB_ERR_WORKSPACE; }
+    p.moving = moving; p.target = target; p.flow_in = flow_in; p.halo_lo = halo_lo; p.halo_hi = halo_hi;
+    p.D = ndim == 3 ? D : 1; p.H = H; p.W = W; p.z_off = ndim == 3 ? z_off : 0; p.Ds = ndim == 3 ? Ds : 1;
+    p.moments = moments;
+    p.partials = (double *)ws + 2;
+    p.ticket = (unsigned *)ws;
+    return TRB_OK;
+}
+
+}  // namespace trb
+
+using namespace trb;
+
+extern "C" size_t trb_flow_direct_workspace_bytes(void) { return (size_t)(kDirectMaxBlocks * 6 + 2) * sizeof(double); }
+
+extern "C" int trb_flow_direct_stats(int ndim, const float *moving_dev, const float *target_slab_dev, const float *flow_slab_dev,
+                                     const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                                     float smooth_lambda, double *moments6_dev, void *workspace_dev, size_t workspace_bytes,
+                                     void *stream)
+{
+    DirectParams p{};
+    int rc = fill_direct(p, ndim, moving_dev, target_slab_dev, flow_slab_dev, halo_lo_dev, halo_hi_dev, D, H, W, z_off, Ds,
+                         moments6_dev, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    p.lambda = smooth_lambda;
+    const size_t n = (size_t)p.Ds * H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ndim == 3) flow_direct_stats_kernel<3><<<direct_grid(n), 256, 0, s>>>(p);
+    else flow_direct_stats_kernel<2><<<direct_grid(n), 256, 0, s>>>(p);
+    return check_cuda(cudaGetLastError(), "flow_direct_stats");
+}
+
+extern "C" int trb_flow_direct_update(int ndim, const float *moving_dev, const float *target_slab_dev,
+                                      const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                                      const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                                      const double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                                      int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                                      float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, void *stream)
+{
+    DirectParams p{};
+    double dummy_ws[1];
+    (void)dummy_ws;
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
+    if (!moving_dev || !target_slab_dev || !flow_in_slab_dev || !flow_out_slab_dev || !moments6_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    if (flow_in_slab_dev == flow_out_slab_dev) { set_error("update is out of place: flow_out must differ from flow_in"); return TRB_ERR_ARG; }
+    if (optimiser != TRB_OPT_SGD && optimiser != TRB_OPT_ADAM) { set_error("bad optimiser"); return TRB_ERR_ARG; }
+    if (optimiser == TRB_OPT_ADAM && (!adam_m_dev || !adam_v_dev || step_index < 1)) { set_error("Adam needs m, v and step_index >= 1"); return TRB_ERR_ARG; }
+    if (ndim == 3 && (z_off < 0 || Ds < 1 || z_off + Ds > D)) { set_error("bad slab"); return TRB_ERR_ARG; }
+    if (ndim == 3 && smooth_lambda != 0.f && ((z_off > 0 && !halo_lo_dev) || (z_off + Ds < D && !halo_hi_dev))) { set_error("interior slab needs both halos"); return TRB_ERR_ARG; }
+    p.moving = moving_dev; p.target = target_slab_dev; p.flow_in = flow_in_slab_dev; p.flow_out = flow_out_slab_dev;
+    p.halo_lo = halo_lo_dev; p.halo_hi = halo_hi_dev;
+    p.D = ndim == 3 ? D : 1; p.H = H; p.W = W; p.z_off = ndim == 3 ? z_off : 0; p.Ds = ndim == 3 ? Ds : 1;
+    p.moments = const_cast<double *>(moments6_dev);
+    p.w_mse = w_mse; p.w_ncc = w_ncc; p.lambda = smooth_lambda; p.lr = lr;
+    p.optimiser = optimiser; p.beta1 = beta1; p.beta2 = beta2; p.eps = adam_eps; p.step = step_index;
+    p.adam_m = adam_m_dev; p.adam_v = adam_v_dev; p.loss_log = loss_log_dev; p.epoch = epoch;
+    const size_t n = (size_t)p.Ds * H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    if (ndim == 3) flow_direct_update_kernel<3><<<direct_grid(n), 256, 0, s>>>(p);
+    else flow_direct_update_kernel<2><<<direct_grid(n), 256, 0, s>>>(p);
+    return check_cuda(cudaGetLastError(), "flow_direct_update");
+}

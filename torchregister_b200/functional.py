@@ -298,3 +298,79 @@ def flow_loss_grad(moving: torch.Tensor, target: torch.Tensor, flow: torch.Tenso
                                      float(w_ncc), loss.data_ptr(), dflow.data_ptr(), _ptr(warped),
                                      ws.data_ptr(), ws.numel(), _stream(dev)), "flow_loss_grad")
     return loss, dflow, warped
+
+
+# --------------------------------------------------------------------------- #
+# EXTENSION: direct per-voxel flow optimisation (no reference counterpart)
+# --------------------------------------------------------------------------- #
+class DirectFlowProblem:
+    """Per-voxel flow field optimised with SGD or Adam on
+    loss = w_mse*MSE + w_ncc*100*(1-NCC) + smooth * mean_axes(mean(forward_diff(flow)^2)).
+
+    Holds a z-slab [z_off, z_off+Ds) of the target/flow (the whole volume by default); `moving` is always the
+    full volume.  One epoch = stats pass -> (all-reduce hook) -> update pass, ping-ponging two flow buffers.
+    """
+
+    def __init__(self, moving, target_slab, max_epochs, z_off=0, flow0=None, optimiser="sgd"):
+        require_cuda(moving, "moving")
+        require_cuda(target_slab, "target")
+        self.lib = _lib.load()
+        self.device = moving.device
+        self.ndim, self.D, self.H, self.W = _vol_dims(moving)
+        if moving.shape[0] != 1 or moving.shape[1] != 1:
+            raise ValueError("direct flow expects [1,1,...] volumes")
+        self.moving = moving.contiguous()
+        self.target = target_slab.contiguous()
+        self.Ds = int(target_slab.shape[2]) if self.ndim == 3 else 1
+        self.z_off = int(z_off) if self.ndim == 3 else 0
+        if tuple(target_slab.shape[-2:]) != (self.H, self.W):
+            raise ValueError("target slab must share H, W with moving")
+        shape = (1, self.ndim) + tuple(self.target.shape[2:])
+        self.flow = (torch.zeros(shape, dtype=torch.float32, device=self.device) if flow0 is None
+                     else flow0.detach().to(self.device, torch.float32).contiguous().clone())
+        if tuple(self.flow.shape) != shape:
+            raise ValueError("flow0 must have shape %s" % (shape,))
+        self._other = torch.empty_like(self.flow)
+        self.optimiser = optimiser
+        self.adam_m = torch.zeros_like(self.flow) if optimiser == "adam" else None
+        self.adam_v = torch.zeros_like(self.flow) if optimiser == "adam" else None
+        self.moments = torch.zeros(6, dtype=torch.float64, device=self.device)
+        self.loss_log = torch.zeros(max(int(max_epochs), 1), dtype=torch.float32, device=self.device)
+        self.workspace = torch.zeros(int(self.lib.trb_flow_direct_workspace_bytes()), dtype=torch.uint8, device=self.device)
+        self.max_epochs = int(max_epochs)
+        self.epoch = 0
+
+    def boundary_slices(self):
+        """(first, last) z-slices of the current flow, [ndim, H, W] each — what the neighbours need as halos."""
+        return self.flow[0, :, 0].contiguous(), self.flow[0, :, -1].contiguous()
+
+    def stats(self, smooth, halo_lo=None, halo_hi=None):
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_flow_direct_stats(
+                self.ndim, self.moving.data_ptr(), self.target.data_ptr(), self.flow.data_ptr(), _ptr(halo_lo), _ptr(halo_hi),
+                self.D, self.H, self.W, self.z_off, self.Ds, float(smooth), self.moments.data_ptr(),
+                self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "flow_direct_stats")
+        return self.moments
+
+    def update(self, lr, w_mse, w_ncc, smooth, halo_lo=None, halo_hi=None, betas=(0.9, 0.999), eps=1e-8):
+        if self.epoch >= self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_flow_direct_update(
+                self.ndim, self.moving.data_ptr(), self.target.data_ptr(), self.flow.data_ptr(), self._other.data_ptr(),
+                _ptr(halo_lo), _ptr(halo_hi), self.D, self.H, self.W, self.z_off, self.Ds, self.moments.data_ptr(),
+                float(w_mse), float(w_ncc), float(smooth), float(lr), OPT[self.optimiser], float(betas[0]), float(betas[1]),
+                float(eps), self.epoch + 1, _ptr(self.adam_m), _ptr(self.adam_v), self.loss_log.data_ptr(), self.epoch,
+                _stream(self.device)), "flow_direct_update")
+        self.flow, self._other = self._other, self.flow
+        self.epoch += 1
+
+    def run(self, n_epochs, lr, w_mse, w_ncc, smooth=0.0, betas=(0.9, 0.999), eps=1e-8):
+        """Single-GPU epochs (whole volume in this problem): no host synchronisation."""
+        for _ in range(n_epochs):
+            self.stats(smooth)
+            self.update(lr, w_mse, w_ncc, smooth, betas=betas, eps=eps)
+
+    @property
+    def losses(self):
+        return self.loss_log[: self.epoch]

@@ -14,7 +14,7 @@ from typing import List, Optional, Tuple
 import torch
 import torch.distributed as dist
 
-__all__ = ["shard_pairs", "slab_range", "allreduce_moments", "ShardedAffine"]
+__all__ = ["shard_pairs", "slab_range", "allreduce_moments", "ShardedAffine", "ShardedDirectFlow"]
 
 
 def shard_pairs(n_pairs: int, world: int, rank: int) -> Tuple[int, int]:
@@ -66,6 +66,55 @@ class ShardedAffine:
     @property
     def best_theta(self):
         return self.prob.best_theta
+
+    @property
+    def losses(self):
+        return self.prob.losses
+
+
+class ShardedDirectFlow:
+    """EXTENSION: direct per-voxel flow registration of ONE large volume split into z-slabs over the ranks
+    (BASELINE configs[4]).  Each rank owns the target/flow/optimiser slab [z0, z1); the moving volume is
+    replicated.  Per epoch: exchange ONE boundary slice of the flow with each neighbour (the smoothness stencil
+    and nothing else crosses slabs), stats pass, all-reduce of the 6 loss moments, update pass."""
+
+    def __init__(self, moving, target, max_epochs, optimiser="sgd", group=None):
+        from . import functional as TF
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.rank = dist.get_rank(group) if dist.is_initialized() else 0
+        D = int(moving.shape[2])
+        self.z0, self.z1 = slab_range(D, self.world, self.rank)
+        self.prob = TF.DirectFlowProblem(moving, target[:, :, self.z0:self.z1].contiguous(), max_epochs,
+                                         z_off=self.z0, optimiser=optimiser)
+        nd, H, W = self.prob.ndim, self.prob.H, self.prob.W
+        dev = self.prob.device
+        self.halo_lo = torch.zeros(nd, H, W, device=dev) if self.rank > 0 else None
+        self.halo_hi = torch.zeros(nd, H, W, device=dev) if self.rank < self.world - 1 else None
+
+    def _exchange(self):
+        if self.world == 1:
+            return
+        first, last = self.prob.boundary_slices()
+        ops = []
+        if self.rank > 0:
+            ops += [dist.P2POp(dist.isend, first, self.rank - 1, self.group), dist.P2POp(dist.irecv, self.halo_lo, self.rank - 1, self.group)]
+        if self.rank < self.world - 1:
+            ops += [dist.P2POp(dist.isend, last, self.rank + 1, self.group), dist.P2POp(dist.irecv, self.halo_hi, self.rank + 1, self.group)]
+        for req in dist.batch_isend_irecv(ops):
+            req.wait()
+
+    def run(self, n_epochs, lr, w_mse, w_ncc, smooth=0.0, betas=(0.9, 0.999), eps=1e-8):
+        for _ in range(n_epochs):
+            if smooth:
+                self._exchange()
+            m = self.prob.stats(smooth, self.halo_lo, self.halo_hi)
+            allreduce_moments(m, self.group)
+            self.prob.update(lr, w_mse, w_ncc, smooth, self.halo_lo, self.halo_hi, betas, eps)
+
+    @property
+    def flow_slab(self):
+        return self.prob.flow
 
     @property
     def losses(self):

@@ -7,11 +7,12 @@ from __future__ import annotations
 
 from torch import cat
 
-from .warpings import flow_register, affine_register, rigid_register, get_affine_warp
+from .warpings import flow_register, direct_flow_register, affine_register, rigid_register, get_affine_warp
 
 
 class Register():
-    def __init__(self, mode='rigid', device='cpu', criterion=None, weight=None, grad_edges=False, debug=False):
+    def __init__(self, mode='rigid', device='cpu', criterion=None, weight=None, grad_edges=False, debug=False, *,
+                 flow_param='unet', smooth=0.0, optm='SGD'):
         '''
         B200 registration with the reference's interface (torchregister.py:12-44).
 
@@ -25,6 +26,9 @@ class Register():
             weight alone re-weights the default [MSE, NCC, NMI] terms. NOTE the reference ignores a
             user criterion in rigid/affine mode and uses MSE (warpings.py:38-40,125-127); so do we.
         grad_edges, debug : as in the reference.
+        flow_param, smooth, optm : keyword-only EXTENSIONS with reference-preserving defaults. flow_param='direct'
+            optimises the dense flow itself (SGD or optm='ADAM') with a smoothness weight `smooth` instead of the
+            reference's U-Net parametrisation ('unet').
         '''
         self.criterion = criterion
         self.weight = weight
@@ -35,6 +39,7 @@ class Register():
         self.theta = None
         self.grad_edges = grad_edges
         self.losses = None
+        self.flow_param, self.smooth, self.optm = flow_param, smooth, optm
 
     def _check_device(self):
         import torch
@@ -53,7 +58,19 @@ class Register():
         moving = moving.to(self.device)
         target = target.to(self.device)
         both = self.criterion is not None and self.weight is not None
-        if self.mode == 'flow':
+        if self.mode == 'flow' and self.flow_param == 'direct':
+            kw = dict(lr=lr, max_epochs=max_epochs, smooth=self.smooth, optimiser=self.optm)
+            if both:
+                kw.update(criterions=self.criterion, weights=self.weight)
+            elif self.weight is not None:
+                kw.update(weights=self.weight)
+            flowreg = direct_flow_register(target.shape[2:], **kw)
+            flowreg.optimize(moving, target, self.device, self.debug)
+            self.theta = flowreg.flow
+            self.warp = flowreg.deform
+            self.losses = flowreg.losses
+            self._flowreg = flowreg
+        elif self.mode == 'flow':
             kw = dict(mode='bilinear', n=n, lr=lr, max_epochs=max_epochs)
             if both:
                 kw.update(criterions=self.criterion, weights=self.weight)

@@ -16,7 +16,8 @@ import torch.nn as nn
 from . import functional as TF
 from .utils import Attention_UNet, NCCLoss
 
-__all__ = ["get_affine_warp", "affine_register", "rigid_register", "flow_register", "similarity_weights"]
+__all__ = ["get_affine_warp", "affine_register", "rigid_register", "flow_register", "direct_flow_register",
+           "similarity_weights"]
 
 
 # --------------------------------------------------------------------------- #
@@ -223,3 +224,49 @@ class flow_register(nn.Module):
     def deform(self, x):
         """Warp `x` with the flow of the last forward pass (reference warpings.py:238-242)."""
         return TF.warp_flow(x, self.flow.detach())
+
+
+class direct_flow_register:
+    """EXTENSION (north_star items 2b/3) — no counterpart in the reference: the dense flow itself is the
+    parameter, optimised with SGD or Adam on  sum_i w_i*crit_i(target, warp(moving, flow)) + smooth * R(flow),
+    R = mean over axes of the mean squared forward difference.  Same duck type as `flow_register`
+    (`optimize`, `deform`, `flow`, `losses`) so `Register(mode='flow', flow_param='direct')` can swap it in.
+    Only nn.MSELoss / NCCLoss terms are supported (they are what the fused kernels evaluate)."""
+
+    def __init__(self, img_size, criterions=None, weights=[0.5, 0.5], lr=1E-3, max_epochs=2000, stop_crit=1E-4,
+                 smooth=0.0, optimiser='sgd', betas=(0.9, 0.999), eps=1e-8):
+        if criterions is None:
+            criterions = [nn.MSELoss(), NCCLoss()]
+            if len(weights) >= 3 and weights[2] != 0:
+                raise NotImplementedError("direct flow supports the MSE and NCC terms only (weight[2] must be 0)")
+            weights = list(weights)[:2]
+        self.w_mse, self.w_ncc, other = _split_criteria(criterions, weights)
+        if other:
+            raise NotImplementedError("direct flow supports nn.MSELoss and NCCLoss criteria only")
+        self.img_size = tuple(img_size)
+        self.lr, self.max_epochs, self.stop_crit = lr, max_epochs, stop_crit
+        self.smooth, self.optimiser, self.betas, self.eps = smooth, optimiser.lower(), betas, eps
+        self.flow, self.losses, self._prob = None, [], None
+
+    def optimize(self, moving, target, device=None, debug=True, grad_edges=False, check_every=50):
+        _reject_edges(grad_edges)
+        prob = TF.DirectFlowProblem(moving, target, self.max_epochs, optimiser=self.optimiser)
+        done = 0
+        message = 'Reached max epochs'
+        while done < self.max_epochs:                       # the stop criterion is polled every `check_every` epochs
+            n = min(check_every, self.max_epochs - done)
+            prob.run(n, self.lr, self.w_mse, self.w_ncc, self.smooth, self.betas, self.eps)
+            done += n
+            lo = prob.losses[done - n:done]
+            hit = (lo <= self.stop_crit).nonzero()
+            if hit.numel():
+                message = 'Converged to %f' % self.stop_crit
+                break
+        self._prob = prob
+        self.flow = prob.flow
+        self.losses = prob.losses.tolist()
+        if debug:
+            print('Optimization ended with status: %s' % message)
+
+    def deform(self, x):
+        return TF.warp_flow(x, self.flow)
