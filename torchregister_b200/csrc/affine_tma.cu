@@ -301,14 +301,17 @@ __device__ __forceinline__ Coef load_coef(const float *coef_s, const TmaParams &
     return k;
 }
 
-// Map the tile through theta, decide whether its source footprint fits the TMA box, publish the
-// box origin and start the loads for `stage`.  Executed by ONE lane.
-template <int BX, int BY, int BZ>
-__device__ __forceinline__ void issue_tile(const TileIter &t, const TmaParams &p, const float *coef_s, unsigned char *stg,
-                                           uint64_t *full, TileMeta *meta, const CUtensorMap *map_mov,
-                                           const CUtensorMap *map_tgt, float inv_d2, float zoff)
+// Per-column constants of the footprint bound: the box needed by z-tile k of a column is
+// [lo_r + k*step_r, hi_r + k*step_r] per source axis r.  Computed once per column (table look-ups and the
+// theta coefficients are off the per-tile path), kept per warp in smem, 12 words.
+struct ColConst {
+    float lo[3], hi[3], step[3];
+    int pair, x0, y0;
+};
+
+__device__ __forceinline__ void compute_col(ColConst &c, const TileIter &t, const TmaParams &p, const float *coef_s,
+                                            float inv_d2, float zoff)
 {
-    using L = SmemLayout<BX, BY, BZ>;
     const int W = p.a.W, H = p.a.H;
     const int pair = t.cg / p.cols_per_pair;
     const int col = t.cg - pair * p.cols_per_pair;
@@ -317,17 +320,33 @@ __device__ __forceinline__ void issue_tile(const TileIter &t, const TmaParams &p
     const int x0 = (col - ty_i * p.tiles_x) * TX, y0 = ty_i * TY;
     const float xa = __ldg(p.a.xb + x0), xe = __ldg(p.a.xb + min(x0 + TX - 1, W - 1));
     const float ya = __ldg(p.a.yb + y0), ye = __ldg(p.a.yb + min(y0 + TY - 1, H - 1));
-    const int z0 = p.a.s_begin + t.tz_i * TZ;
-    const float za = fmaf(inv_d2, (float)z0, zoff), ze = fmaf(inv_d2, (float)min(z0 + TZ - 1, p.a.s_end - 1), zoff);
+    const float za0 = fmaf(inv_d2, (float)p.a.s_begin, zoff);
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+        const float base = k.A[r][0] * xa + k.A[r][1] * ya + k.A[r][2] * za0 + k.C[r];
+        const float dx = k.A[r][0] * (xe - xa), dy = k.A[r][1] * (ye - ya), dz = k.A[r][2] * inv_d2 * (float)(TZ - 1);
+        c.lo[r] = base + fminf(dx, 0.f) + fminf(dy, 0.f) + fminf(dz, 0.f) - 0.03f;
+        c.hi[r] = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.03f;
+        c.step[r] = k.A[r][2] * inv_d2 * (float)TZ;
+    }
+    c.pair = pair; c.x0 = x0; c.y0 = y0;
+}
+
+// Decide whether the tile's source footprint fits the TMA box, publish the box origin and start the loads
+// for `stage`.  Executed by ONE lane; ~40 instructions (the per-column part lives in ColConst).
+template <int BX, int BY, int BZ>
+__device__ __forceinline__ void issue_tile(int tz_i, const ColConst &c, const TmaParams &p, unsigned char *stg,
+                                           uint64_t *full, TileMeta *meta, const CUtensorMap *map_mov,
+                                           const CUtensorMap *map_tgt)
+{
+    using L = SmemLayout<BX, BY, BZ>;
     int o[3];
     bool fits = true;
     const int B[3] = {BX, BY, BZ};
+    const float kf = (float)tz_i;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
-        const float base = k.A[r][0] * xa + k.A[r][1] * ya + k.A[r][2] * za + k.C[r];
-        const float dx = k.A[r][0] * (xe - xa), dy = k.A[r][1] * (ye - ya), dz = k.A[r][2] * (ze - za);
-        const float lo = base + fminf(dx, 0.f) + fminf(dy, 0.f) + fminf(dz, 0.f) - 0.02f;
-        const float hi = base + fmaxf(dx, 0.f) + fmaxf(dy, 0.f) + fmaxf(dz, 0.f) + 0.02f;
+        const float lo = fmaf(kf, c.step[r], c.lo[r]), hi = fmaf(kf, c.step[r], c.hi[r]);
         // keep the float->int conversions defined for wild thetas
         const float loc = fminf(fmaxf(lo, -1.0e6f), 1.0e6f), hic = fminf(fmaxf(hi, -1.0e6f), 1.0e6f);
         // TMA needs the box start 16-byte aligned along x (tools/tma_probe.cu: an unaligned innermost
@@ -342,8 +361,8 @@ __device__ __forceinline__ void issue_tile(const TileIter &t, const TmaParams &p
     *meta = m;
     const unsigned tgt_bytes = L::kTgtFloats * 4, box_bytes = L::kBoxFloats * 4;
     mbar_arrive_expect_tx(full, fits ? (tgt_bytes + box_bytes) : tgt_bytes);
-    if (fits) tma_load_4d(stg, map_mov, full, o[0], o[1], o[2], pair);
-    tma_load_4d(stg + L::kBoxFloats * 4, map_tgt, full, x0, y0, z0, pair);
+    if (fits) tma_load_4d(stg, map_mov, full, o[0], o[1], o[2], c.pair);
+    tma_load_4d(stg + L::kBoxFloats * 4, map_tgt, full, c.x0, c.y0, p.a.s_begin + tz_i * TZ, c.pair);
 }
 
 // sum 41 per-lane values over the warp.  The first 32 are reduced "transposed" (recursive halving:
@@ -551,14 +570,19 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
         for (int v = lane; v < TRB_MOMENTS; v += 32) __stcg(mine + v, 0.0);
         warp_arrive_group(p, pr, G, lane);
     }
+    __shared__ ColConst colc[kConsumerWarps];   // each warp's copy of the footprint constants of `ahead`'s column
     if (threadIdx.x == 0) {                     // prologue: fill the ring
         TileIter t = cur;
+        ColConst c;
+        compute_col(c, t, p, coef_s, inv_d2, zoff);
         for (int i = 0; i < NSTAGE && t.phase != 2; ++i) {
-            issue_tile<BX, BY, BZ>(t, p, coef_s, smem_raw + (size_t)i * L::kStageBytes, full_bar + i, meta + i, &map_mov, &map_tgt, inv_d2, zoff);
-            iter_next(t, p, b, G);
+            issue_tile<BX, BY, BZ>(t.tz_i, c, p, smem_raw + (size_t)i * L::kStageBytes, full_bar + i, meta + i, &map_mov, &map_tgt);
+            if (iter_next(t, p, b, G) && t.phase != 2) compute_col(c, t, p, coef_s, inv_d2, zoff);
         }
     }
     for (int i = 0; i < NSTAGE && ahead.phase != 2; ++i) iter_next(ahead, p, b, G);   // ahead = cur + NSTAGE tiles
+    if (lane == 0 && ahead.phase != 2) compute_col(colc[warp], ahead, p, coef_s, inv_d2, zoff);
+    __syncwarp();
 
     // per-pair totals of this thread, folded with its x,y,z base coordinates.  Touched once per column
     // only: kept in local memory (volatile) so the 41 values do not occupy registers in the hot loop.
@@ -658,11 +682,13 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                 if (old == kConsumerWarps - 1) {
                     done_cnt[stage] = 0u;
                     if (ahead.phase != 2)
-                        issue_tile<BX, BY, BZ>(ahead, p, coef_s, stg, full_bar + stage, meta + stage, &map_mov, &map_tgt, inv_d2, zoff);
+                        issue_tile<BX, BY, BZ>(ahead.tz_i, colc[warp], p, stg, full_bar + stage, meta + stage, &map_mov, &map_tgt);
                 }
             }
             ++it;
-            if (ahead.phase != 2) iter_next(ahead, p, b, G);
+            if (ahead.phase != 2 && iter_next(ahead, p, b, G) && ahead.phase != 2 && lane == 0)
+                compute_col(colc[warp], ahead, p, coef_s, inv_d2, zoff);      // once per column, per warp
+            __syncwarp();
             col_done = iter_next(cur, p, b, G);
         }
 
