@@ -520,6 +520,17 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
     const int G = gridDim.x, b = blockIdx.x;
     const float inv_d2 = 2.f / (float)D, zoff = 1.f / (float)D - 1.f;      // zv(z) = (2z+1)/D - 1
 
+    // Programmatic dependent launch: let the next epoch's grid be scheduled as SMs drain (its CTAs get as far
+    // as this point — smem carve-up, barrier init — while our stragglers and final phase finish), and do not
+    // read theta / touch the workspace until the previous epoch's grid has completed and flushed.
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+    if (threadIdx.x == 0) {
+        pair_cnt[0] = pair_cnt[1] = 0u;
+        for (int i = 0; i < NSTAGE; ++i) { mbar_init(full_bar + i, 1); done_cnt[i] = 0u; }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+
     // coordinate maps of all pairs -> smem (theta was written by the previous epoch's epilogue)
     if (p.n_pairs <= kMaxCachedPairs) {
         for (int pr = threadIdx.x; pr < p.n_pairs; pr += kTmaThreads) {
@@ -831,8 +842,14 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
     }
     for (int e = 0; e < n_launch; ++e) {
         p.a.epoch = epoch0 + e;
-        if (fused) kf<<<grid, kTmaThreads, smem, stream>>>(p, map_mov, map_tgt);
-        else ku<<<grid, kTmaThreads, smem, stream>>>(p, map_mov, map_tgt);
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(kTmaThreads); cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        attr[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = attr; cfg.numAttrs = 1;
+        cudaError_t le = fused ? cudaLaunchKernelEx(&cfg, kf, p, map_mov, map_tgt) : cudaLaunchKernelEx(&cfg, ku, p, map_mov, map_tgt);
+        if (le != cudaSuccess) return check_cuda(le, "cudaLaunchKernelEx(affine3d_tma)");
     }
     return check_cuda(cudaGetLastError(), "affine3d_tma");
 }
