@@ -124,11 +124,14 @@ int trb_affine_moments(int ndim,
                        const float *state_dev, double *moments_dev,
                        void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* extra_dev (optional, may be NULL): [n_pairs][13] fp64 = an additional loss term and its gradient w.r.t.
+ * theta, evaluated outside (used for the NMI/KDE term, reference utils.py:224-259, until it is fused). */
 int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs,
                      int D, int H, int W,
                      float *state_dev, float *loss_log_dev, int log_stride, int epoch,
                      float w_mse, float w_ncc, float lr,
-                     int optimiser, float beta1, float beta2, float adam_eps, void *stream);
+                     int optimiser, float beta1, float beta2, float adam_eps,
+                     const double *extra_dev, void *stream);
 
 /* Forward warp only: out[c] = grid_sample(moving[c], affine_grid(theta)) for
  * n_channels volumes sharing one theta (dev, 12|6 floats).

@@ -70,10 +70,9 @@ def test_criterion_conventions():
     from torchregister_b200.warpings import similarity_weights, _split_criteria
     from torchregister_b200.utils import NCCLoss
     # reference warpings.py:38-40,125-127: any user criterion -> MSE only
-    assert similarity_weights([nn.L1Loss()], [0.2], "t") == (1.0, 0.0)
-    assert similarity_weights(None, [0.0, 1.0, 0.0], "t") == (0.0, 1.0)
-    with pytest.raises(NotImplementedError, match="NMI"):
-        similarity_weights(None, [0.33, 0.33, 0.33], "t")
+    assert similarity_weights([nn.L1Loss()], [0.2], "t") == (1.0, 0.0, 0.0)
+    assert similarity_weights(None, [0.0, 1.0, 0.0], "t") == (0.0, 1.0, 0.0)
+    assert similarity_weights(None, [0.33, 0.33, 0.33], "t") == (0.33, 0.33, 0.33)
     w_mse, w_ncc, other = _split_criteria([nn.MSELoss(), NCCLoss(alpha=50), nn.L1Loss()], [0.5, 0.4, 0.1])
     assert w_mse == 0.5 and abs(w_ncc - 0.2) < 1e-12 and len(other) == 1
 
@@ -145,3 +144,19 @@ def test_shard_planner():
     assert slab_range(512, 8, 3) == (192, 256)
     with pytest.raises(ValueError):
         shard_pairs(4, 2, 2)
+
+
+def test_nmi_loss_matches_port():
+    """NMILoss (blocked KDE, hand-written backward) against the oracle restatement of utils.py:18-79,224-259."""
+    import torchregister_b200 as tr
+    from oracle import torch_port as tp
+    from torchregister_b200.synth import make_pair
+    for shape, patch in (((48, 40), 100), ((14, 12, 10), 6)):
+        mov, tgt = make_pair(shape, "rigid")
+        w1 = (3.0 * mov + 0.1).clone().requires_grad_(True)          # range 3: the KDE is not degenerate
+        w2 = w1.detach().clone().requires_grad_(True)
+        a = tr.NMILoss(patch_size=patch)(3.0 * tgt, w1)
+        b = tp.nmi_loss(3.0 * tgt, w2, patch=patch)
+        a.backward(); b.backward()
+        assert abs(a.item() - b.item()) <= 1e-3 * abs(b.item()) + 1e-4
+        assert (w1.grad - w2.grad).abs().max() <= 2e-3 * w2.grad.abs().max()

@@ -357,8 +357,9 @@ def test_register_flow_mode_api():
     two = torch.cat([mov, 0.5 * tgt], dim=1)
     out = reg(two)
     assert tuple(out.shape) == (1, 2, 160, 160) and torch.isfinite(out).all()
-    with pytest.raises(NotImplementedError, match="NMI"):
-        tr.Register(mode="flow", device=DEV).optim(mov, tgt, max_epochs=1)
+    default = tr.Register(mode="flow", device=DEV)                  # reference defaults: MSE + NCC + NMI, weights .33
+    default.optim(mov, tgt, lr=1e-3, max_epochs=1, n=32)
+    assert len(default.losses) == 1 and np.isfinite(default.losses[0])
 
 
 # --------------------------------------------------------------------------------------------
@@ -420,3 +421,17 @@ def test_register_direct_flow_extension():
     assert reg.losses[-1] < reg.losses[0]
     out = reg(torch.cat([mov, mov], 1))
     assert tuple(out.shape) == (1, 2, 24, 28, 32)
+
+
+def test_default_weights_with_nmi_vs_reference_golden():
+    """Register defaults (0.33*MSE + 0.33*NCC + 0.33*NMI): the golden run is the unmodified reference incl. its real
+    NMI term (2-D).  The NMI term itself is fp32 rounding noise for data in [0,1] (|NMI-1| ~ 1e-6), so it is
+    compared on the total loss and theta."""
+    import torchregister_b200 as tr
+    g = load_golden("rigid2d_default")
+    mov, tgt = torch.from_numpy(g["moving"]), torch.from_numpy(g["target"])
+    reg = tr.Register(mode="rigid", device=DEV)
+    reg.optim(mov, tgt, lr=float(g["lr"]), max_epochs=int(g["epochs"]), reg0=torch.from_numpy(g["p0"]))
+    losses = reg.losses.cpu().numpy()
+    assert np.allclose(losses, g["losses"], rtol=2e-4, atol=2e-4), (losses, g["losses"])
+    assert np.abs(reg.theta.cpu().numpy() - g["best_theta"]).max() <= 1e-5

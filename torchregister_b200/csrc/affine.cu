@@ -432,7 +432,7 @@ extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float
 extern "C" int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs, int D, int H, int W,
                                 float *state_dev, float *loss_log_dev, int log_stride, int epoch,
                                 float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2,
-                                float adam_eps, void *stream)
+                                float adam_eps, const double *extra_dev, void *stream)
 {
     int rc = validate_common(ndim, n_pairs, D, H, W);
     if (rc) return rc;
@@ -444,6 +444,7 @@ extern "C" int trb_affine_apply(int ndim, int mode, const double *moments_dev, i
     p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride; p.epoch = epoch;
     p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
+    p.extra = extra_dev;
     cudaStream_t s = (cudaStream_t)stream;
     const int tb = 32, nb = (n_pairs + tb - 1) / tb;
     if (ndim == 3) affine_apply_kernel<3><<<nb, tb, 0, s>>>(p, moments_dev);

@@ -29,6 +29,7 @@ struct AffineParams {
     float w_mse, w_ncc, lr;
     int mode, optimiser;
     float beta1, beta2, adam_eps;
+    const double *extra;         // optional [n_pairs][13]: extra loss term and its d/dtheta (e.g. the NMI term), or NULL
 };
 
 // ---- Theta.forward (utils.py:287-310), fp32 like the reference ------------------
@@ -114,7 +115,14 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
             const int i = r * NC + c;
             dth[i] = (lc.cw * M[29 + i] + lc.ct * M[17 + i] + lc.c0 * M[5 + i]) * scale[r];
         }
-    const float loss = (float)lc.loss;
+    double loss_d = lc.loss;
+    if (p.extra) {                                  // externally evaluated term (already in theta units)
+        const double *ex = p.extra + (size_t)pair * 13;
+        loss_d += ex[0];
+#pragma unroll
+        for (int i = 0; i < NT; ++i) dth[i] += ex[1 + i];
+    }
+    const float loss = (float)loss_d;
     // best tracking on the pre-step theta (warpings.py:85-93,151-159: strictly lower)
     if (p.epoch == 0 || loss < best_prev) {
         st[TRB_STATE_BEST_LOSS] = loss;

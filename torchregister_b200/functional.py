@@ -152,7 +152,8 @@ class AffineProblem:
         return out
 
     def apply(self, moments: torch.Tensor, lr: float, w_mse: float, w_ncc: float, optimiser: str = "sgd",
-              betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+              betas=(0.9, 0.999), eps: float = 1e-8, extra: Optional[torch.Tensor] = None) -> None:
+        """extra: optional [n_pairs, 13] float64 — an additional loss term and its d/dtheta per pair."""
         if self.epoch + 1 > self.max_epochs:
             raise ValueError("max_epochs exceeded")
         with torch.cuda.device(self.device):
@@ -160,12 +161,17 @@ class AffineProblem:
                 self.ndim, MODE[self.mode], moments.data_ptr(), self.n_pairs, self.D, self.H, self.W,
                 self.state.data_ptr(), self.loss_log.data_ptr(), self.loss_log.shape[1], self.epoch,
                 float(w_mse), float(w_ncc), float(lr), OPT[optimiser], float(betas[0]), float(betas[1]), float(eps),
-                _stream(self.device)), "affine_apply")
+                _ptr(extra), _stream(self.device)), "affine_apply")
         self.epoch += 1
 
     # -- results (device tensors; reading them on the host is the only sync)
     def _theta(self, off: int) -> torch.Tensor:
         return self.state[:, off: off + self.nt].reshape(self.n_pairs, self.ndim, self.ndim + 1).clone()
+
+    @property
+    def theta(self) -> torch.Tensor:
+        """theta the next epoch samples with (== final theta once the loop is over)."""
+        return self._theta(S_THETA)
 
     @property
     def final_theta(self) -> torch.Tensor:

@@ -19,7 +19,7 @@ from . import functional as TF
 
 EPSILON = 1E-10
 
-__all__ = ["EPSILON", "NCCLoss", "SSDLoss", "norm", "padNd", "Theta", "Regressor", "SpatialTransformer",
+__all__ = ["EPSILON", "NCCLoss", "SSDLoss", "NMILoss", "norm", "padNd", "Theta", "Regressor", "SpatialTransformer",
            "attention_grid", "Attention_UNet"]
 
 
@@ -55,6 +55,87 @@ class SSDLoss(nn.Module):
     def forward(self, y, yp):
         self.SSD = torch.sum((y - yp) ** 2)
         return self.SSD * self.alpha
+
+
+class _KDEMutualInfoFn(torch.autograd.Function):
+    """|NMI - 1| * alpha averaged over chunks, for chunked samples t_s, w_s of shape [n, P], differentiable in w_s.
+
+    Same arithmetic as the reference's K_gauss / PDF_xis / get_pdf / NMI (utils.py:18-79), including the swapped
+    min/max of the bin range (:45-49), the 1/(2*pi) kernel constant (:19) and the "joint" density being a 1-D KDE
+    over the concatenation of both images (:62-63) — but evaluated in blocks of bins with the backward written
+    out by hand, so the [n, P, 256] temporaries (8 GB each in 3-D) and their autograd copies never exist."""
+
+    @staticmethod
+    def _bins(sig, steps):
+        hi, lo = torch.max(sig).item(), torch.min(sig).item()
+        return torch.linspace(hi, lo, steps, dtype=torch.float, device=sig.device).to(sig.dtype)
+
+    @staticmethod
+    def _pdf(sig, xs, h, block):
+        cols = []
+        for i0 in range(0, xs.numel(), block):
+            z = (sig.unsqueeze(-1) - xs[i0:i0 + block]) / h
+            cols.append((1 / h) * torch.mean((1 / (2 * torch.pi)) * torch.exp(-(z ** 2) / 2), dim=1))
+        return torch.cat(cols, dim=1)
+
+    @staticmethod
+    def forward(ctx, t_s, w_s, bins, h, alpha, block):
+        with torch.no_grad():
+            both = torch.cat((t_s, w_s), dim=1)
+            x1, x2, xj = (_KDEMutualInfoFn._bins(v, bins) for v in (t_s, w_s, both))
+            pdf1 = _KDEMutualInfoFn._pdf(t_s, x1, h, block)
+            pdf2 = _KDEMutualInfoFn._pdf(w_s, x2, h, block)
+            pdfj = 0.5 * (_KDEMutualInfoFn._pdf(t_s, xj, h, block) + _KDEMutualInfoFn._pdf(w_s, xj, h, block))
+        with torch.enable_grad():                      # the [n, 256] tail of the graph is tiny: let autograd do it
+            q2 = pdf2.detach().requires_grad_(True)
+            qj = pdfj.detach().requires_grad_(True)
+            p1 = pdf1 / torch.sum(pdf1, dim=1, keepdim=True)
+            p2 = q2 / torch.sum(q2, dim=1, keepdim=True)
+            pj = qj / torch.sum(qj, dim=1, keepdim=True)
+            e1 = -torch.sum(p1 * -torch.log2(p1 + EPSILON), dim=1)
+            e2 = -torch.sum(p2 * -torch.log2(p2 + EPSILON), dim=1)
+            ej = -torch.sum(pj * -torch.log2(pj + EPSILON), dim=1)
+            mi = e1 + e2 - ej
+            loss = torch.mean(torch.abs(2 * mi / (e1 + e2) - 1.) * alpha)
+            g2, gj = torch.autograd.grad(loss, (q2, qj))
+        ctx.save_for_backward(w_s, x2, xj, g2, gj)
+        ctx.h, ctx.block = h, block
+        return loss.detach()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        w_s, x2, xj, g2, gj = ctx.saved_tensors
+        h, block = ctx.h, ctx.block
+        n_s = w_s.shape[1]
+        grad = torch.zeros_like(w_s)
+        c = (1 / h) * (1 / (2 * torch.pi))
+        for xs, g, cnt in ((x2, g2, n_s), (xj, gj, 2 * n_s)):
+            for i0 in range(0, xs.numel(), block):
+                z = (w_s.unsqueeze(-1) - xs[i0:i0 + block]) / h
+                # d/dw of c * exp(-z^2/2) / cnt  =  -c * z / h * exp(-z^2/2) / cnt
+                grad += torch.sum(g[:, None, i0:i0 + block] * (-(c / (h * cnt)) * z * torch.exp(-(z ** 2) / 2)), dim=-1)
+        return None, grad * grad_out, None, None, None, None
+
+
+class NMILoss(nn.Module):
+    """Normalised-mutual-information term of the reference's default loss (utils.py:224-259): nearest-resample
+    both images to (2*patch)^n, view as 2^n chunks of patch^n, 256-bin Gaussian KDE (bandwidth 3) of target,
+    warped and their concatenation, loss = mean(|NMI - 1|) * alpha.  Evaluated with PyTorch ops (host code):
+    fusing it into the CUDA step is the first "next" row of SURVEY.md §8f."""
+
+    def __init__(self, alpha=1000, bins=256, patch_size=100, bandwidth=3, block=8):
+        super().__init__()
+        self.bins, self.alpha, self.patch, self.bandwidth, self.block = bins, alpha, patch_size, bandwidth, block
+
+    def _chunks(self, v):
+        nd = v.dim() - 2
+        r = self.patch * 2
+        v = F.interpolate(v, size=(r,) * nd, mode='nearest')
+        return v.reshape((2 ** nd) * v.shape[0] * v.shape[1], -1)
+
+    def forward(self, y, yp):
+        return _KDEMutualInfoFn.apply(self._chunks(y), self._chunks(yp), self.bins, float(self.bandwidth),
+                                      float(self.alpha), self.block)
 
 
 def norm(x):

@@ -14,7 +14,7 @@ import torch
 import torch.nn as nn
 
 from . import functional as TF
-from .utils import Attention_UNet, NCCLoss
+from .utils import Attention_UNet, NCCLoss, NMILoss
 
 __all__ = ["get_affine_warp", "affine_register", "rigid_register", "flow_register", "direct_flow_register",
            "similarity_weights"]
@@ -50,23 +50,20 @@ def get_affine_warp(theta, moving):
 # --------------------------------------------------------------------------- #
 # criterion bookkeeping
 # --------------------------------------------------------------------------- #
-def similarity_weights(criterions, weights, where: str) -> Tuple[float, float]:
+def similarity_weights(criterions, weights, where: str) -> Tuple[float, float, float]:
     """Map the reference's (criterions, weights) convention for the rigid/affine loops
-    (warpings.py:36-40,123-127) onto the fused kernel's (w_mse, w_ncc).
+    (warpings.py:36-40,123-127) onto (w_mse, w_ncc, w_nmi).
 
       criterions is None     -> [MSE, NCC, NMI] with `weights`
       criterions is not None -> the reference silently replaces it by [MSE], [1.]
-    The NMI term (reference utils.py:224-259) is not fused yet: weight[2] must be 0."""
+    MSE and NCC are evaluated inside the fused CUDA step; a non-zero NMI weight switches the loop to the
+    three-launch form (moments / NMI term through PyTorch ops / apply), see _affine_like."""
     if criterions is not None:
-        return 1.0, 0.0
+        return 1.0, 0.0, 0.0
     w = list(weights)
     if len(w) < 3:
         raise IndexError("weights must have 3 entries (MSE, NCC, NMI) when criterions is None")
-    if w[2] != 0:
-        raise NotImplementedError(
-            "%s: the NMI/KDE similarity term (weight[2]=%g) is not part of the fused CUDA path yet "
-            "(SURVEY.md §8f-1). Pass weight=[w_mse, w_ncc, 0.] — e.g. Register(weight=[0.5, 0.5, 0.])." % (where, w[2]))
-    return float(w[0]), float(w[1])
+    return float(w[0]), float(w[1]), float(w[2])
 
 
 def _reject_edges(grad_edges):
@@ -76,9 +73,29 @@ def _reject_edges(grad_edges):
             "the reference itself raises at its default padding. Pass grad_edges=False.")
 
 
-def _affine_like(mode, moving, target, lr, epochs, weights_pair, params0, debug, want_warped=True):
+def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, want_warped=True):
+    w_mse, w_ncc, w_nmi = weights3
     prob = TF.AffineProblem(moving, target, mode, params0, epochs)
-    prob.run(epochs, lr, weights_pair[0], weights_pair[1])
+    if w_nmi == 0:
+        prob.run(epochs, lr, w_mse, w_ncc)               # one fused launch per epoch, no host round trips
+    else:
+        # Default weights of the reference include the NMI/KDE term (utils.py:224-259).  It is not fused yet
+        # (SURVEY.md §8f-1): per epoch the MSE/NCC moments come from the CUDA pass, the NMI term and its
+        # gradient w.r.t. the warped volume from PyTorch ops, chained to theta by trb_warp_affine_vjp, and the
+        # update is applied on the device by trb_affine_apply.  Still no host synchronisation.
+        nmi = NMILoss()
+        nd = moving.dim() - 2
+        n_slices = int(moving.shape[2])
+        extra = torch.zeros(1, 13, dtype=torch.float64, device=moving.device)
+        for _ in range(epochs):
+            theta = prob.theta
+            mom = prob.moments(0, n_slices)
+            warped = TF.warp_affine(theta, moving).requires_grad_(True)
+            term = w_nmi * nmi(target, warped)
+            (gw,) = torch.autograd.grad(term, warped)
+            extra[0, 0] = term.detach().double()
+            extra[0, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta, moving, gw.contiguous()).reshape(-1)
+            prob.apply(mom, lr, w_mse, w_ncc, extra=extra)
     final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
     # the reference keeps the warped volumes of the final and best epochs; we never write them during
     # the loop and re-create them here only when the caller wants them (Register.optim does not)
@@ -176,14 +193,11 @@ class flow_register(nn.Module):
         self.flow = None
         self.warp = None
         if criterions is None:
-            # reference default: [MSELoss, NCCLoss, NMILoss] (warpings.py:179)
-            if len(weights) >= 3 and weights[2] != 0:
-                raise NotImplementedError(
-                    "flow_register: the default criteria include the NMI/KDE term (weight[2]=%g), which is not "
-                    "part of the CUDA path yet (SURVEY.md §8f-1). Pass weights=[w_mse, w_ncc, 0.] or explicit "
-                    "criterions=[nn.MSELoss(), NCCLoss()]." % weights[2])
-            criterions = [nn.MSELoss(), NCCLoss()]
-            weights = list(weights)[:2]
+            # reference default: [MSELoss, NCCLoss, NMILoss] (warpings.py:179); a zero-weight NMI term is dropped
+            # (it costs a 256-bin KDE over 8e6 samples per epoch and contributes nothing)
+            criterions = [nn.MSELoss(), NCCLoss(), NMILoss()]
+            if len(weights) >= 3 and weights[2] == 0:
+                criterions, weights = criterions[:2], list(weights)[:2]
         self.criterions, self.weights = criterions, weights
         self.lr, self.max_epochs, self.stop_crit = lr, max_epochs, stop_crit
         self.optimizer = torch.optim.SGD(self.model.parameters(), lr)
