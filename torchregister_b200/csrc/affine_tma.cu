@@ -138,7 +138,7 @@ struct Acc {
 
 // one pair of voxels (same x,y; z and z+1).  box_m: smem byte address of the staged box.
 // SECOND=false masks voxel b.
-template <int BX, int BY, bool SECOND>
+template <int BX, int BY, bool SECOND, bool MSE_ONLY>
 __device__ __forceinline__ void pair_step(uint32_t box_m, float Mrel, float2 ix, float2 iy, float2 iz,
                                           float2 t, float2 zf, Acc &A)
 {
@@ -178,24 +178,39 @@ __device__ __forceinline__ void pair_step(uint32_t box_m, float Mrel, float2 ix,
 #pragma unroll
         for (int r = 0; r < 3; ++r) G[r] = __fmul2_rn(G[r], m);
     }
-    A.s[0] = __fadd2_rn(A.s[0], t);
-    A.s[1] = __fadd2_rn(A.s[1], val);
-    A.s[2] = __ffma2_rn(t, t, A.s[2]);
-    A.s[3] = __ffma2_rn(val, val, A.s[3]);
-    A.s[4] = __ffma2_rn(t, val, A.s[4]);
-    const float2 tzf = __fmul2_rn(t, zf), wzf = __fmul2_rn(val, zf);
+    if (MSE_ONLY) {
+        // w_ncc == 0: dL/dw_v = gm * (w_v - t_v) is known up front, so ONE weighted family (d = w - t) replaces
+        // the three (1, t, w): 9 packed moment updates instead of 25.  Stored in the "w" slots with the "t"
+        // slots left at zero, which the shared epilogue turns into gm * sum d*J.
+        const float2 d = sub2(val, t);
+        A.s[2] = __ffma2_rn(d, d, A.s[2]);                 // sum d^2 rides in the sum t^2 slot
+        const float2 dzf = __fmul2_rn(d, zf);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        A.P[0][r] = __fadd2_rn(A.P[0][r], G[r]);
-        A.P[1][r] = __ffma2_rn(t, G[r], A.P[1][r]);
-        A.P[2][r] = __ffma2_rn(val, G[r], A.P[2][r]);
-        A.Q[0][r] = __ffma2_rn(zf, G[r], A.Q[0][r]);
-        A.Q[1][r] = __ffma2_rn(tzf, G[r], A.Q[1][r]);
-        A.Q[2][r] = __ffma2_rn(wzf, G[r], A.Q[2][r]);
+        for (int r = 0; r < 3; ++r) {
+            A.P[2][r] = __ffma2_rn(d, G[r], A.P[2][r]);
+            A.Q[2][r] = __ffma2_rn(dzf, G[r], A.Q[2][r]);
+        }
+    } else {
+        A.s[0] = __fadd2_rn(A.s[0], t);
+        A.s[1] = __fadd2_rn(A.s[1], val);
+        A.s[2] = __ffma2_rn(t, t, A.s[2]);
+        A.s[3] = __ffma2_rn(val, val, A.s[3]);
+        A.s[4] = __ffma2_rn(t, val, A.s[4]);
+        const float2 tzf = __fmul2_rn(t, zf), wzf = __fmul2_rn(val, zf);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            A.P[0][r] = __fadd2_rn(A.P[0][r], G[r]);
+            A.P[1][r] = __ffma2_rn(t, G[r], A.P[1][r]);
+            A.P[2][r] = __ffma2_rn(val, G[r], A.P[2][r]);
+            A.Q[0][r] = __ffma2_rn(zf, G[r], A.Q[0][r]);
+            A.Q[1][r] = __ffma2_rn(tzf, G[r], A.Q[1][r]);
+            A.Q[2][r] = __ffma2_rn(wzf, G[r], A.Q[2][r]);
+        }
     }
 }
 
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
+template <bool MSE_ONLY>
 __device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
                                              float t, float zf, Acc &A)
 {
@@ -223,13 +238,23 @@ __device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int 
     G[1] = fmaf(tz, e1 - e0, e0);
     const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
     G[0] = fmaf(tz, dx1 - dx0, dx0);
-    A.s[0].x += t; A.s[1].x += val;
-    A.s[2].x = fmaf(t, t, A.s[2].x); A.s[3].x = fmaf(val, val, A.s[3].x); A.s[4].x = fmaf(t, val, A.s[4].x);
+    if (MSE_ONLY) {
+        const float d = val - t;
+        A.s[2].x = fmaf(d, d, A.s[2].x);
 #pragma unroll
-    for (int r = 0; r < 3; ++r) {
-        const float g = G[r], tg = t * g, wg = val * g;
-        A.P[0][r].x += g; A.P[1][r].x += tg; A.P[2][r].x += wg;
-        A.Q[0][r].x = fmaf(zf, g, A.Q[0][r].x); A.Q[1][r].x = fmaf(zf, tg, A.Q[1][r].x); A.Q[2][r].x = fmaf(zf, wg, A.Q[2][r].x);
+        for (int r = 0; r < 3; ++r) {
+            A.P[2][r].x = fmaf(d, G[r], A.P[2][r].x);
+            A.Q[2][r].x = fmaf(zf * d, G[r], A.Q[2][r].x);
+        }
+    } else {
+        A.s[0].x += t; A.s[1].x += val;
+        A.s[2].x = fmaf(t, t, A.s[2].x); A.s[3].x = fmaf(val, val, A.s[3].x); A.s[4].x = fmaf(t, val, A.s[4].x);
+#pragma unroll
+        for (int r = 0; r < 3; ++r) {
+            const float g = G[r], tg = t * g, wg = val * g;
+            A.P[0][r].x += g; A.P[1][r].x += tg; A.P[2][r].x += wg;
+            A.Q[0][r].x = fmaf(zf, g, A.Q[0][r].x); A.Q[1][r].x = fmaf(zf, tg, A.Q[1][r].x); A.Q[2][r].x = fmaf(zf, wg, A.Q[2][r].x);
+        }
     }
 }
 
@@ -501,7 +526,7 @@ __device__ void final_phase(const TmaParams &p, double *fin_s /*[16][TRB_MOMENTS
     }
 }
 
-template <int BX, int BY, int BZ, int NSTAGE, bool FUSED>
+template <int BX, int BY, int BZ, int NSTAGE, bool FUSED, bool MSE_ONLY>
 __global__ void __launch_bounds__(kTmaThreads, 1)
 affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_mov, const __grid_constant__ CUtensorMap map_tgt)
 {
@@ -660,7 +685,7 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                             case 2: t = make_float2(lds_f<4 * TX * TY * 4>(tg), lds_f<5 * TX * TY * 4>(tg)); break;
                             default: t = make_float2(lds_f<6 * TX * TY * 4>(tg), lds_f<7 * TX * TY * 4>(tg)); break;
                             }
-                            pair_step<BX, BY, true>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                             zf = __fadd2_rn(zf, f2(2.f));
                         }
                     } else {
@@ -673,14 +698,14 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                             const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
                             const float2 t = make_float2(lds_f_dyn(tg + zz * (TX * TY * 4)),
                                                          lds_f_dyn(tg + (second ? zz + 1 : zz) * (TX * TY * 4)));
-                            if (second) pair_step<BX, BY, true>(box_addr, Mrel, ix, iy, iz, t, zf, A);
-                            else pair_step<BX, BY, false>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            if (second) pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            else pair_step<BX, BY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                         }
                     }
                 } else {
                     for (int zz = 0; zz < nz; ++zz) {
                         const float zf = (float)(z0 + zz);
-                        voxel_direct(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
+                        voxel_direct<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
                                      lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
                     }
                 }
@@ -831,11 +856,15 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
     p.full_rounds = (int)(total_cols / grid);
     p.tail_tiles = (total_cols - (long long)p.full_rounds * grid) * p.tiles_z;
     const size_t smem = (size_t)kStages * L::kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * sizeof(TileMeta);
-    auto kf = affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true>;
-    auto ku = affine3d_tma_kernel<kBX, kBY, kBZ, kStages, false>;
+    // MSE-only steps (w_ncc == 0: the reference's "criterion given" branch, warpings.py:38-40,125-127) need one
+    // weighted moment family instead of three; the sharded (unfused) form always produces the full moment set
+    const bool mse_only = fused && a.w_ncc == 0.f;
+    auto kf = mse_only ? affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, true> : affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, false>;
+    auto ku = affine3d_tma_kernel<kBX, kBY, kBZ, kStages, false, false>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(kf, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e == cudaSuccess) e = cudaFuncSetAttribute(affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(ku, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return check_cuda(e, "cudaFuncSetAttribute(tma kernel)");
         attr_set = true;
