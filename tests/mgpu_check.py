@@ -35,11 +35,13 @@ def main():
     # (c) one volume, direct flow, z-slabs + halo exchange + all-reduce of 6 moments
     shape = (48, 40, 44)
     mov, tgt = (t.to(dev) for t in make_pair(shape, "flow"))
-    whole = TF.DirectFlowProblem(mov, tgt, 4, flow0=(0.3 * smooth_flow(shape, 1.0)).to(dev), optimiser="adam")
-    whole.run(4, 0.05, 0.5, 0.5, 3.0)
-    sd = ShardedDirectFlow(mov, tgt, 4, optimiser="adam")
+    # SGD for the tight comparison (Adam amplifies last-bit differences of the moment sums where the gradient is
+    # rounding noise, see test_direct_flow_slabs_equal_whole_volume)
+    whole = TF.DirectFlowProblem(mov, tgt, 4, flow0=(0.3 * smooth_flow(shape, 1.0)).to(dev), optimiser="sgd")
+    whole.run(4, 0.5, 0.5, 0.5, 3.0)
+    sd = ShardedDirectFlow(mov, tgt, 4, optimiser="sgd")
     sd.prob.flow.copy_((0.3 * smooth_flow(shape, 1.0)).to(dev)[:, :, sd.z0:sd.z1])
-    sd.run(4, 0.05, 0.5, 0.5, 3.0)
+    sd.run(4, 0.5, 0.5, 0.5, 3.0)
     assert torch.allclose(sd.flow_slab, whole.flow[:, :, sd.z0:sd.z1], atol=2e-6), (sd.flow_slab - whole.flow[:, :, sd.z0:sd.z1]).abs().max()
     assert torch.allclose(sd.losses, whole.losses, rtol=2e-5)
 

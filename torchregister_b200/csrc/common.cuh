@@ -41,6 +41,21 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 }
 
+// Row-wise voxel loop: a 256-thread CTA takes two rows (z,y) at a time, 128 threads along x each, so the only
+// integer division is one 32-bit div per row (the per-voxel 64-bit idx % W, idx / W of the first version cost
+// more than the whole interpolation).  f(idx, x, y, z).
+template <typename F>
+__device__ __forceinline__ void for_each_voxel(int D, int H, int W, F f)
+{
+    const int rows = D * H;
+    const int rx = threadIdx.x & 127, ry = threadIdx.x >> 7;
+    for (int row = 2 * blockIdx.x + ry; row < rows; row += 2 * gridDim.x) {
+        const int z = row / H, y = row - z * H;
+        const size_t base = (size_t)row * W;
+        for (int x = rx; x < W; x += 128) f(base + x, x, y, z);
+    }
+}
+
 // ---- similarity coefficients from the five global moments -------------------
 // dL/dw_v = cw*w_v + ct*t_v + c0   (reference utils.py:197-205,
 // nn.MSELoss at warpings.py:37,124; weighted sum warpings.py:78-79,144-145)

@@ -85,20 +85,16 @@ __device__ __forceinline__ Sample<NDIM> sample_zero_pad(const float *__restrict_
     return s;
 }
 
-// voxel index -> (x,y,z) and the sample position displaced by the flow
+// voxel (x,y,z) -> the sample position displaced by the flow
 template <int NDIM>
-__device__ __forceinline__ void flow_position(const float *__restrict__ flow, size_t vol, size_t idx,
+__device__ __forceinline__ void flow_position(const float *__restrict__ flow, size_t vol, size_t idx, int x, int y, int z,
                                               int D, int H, int W, float &px, float &py, float &pz)
 {
-    const int x = (int)(idx % W);
-    const size_t q = idx / W;
     if (NDIM == 3) {
-        const int y = (int)(q % H), z = (int)(q / H);
         pz = flow_pos(D, z, ld_stream_f(flow + idx));
         py = flow_pos(H, y, ld_stream_f(flow + vol + idx));
         px = flow_pos(W, x, ld_stream_f(flow + 2 * vol + idx));
     } else {
-        const int y = (int)q;
         pz = 0.f;
         py = flow_pos(H, y, ld_stream_f(flow + idx));
         px = flow_pos(W, x, ld_stream_f(flow + vol + idx));
@@ -110,12 +106,12 @@ __global__ void __launch_bounds__(256) warp_flow_kernel(const float *__restrict_
                                                          float *__restrict__ out, int n_channels, int D, int H, int W)
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol; idx += (size_t)gridDim.x * blockDim.x) {
+    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
         for (int c = 0; c < n_channels; ++c)
             out[(size_t)c * vol + idx] = sample_zero_pad<NDIM, false>(src + (size_t)c * vol, D, H, W, px, py, pz).val;
-    }
+    });
 }
 
 // dflow channel a (spatial axis a) receives the derivative along sampling coordinate NDIM-1-a
@@ -132,12 +128,12 @@ __global__ void __launch_bounds__(256) warp_flow_vjp_kernel(const float *__restr
                                                              int D, int H, int W)
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol; idx += (size_t)gridDim.x * blockDim.x) {
+    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
         const Sample<NDIM> s = sample_zero_pad<NDIM, true>(src, D, H, W, px, py, pz);
         store_dflow<NDIM>(dflow, vol, idx, ld_stream_f(gout + idx), s.g);
-    }
+    });
 }
 
 // workspace layout (doubles): [0..3] cw, ct, c0, loss ; [4] ticket (as unsigned) ; [8..] partials[blocks][5]
@@ -153,9 +149,9 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
     float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     double acc[5] = {0, 0, 0, 0, 0};
     int cnt = 0;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol; idx += (size_t)gridDim.x * blockDim.x) {
+    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
         const float w = sample_zero_pad<NDIM, false>(moving, D, H, W, px, py, pz).val;
         const float t = ld_stream_f(target + idx);
         if (warped) warped[idx] = w;
@@ -166,7 +162,7 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
             for (int i = 0; i < 5; ++i) { acc[i] += (double)s[i]; s[i] = 0.f; }
             cnt = 0;
         }
-    }
+    });
 #pragma unroll
     for (int i = 0; i < 5; ++i) acc[i] += (double)s[i];
     __shared__ double red[8][5];
@@ -215,14 +211,14 @@ __global__ void __launch_bounds__(256) flow_grad_kernel(const float *__restrict_
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
     const float cw = (float)ws[0], ct = (float)ws[1], c0 = (float)ws[2];
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < vol; idx += (size_t)gridDim.x * blockDim.x) {
+    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
         const Sample<NDIM> s = sample_zero_pad<NDIM, true>(moving, D, H, W, px, py, pz);
         const float t = ld_stream_f(target + idx);
         const float r = fmaf(cw, s.val, fmaf(ct, t, c0));
         store_dflow<NDIM>(dflow, vol, idx, r, s.g);
-    }
+    });
 }
 
 static unsigned flow_grid(size_t vol)
@@ -230,7 +226,7 @@ static unsigned flow_grid(size_t vol)
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    size_t nb = (vol + 255) / 256;
+    size_t nb = (vol + 255) / 256;      // enough CTAs for every SM to hold 8; each strides over row pairs
     const size_t cap = (size_t)sms * 8;
     if (nb > cap) nb = cap;
     if (nb > kFlowMaxBlocks) nb = kFlowMaxBlocks;

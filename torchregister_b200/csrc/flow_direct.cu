@@ -18,6 +18,19 @@
 
 namespace trb {
 
+// row-wise voxel loop over a slab (see flow.cu): f(idx, x, y, zl)
+template <typename F>
+__device__ __forceinline__ void for_each_slab_voxel(int Ds, int H, int W, F f)
+{
+    const int rows = Ds * H;
+    const int rx = threadIdx.x & 127, ry = threadIdx.x >> 7;
+    for (int row = 2 * blockIdx.x + ry; row < rows; row += 2 * gridDim.x) {
+        const int zl = row / H, y = row - zl * H;
+        const size_t base = (size_t)row * W;
+        for (int x = rx; x < W; x += 128) f(base + x, x, y, zl);
+    }
+}
+
 struct DirectParams {
     const float *moving, *target, *flow_in, *halo_lo, *halo_hi;
     float *flow_out, *adam_m, *adam_v, *loss_log;
@@ -110,10 +123,8 @@ __global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectPara
     double acc[6] = {0, 0, 0, 0, 0, 0};
     float s[6] = {0, 0, 0, 0, 0, 0};
     int cnt = 0;
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < slab; idx += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % W);
-        const size_t q = idx / W;
-        const int y = (int)(q % H), zl = (int)(q / H), z = p.z_off + zl;
+    for_each_slab_voxel(Ds, H, W, [&](size_t idx, int x, int y, int zl) {
+        const int z = p.z_off + zl;
         float f[3] = {0.f, 0.f, 0.f};          // f[c]: channel c displaces spatial axis c (0 = D|H first axis)
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) f[c] = ld_stream_f(p.flow_in + (size_t)c * slab + idx);
@@ -140,7 +151,7 @@ __global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectPara
             for (int i = 0; i < 6; ++i) { acc[i] += (double)s[i]; s[i] = 0.f; }
             cnt = 0;
         }
-    }
+    });
 #pragma unroll
     for (int i = 0; i < 6; ++i) acc[i] += (double)s[i];
     __shared__ double red[8][6];
@@ -195,10 +206,8 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
         bc1 = 1.f - powf(p.beta1, (float)p.step);
         bc2s = sqrtf(1.f - powf(p.beta2, (float)p.step));
     }
-    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < slab; idx += (size_t)gridDim.x * blockDim.x) {
-        const int x = (int)(idx % W);
-        const size_t q = idx / W;
-        const int y = (int)(q % H), zl = (int)(q / H), z = p.z_off + zl;
+    for_each_slab_voxel(Ds, H, W, [&](size_t idx, int x, int y, int zl) {
+        const int z = p.z_off + zl;
         float f[3] = {0.f, 0.f, 0.f};
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) f[c] = ld_stream_f(p.flow_in + (size_t)c * slab + idx);
@@ -237,7 +246,7 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
             }
             p.flow_out[o] = nv;
         }
-    }
+    });
 }
 
 constexpr int kDirectMaxBlocks = 4096;
