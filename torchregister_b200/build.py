@@ -48,6 +48,7 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     env = dict(os.environ)
     # the image exports CC/CXX pointing at a gcc wrapper without OpenMP specs; nvcc only needs g++
     extra = ["-DTRB_TIMING"] if os.environ.get("TRB_TIMING") else []
+    extra += ["-D" + d for d in os.environ.get("TRB_DEFINES", "").split() if d]
     cmd = [_nvcc()] + NVCC_FLAGS + extra + ["-ccbin", shutil.which("g++") or "g++", "-o", LIB_PATH] + \
           [os.path.join(CSRC, s) for s in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True, env=env)
