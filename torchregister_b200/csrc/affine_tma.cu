@@ -87,6 +87,8 @@ struct TmaParams {
     int cols_per_pair;                 // tiles_x * tiles_y
     int full_rounds;                   // rounds in which every CTA owns one whole column
     long long tail_tiles;              // tiles of the remaining columns, cut into one span per CTA
+    int use_groups;                    // grid reduction: 1 = 16-CTA groups folded during the launch (many pairs),
+                                       // 0 = the last CTA folds all slots directly with all its warps (few pairs)
 };
 
 struct TileMeta { int ox, oy, oz, fits; };
@@ -499,7 +501,7 @@ __device__ void warp_publish_pair(const float (&acc)[TRB_MOMENTS], float *red /*
         for (int w = 0; w < kConsumerWarps; ++w) s += (double)red[w * kRedLd + v];
         __stcg(mine + v, s);
     }
-    warp_arrive_group(p, pair, G, lane);
+    if (p.use_groups) warp_arrive_group(p, pair, G, lane);
 }
 
 // Run by the LAST CTA to complete its tiles (all 16 warps): per pair, add the group slots in index order
@@ -508,21 +510,47 @@ template <bool FUSED>
 __device__ void final_phase(const TmaParams &p, double *fin_s /*[16][TRB_MOMENTS + 1] smem*/, int G, int warp, int lane)
 {
     constexpr int LD = TRB_MOMENTS + 1;
-    const int n_groups = (G + kGroup - 1) / kGroup;
-    for (int pair = warp; pair < p.n_pairs; pair += kConsumerWarps) {
-        const double2 r = warp_fold_slots(p, pair, G, G + n_groups, lane);
-        double *row = fin_s + warp * LD;
-        row[lane] = r.x;
-        if (lane + 32 < TRB_MOMENTS) row[lane + 32] = r.y;
-        __syncwarp();
-        TRB_T(5);
-        if (FUSED) {
-            if (lane == 0) affine_epilogue<3>(row, p.a, pair);
-        } else {
-            for (int v = lane; v < TRB_MOMENTS; v += 32) p.a.moments_out[(size_t)pair * TRB_MOMENTS + v] = row[v];
+    if (p.use_groups) {
+        const int n_groups = (G + kGroup - 1) / kGroup;
+        for (int pair = warp; pair < p.n_pairs; pair += kConsumerWarps) {
+            const double2 r = warp_fold_slots(p, pair, G, G + n_groups, lane);
+            double *row = fin_s + warp * LD;
+            row[lane] = r.x;
+            if (lane + 32 < TRB_MOMENTS) row[lane + 32] = r.y;
+            __syncwarp();
+            if (FUSED) {
+                if (lane == 0) affine_epilogue<3>(row, p.a, pair);
+            } else {
+                for (int v = lane; v < TRB_MOMENTS; v += 32) p.a.moments_out[(size_t)pair * TRB_MOMENTS + v] = row[v];
+            }
+            __syncwarp();
+        }
+        return;
+    }
+    // few pairs (n_pairs <= 16): no group stage — every warp folds a contiguous range of one pair's G slots
+    // (one round trip), the ranges are combined in index order, one warp per pair runs the epilogue
+    const int np = p.n_pairs;
+    const int wpp = kConsumerWarps / np;                     // warps per pair
+    const int pl = warp / wpp, part = warp - pl * wpp;
+    if (pl < np) {
+        const double2 r = warp_fold_slots(p, pl, G * part / wpp, G * (part + 1) / wpp, lane);
+        fin_s[warp * LD + lane] = r.x;
+        if (lane + 32 < TRB_MOMENTS) fin_s[warp * LD + lane + 32] = r.y;
+    }
+    __syncthreads();
+    if (warp < np) {
+        double *row = fin_s + (warp * wpp) * LD;
+        for (int v = lane; v < TRB_MOMENTS; v += 32) {
+            double t = row[v];
+            for (int q = 1; q < wpp; ++q) t += row[q * LD + v];
+            row[v] = t;
         }
         __syncwarp();
-        TRB_T(6);
+        if (FUSED) {
+            if (lane == 0) affine_epilogue<3>(row, p.a, warp);
+        } else {
+            for (int v = lane; v < TRB_MOMENTS; v += 32) p.a.moments_out[(size_t)warp * TRB_MOMENTS + v] = row[v];
+        }
     }
 }
 
@@ -604,7 +632,7 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
         if (touched[pr >> 5] & (1u << (pr & 31))) continue;
         double *mine = slot_ptr(p, pr, b);
         for (int v = lane; v < TRB_MOMENTS; v += 32) __stcg(mine + v, 0.0);
-        warp_arrive_group(p, pr, G, lane);
+        if (p.use_groups) warp_arrive_group(p, pr, G, lane);
     }
     __shared__ ColConst colc[kConsumerWarps];   // each warp's copy of the footprint constants of `ahead`'s column
     if (threadIdx.x == 0) {                     // prologue: fill the ring
@@ -861,6 +889,7 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
     if (grid_ll > total_cols * p.tiles_z) grid_ll = total_cols * p.tiles_z;
     if (grid_ll > kMaxSlots - 64) grid_ll = kMaxSlots - 64;       // slots G.. hold the group sums
     const int grid = (int)grid_ll;
+    p.use_groups = n_pairs > kConsumerWarps ? 1 : 0;
     p.full_rounds = (int)(total_cols / grid);
     p.tail_tiles = (total_cols - (long long)p.full_rounds * grid) * p.tiles_z;
     const size_t smem = (size_t)kStages * L::kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * sizeof(TileMeta);
