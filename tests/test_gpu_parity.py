@@ -439,3 +439,25 @@ def test_default_weights_with_nmi_vs_reference_golden():
     losses = reg.losses.cpu().numpy()
     assert np.allclose(losses, g["losses"], rtol=2e-4, atol=2e-4), (losses, g["losses"])
     assert np.abs(reg.theta.cpu().numpy() - g["best_theta"]).max() <= 1e-5
+
+
+def test_tma_kernel_many_pairs_group_reduction():
+    """> 16 pairs per launch switches the grid reduction to the grouped form (16-CTA groups folded during the
+    launch); it must agree with per-pair launches and be bit-reproducible."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    shape = (16, 32, 32)
+    n = 21
+    pairs = [make_pair(shape, "rigid", seed=400 + i) for i in range(n)]
+    mov = torch.cat([p[0] for p in pairs]).to(DEV)
+    tgt = torch.cat([p[1] for p in pairs]).to(DEV)
+    p0 = torch.tensor([[0.005 * (i + 1), -0.01, 0.02, 0.05, -0.05, 0.02] for i in range(n)], device=DEV)
+    a = _run(TF, mov, tgt, "rigid", p0, 4, 1e-3, (0.5, 0.5), "auto")
+    b = _run(TF, mov, tgt, "rigid", p0, 4, 1e-3, (0.5, 0.5), "auto")
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
+    for i in (0, 7, 20):
+        s = _run(TF, mov[i:i + 1], tgt[i:i + 1], "rigid", p0[i:i + 1], 4, 1e-3, (0.5, 0.5), "auto")
+        assert torch.allclose(s[0][0], a[0][i], rtol=1e-4)
+        assert torch.allclose(s[1][0], a[1][i], atol=2e-6)
+    d = _run(TF, mov, tgt, "rigid", p0, 4, 1e-3, (0.5, 0.5), "direct")
+    assert torch.allclose(a[0], d[0], rtol=1e-4) and torch.allclose(a[1], d[1], atol=2e-6)

@@ -527,7 +527,7 @@ __device__ void final_phase(const TmaParams &p, double *fin_s /*[16][TRB_MOMENTS
         }
         return;
     }
-    // few pairs (n_pairs <= 16): no group stage — every warp folds a contiguous range of one pair's G slots
+    // one or two pairs: no group stage — every warp folds a contiguous range of one pair's G slots
     // (one round trip), the ranges are combined in index order, one warp per pair runs the epilogue
     const int np = p.n_pairs;
     const int wpp = kConsumerWarps / np;                     // warps per pair
@@ -758,8 +758,11 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                 }
             }
             ++it;
-            if (ahead.phase != 2 && iter_next(ahead, p, b, G) && ahead.phase != 2 && lane == 0)
-                compute_col(colc[warp], ahead, p, coef_s, inv_d2, zoff);      // once per column, per warp
+            if (ahead.phase != 2) {
+                const bool moved = iter_next(ahead, p, b, G);
+                if (moved && ahead.phase != 2 && lane == 0)
+                    compute_col(colc[warp], ahead, p, coef_s, inv_d2, zoff);      // once per column, per warp
+            }
             __syncwarp();
             col_done = iter_next(cur, p, b, G);
         }
@@ -889,7 +892,7 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
     if (grid_ll > total_cols * p.tiles_z) grid_ll = total_cols * p.tiles_z;
     if (grid_ll > kMaxSlots - 64) grid_ll = kMaxSlots - 64;       // slots G.. hold the group sums
     const int grid = (int)grid_ll;
-    p.use_groups = n_pairs > kConsumerWarps ? 1 : 0;
+    p.use_groups = n_pairs > 2 ? 1 : 0;        // measured: the direct fold only pays for one or two pairs
     p.full_rounds = (int)(total_cols / grid);
     p.tail_tiles = (total_cols - (long long)p.full_rounds * grid) * p.tiles_z;
     const size_t smem = (size_t)kStages * L::kStageBytes + 2 * kStages * sizeof(uint64_t) + kStages * sizeof(TileMeta);
