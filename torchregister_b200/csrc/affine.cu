@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const float *__restric
     for (int i = 0; i < NT; ++i) th[i] = __ldg(theta + i);
     const size_t HW = (size_t)H * W, vol = HW * (NDIM == 3 ? D : 1);
     const float hw = 0.5f * W, hh = 0.5f * H, hd = 0.5f * D;
-    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
+    for_each_voxel<2>(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         const float xv = __ldg(xb + x), yv = __ldg(yb + y);
         if (NDIM == 3) {
             const float zv = __ldg(zb + z);

@@ -27,6 +27,7 @@ __device__ __forceinline__ void for_each_slab_voxel(int Ds, int H, int W, F f)
     for (int row = 2 * blockIdx.x + ry; row < rows; row += 2 * gridDim.x) {
         const int zl = row / H, y = row - zl * H;
         const size_t base = (size_t)row * W;
+#pragma unroll 1
         for (int x = rx; x < W; x += 128) f(base + x, x, y, zl);
     }
 }
@@ -120,9 +121,7 @@ __global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectPara
     const int W = p.W, H = p.H, D = NDIM == 3 ? p.D : 1, Ds = NDIM == 3 ? p.Ds : 1;
     const size_t HW = (size_t)H * W, slab = HW * Ds;
     const float wx = smooth_weight<NDIM>(p, 0), wy = smooth_weight<NDIM>(p, 1), wz = NDIM == 3 ? smooth_weight<NDIM>(p, 2) : 0.f;
-    double acc[6] = {0, 0, 0, 0, 0, 0};
-    float s[6] = {0, 0, 0, 0, 0, 0};
-    int cnt = 0;
+    float s[6] = {0, 0, 0, 0, 0, 0};          // fp32 per thread (~50 voxels), fp64 above (see flow.cu)
     for_each_slab_voxel(Ds, H, W, [&](size_t idx, int x, int y, int zl) {
         const int z = p.z_off + zl;
         float f[3] = {0.f, 0.f, 0.f};          // f[c]: channel c displaces spatial axis c (0 = D|H first axis)
@@ -146,14 +145,10 @@ __global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectPara
             }
             s[5] += sm;
         }
-        if (++cnt == 64) {
-#pragma unroll
-            for (int i = 0; i < 6; ++i) { acc[i] += (double)s[i]; s[i] = 0.f; }
-            cnt = 0;
-        }
     });
+    double acc[6];
 #pragma unroll
-    for (int i = 0; i < 6; ++i) acc[i] += (double)s[i];
+    for (int i = 0; i < 6; ++i) acc[i] = (double)s[i];
     __shared__ double red[8][6];
     __shared__ bool is_last;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
