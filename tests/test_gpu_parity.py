@@ -461,3 +461,25 @@ def test_tma_kernel_many_pairs_group_reduction():
         assert torch.allclose(s[1][0], a[1][i], atol=2e-6)
     d = _run(TF, mov, tgt, "rigid", p0, 4, 1e-3, (0.5, 0.5), "direct")
     assert torch.allclose(a[0], d[0], rtol=1e-4) and torch.allclose(a[1], d[1], atol=2e-6)
+
+
+def test_register_batch_extension_and_dtype():
+    """EXTENSION: Register on a batch of independent pairs ([N,1,...]) equals N single-pair runs; float64 /
+    CPU inputs are moved to float32 on the device like the reference's `.to(dtype=torch.float, device=device)`."""
+    import torchregister_b200 as tr
+    from torchregister_b200.synth import make_pair
+    shape = (24, 32, 40)
+    pairs = [make_pair(shape, "rigid", seed=500 + i) for i in range(3)]
+    mov = torch.cat([p[0] for p in pairs]).double()
+    tgt = torch.cat([p[1] for p in pairs]).double()
+    p0 = torch.tensor([[0.01 * (i + 1), -0.01, 0.03, 0.05, -0.05, 0.02] for i in range(3)])
+    reg = tr.Register(mode="rigid", device=DEV, weight=[0.5, 0.5, 0.0])
+    reg.optim(mov, tgt, lr=1e-3, max_epochs=5, reg0=p0)
+    assert tuple(reg.theta.shape) == (3, 3, 4)
+    out = reg(mov)
+    assert tuple(out.shape) == tuple(mov.shape) and out.dtype == torch.float32
+    for i in range(3):
+        one = tr.Register(mode="rigid", device=DEV, weight=[0.5, 0.5, 0.0])
+        one.optim(mov[i:i + 1], tgt[i:i + 1], lr=1e-3, max_epochs=5, reg0=p0[i])
+        assert torch.allclose(one.theta[0], reg.theta[i], atol=2e-6)
+        assert torch.allclose(one(mov[i:i + 1]), out[i:i + 1], atol=1e-5)

@@ -55,8 +55,11 @@ class Register():
         `reg0` (keyword-only extension): initial rigid parameters instead of the torch.rand draw.
         '''
         self._check_device()
-        moving = moving.to(self.device)
-        target = target.to(self.device)
+        # the reference works in float32 throughout (dtype=torch.float, warpings.py:48,55; utils.py:347)
+        moving = moving.to(device=self.device, dtype=__import__('torch').float32)
+        target = target.to(device=self.device, dtype=__import__('torch').float32)
+        if self.mode == 'flow' and moving.shape[0] != 1:
+            raise ValueError("flow mode registers one pair per call (moving must be [1,1,...])")
         both = self.criterion is not None and self.weight is not None
         if self.mode == 'flow' and self.flow_param == 'direct':
             kw = dict(lr=lr, max_epochs=max_epochs, smooth=self.smooth, optimiser=self.optm)
@@ -94,14 +97,14 @@ class Register():
             if reg0 is not None and self.mode == 'rigid':
                 kw.update(reg0=reg0)
             _, theta = fn(moving, target, **kw)
-            self.theta = theta[-1]
-            self.losses = probs[0].losses[0]          # device tensor: per-epoch loss log (harmless superset)
+            self.theta = theta[-1]                    # best theta, [1,nd,nd+1] ([N,nd,nd+1] for a batch: extension)
+            self.losses = probs[0].losses[0] if moving.shape[0] == 1 else probs[0].losses   # device tensor(s): loss log
 
     def __call__(self, moving):
         '''
         Warp `moving` [1,c,...] with the deformation found by `optim` (reference torchregister.py:108-129).
         '''
-        moving = moving.to(self.device)
+        moving = moving.to(device=self.device, dtype=__import__('torch').float32)
         if self.mode == 'flow':
             return self.warp(moving)                 # all channels in one launch
         return self.warp(self.theta, moving)

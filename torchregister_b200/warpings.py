@@ -43,7 +43,12 @@ class _AffineWarpFn(torch.autograd.Function):
 def get_affine_warp(theta, moving):
     """warped = grid_sample(moving, affine_grid(theta), bilinear, zeros, align_corners=False)
     (reference warpings.py:18-26).  theta: [1,2,3] / [1,3,4] or flat [*,6] / [*,12].
-    One fused kernel, no materialised grid; differentiable w.r.t. theta."""
+    One fused kernel, no materialised grid; differentiable w.r.t. theta.  EXTENSION: a batch
+    moving [N,C,...] with theta [N,nd,nd+1] is warped pair-wise (the reference supports N == 1 only)."""
+    if moving.shape[0] > 1:
+        nd = moving.dim() - 2
+        th = theta.reshape(moving.shape[0], nd, nd + 1)
+        return torch.cat([_AffineWarpFn.apply(th[i:i + 1], moving[i:i + 1]) for i in range(moving.shape[0])], dim=0)
     return _AffineWarpFn.apply(theta, moving)
 
 
@@ -73,6 +78,13 @@ def _reject_edges(grad_edges):
             "the reference itself raises at its default padding. Pass grad_edges=False.")
 
 
+def _warp_batch(theta, moving):
+    """theta [N, nd, nd+1] applied pair-wise to moving [N, C, ...] (N == 1: the reference's case)."""
+    if moving.shape[0] == 1:
+        return TF.warp_affine(theta, moving)
+    return torch.cat([TF.warp_affine(theta[i], moving[i:i + 1]) for i in range(moving.shape[0])], dim=0)
+
+
 def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, want_warped=True):
     w_mse, w_ncc, w_nmi = weights3
     prob = TF.AffineProblem(moving, target, mode, params0, epochs)
@@ -86,21 +98,23 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
         nmi = NMILoss()
         nd = moving.dim() - 2
         n_slices = int(moving.shape[2])
-        extra = torch.zeros(1, 13, dtype=torch.float64, device=moving.device)
+        n_pairs = int(moving.shape[0])
+        extra = torch.zeros(n_pairs, 13, dtype=torch.float64, device=moving.device)
         for _ in range(epochs):
             theta = prob.theta
             mom = prob.moments(0, n_slices)
-            warped = TF.warp_affine(theta, moving).requires_grad_(True)
-            term = w_nmi * nmi(target, warped)
-            (gw,) = torch.autograd.grad(term, warped)
-            extra[0, 0] = term.detach().double()
-            extra[0, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta, moving, gw.contiguous()).reshape(-1)
+            for i in range(n_pairs):
+                warped = TF.warp_affine(theta[i], moving[i:i + 1]).requires_grad_(True)
+                term = w_nmi * nmi(target[i:i + 1], warped)
+                (gw,) = torch.autograd.grad(term, warped)
+                extra[i, 0] = term.detach().double()
+                extra[i, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta[i], moving[i:i + 1], gw.contiguous()).reshape(-1)
             prob.apply(mom, lr, w_mse, w_ncc, extra=extra)
     final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
     # the reference keeps the warped volumes of the final and best epochs; we never write them during
     # the loop and re-create them here only when the caller wants them (Register.optim does not)
-    final_warped = TF.warp_affine(final_theta, moving) if want_warped else None
-    best_warped = TF.warp_affine(best_theta, moving) if want_warped else None
+    final_warped = _warp_batch(final_theta, moving) if want_warped else None
+    best_warped = _warp_batch(best_theta, moving) if want_warped else None
     if debug:
         print('losses (first, best, last): %s' % (prob.losses[0, [0, -1]].tolist(),))
     return prob, [final_warped, best_warped], [final_theta, best_theta]
@@ -116,7 +130,7 @@ def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu',
     TF.require_cuda(moving, "moving")
     nd = moving.dim() - 2
     wp = similarity_weights(criterions, weights, "affine_register")
-    ident = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)
+    ident = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)      # every pair starts at identity
     prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug, _want_warped)
     if _problem_out is not None:
         _problem_out.append(prob)
@@ -134,7 +148,8 @@ def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', 
     wp = similarity_weights(criterions, weights, "rigid_register")
     npar = 6 if moving.dim() == 5 else 3
     if reg0 is None:
-        reg0 = torch.rand(npar, device=moving.device)
+        # one draw per pair; for N == 1 this is the reference's torch.rand(6|3) on the data's device
+        reg0 = torch.rand(npar, device=moving.device) if moving.shape[0] == 1 else torch.rand(moving.shape[0], npar, device=moving.device)
     if debug:
         print(reg0)
     prob, warped, theta = _affine_like("rigid", moving, target, lr, epochs, wp, reg0, debug, _want_warped)
