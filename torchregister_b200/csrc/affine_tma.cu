@@ -493,6 +493,10 @@ __device__ void warp_publish_pair(const float (&acc)[TRB_MOMENTS], float *red /*
         asm volatile("atom.acq_rel.cta.shared::cta.add.u32 %0, [%1], 1;" : "=r"(old) : "r"(smem_u32(cnt)) : "memory");
     old = __shfl_sync(kFull, old, 0);
     if (old != kConsumerWarps - 1) return;
+    // lane 0's acq_rel atomic synchronises with the other warps' (release) arrivals; __syncwarp extends that
+    // ordering to the remaining lanes before they read the 16 rows.  (compute-sanitizer racecheck flags these
+    // reads because it only models barriers, not atomics-based hand-over.)
+    __syncwarp();
     if (lane == 0) *cnt = 0u;
     double *mine = slot_ptr(p, pair, blockIdx.x);
     for (int v = lane; v < TRB_MOMENTS; v += 32) {
