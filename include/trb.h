@@ -200,6 +200,27 @@ int trb_flow_direct_update(int ndim, const float *moving_dev, const float *targe
                            int optimiser, float beta1, float beta2, float adam_eps, int step_index,
                            float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, void *stream);
 
+/* Fused 3-D epoch: ONE streaming pass per epoch (32 B/voxel SGD, 80 B/voxel Adam) instead of stats + update.
+ * Needs 3*Ds*H*W < 2^31.  moments6_dev is read and then overwritten:
+ *   in : [0..4] similarity sums of flow_in over the WHOLE volume (only used when w_ncc != 0: run
+ *        trb_flow_direct_stats with lambda 0 once before the first epoch, all-reduced when sharded);
+ *   out: [0..4] this slab's similarity sums of flow_out (w_ncc != 0) or of flow_in (w_ncc == 0), [5] this slab's
+ *        smoothness sum of flow_in.  Sharded callers all-reduce the 6 values between epochs.
+ * loss_log_dev[epoch-1] is completed by the call for `epoch` when complete_prev != 0 (= the previous call was a
+ * fused step with the same weights and no trb_flow_direct_finish in between), the last one by
+ * trb_flow_direct_finish (epochs_done = number of epochs done).  workspace as trb_flow_direct_workspace_bytes(), the same one for every call. */
+int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
+                         const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                         const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                         double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                         int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                         float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
+                         void *workspace_dev, size_t workspace_bytes, void *stream);
+
+int trb_flow_direct_finish(const double *moments6_dev, int D, int H, int W, float w_mse, float w_ncc,
+                           float smooth_lambda, float *loss_log_dev, int epochs_done,
+                           void *workspace_dev, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

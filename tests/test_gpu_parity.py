@@ -415,6 +415,66 @@ def test_direct_flow_slabs_equal_whole_volume():
         assert torch.allclose(slabs[0].losses, whole.losses, rtol=1e-5)
 
 
+@pytest.mark.parametrize("shape", [(13, 19, 37), (40, 33, 70)])
+@pytest.mark.parametrize("opt,weights,smooth", [("sgd", (1.0, 0.0), 0.0), ("sgd", (1.0, 0.0), 4.0), ("sgd", (0.5, 0.5), 4.0),
+                                                ("sgd", (0.0, 1.0), 0.0), ("adam", (0.5, 0.5), 4.0), ("adam", (1.0, 0.0), 0.0)])
+def test_direct_flow_fused_epoch_equals_two_pass(shape, opt, weights, smooth):
+    """trb_flow_direct_step (one pass per epoch, z-marching tiles) against stats + update on ragged shapes: several
+    x/y tiles with inactive threads, several z chunks, every template variant."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair, smooth_flow
+    mov, tgt = (t.to(DEV) for t in make_pair(shape, "flow"))
+    flow0 = (0.3 * smooth_flow(shape, 1.0)).to(DEV)
+    lr = 0.5 if opt == "sgd" else 0.05
+    a = TF.DirectFlowProblem(mov, tgt, 4, flow0=flow0, optimiser=opt)
+    b = TF.DirectFlowProblem(mov, tgt, 4, flow0=flow0, optimiser=opt)
+    assert a.fused
+    a.run(2, lr, weights[0], weights[1], smooth)
+    a.run(2, lr, weights[0], weights[1], smooth)       # a second run() continues the loss log correctly
+    b.run_two_pass(4, lr, weights[0], weights[1], smooth)
+    assert torch.allclose(a.losses, b.losses, rtol=2e-5, atol=1e-7), (a.losses, b.losses)
+    atol, frac_ok = (1e-6, 0.0) if opt == "sgd" else (1e-4, 2e-3)   # Adam: see the slab test below
+    bad = ((a.flow - b.flow).abs() > atol).float().mean().item()
+    assert bad <= frac_ok, (bad, (a.flow - b.flow).abs().max().item())
+
+
+def test_direct_flow_fused_slabs_equal_whole_volume():
+    """The fused epoch in slab form (what ShardedDirectFlow drives): halos, summed moments, finish."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair, smooth_flow
+    shape = (18, 20, 40)
+    mov, tgt = (t.to(DEV) for t in make_pair(shape, "flow"))
+    flow0 = (0.3 * smooth_flow(shape, 1.0)).to(DEV)
+    cuts = [(0, 7), (7, 12), (12, 18)]
+    for w in ((0.5, 0.5), (1.0, 0.0)):
+        whole = TF.DirectFlowProblem(mov, tgt, 3, flow0=flow0)
+        whole.run(3, 0.5, w[0], w[1], 4.0)
+        slabs = [TF.DirectFlowProblem(mov, tgt[:, :, a:b].contiguous(), 3, z_off=a, flow0=flow0[:, :, a:b].contiguous())
+                 for a, b in cuts]
+
+        def share():
+            total = sum(s.moments.clone() for s in slabs)
+            for s in slabs:
+                s.moments.copy_(total)
+
+        if slabs[0].prime(w[1]):
+            for s in slabs[1:]:
+                s.prime(w[1])
+            share()
+        for _ in range(3):
+            bounds = [s.boundary_slices() for s in slabs]
+            halos = [(bounds[i - 1][1] if i > 0 else None, bounds[i + 1][0] if i < len(slabs) - 1 else None) for i in range(len(slabs))]
+            for i, s in enumerate(slabs):
+                s.step(0.5, w[0], w[1], 4.0, *halos[i])
+            share()
+        for s in slabs:
+            s.finish(w[0], w[1], 4.0)
+        got = torch.cat([s.flow for s in slabs], dim=2)
+        assert (got - whole.flow).abs().max().item() <= 1e-6
+        for s in slabs:
+            assert torch.allclose(s.losses, whole.losses, rtol=1e-5), (s.losses, whole.losses)
+
+
 def test_register_direct_flow_extension():
     import torchregister_b200 as tr
     from torchregister_b200.synth import make_pair

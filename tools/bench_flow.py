@@ -23,7 +23,11 @@ us = timeit(lambda: TF.flow_loss_grad(mov, tgt, flow, 1.0, 0.0)); out["flow_node
 us = timeit(lambda: TF.warp_flow(mov, flow)); out["warp_flow"] = {"us": us, "alg_GBps": 20 * vox / us / 1e3}
 th = torch.tensor([[1.01, .02, -.01, .01], [-.02, .99, .01, 0.], [.01, -.01, 1., .02]], device=dev)
 us = timeit(lambda: TF.warp_affine(th, mov)); out["warp_affine"] = {"us": us, "alg_GBps": 8 * vox / us / 1e3}
-for opt, bpv in (("sgd", 52), ("adam", 100)):
-    prob = TF.DirectFlowProblem(mov, tgt, 100000, optimiser=opt)
-    us = timeit(lambda: prob.run(1, 0.05, 0.5, 0.5, 2.0)); out["direct_flow_epoch_" + opt] = {"us": us, "alg_GBps": bpv * vox / us / 1e3, "bytes_per_voxel": bpv}
+for opt, bpv2, bpv1 in (("sgd", 52, 32), ("adam", 100, 80)):
+    prob = TF.DirectFlowProblem(mov, tgt, 1000000, optimiser=opt)
+    us = timeit(lambda: prob.run_two_pass(1, 0.05, 0.5, 0.5, 2.0)); out["direct_flow_two_pass_" + opt] = {"us": us, "alg_GBps": bpv2 * vox / us / 1e3, "bytes_per_voxel": bpv2}
+    for name, w, sm in (("mse+ncc_smooth", (0.5, 0.5), 2.0), ("mse_smooth", (1.0, 0.0), 2.0), ("mse+ncc", (0.5, 0.5), 0.0), ("mse", (1.0, 0.0), 0.0)):
+        prob = TF.DirectFlowProblem(mov, tgt, 1000000, optimiser=opt)
+        us = timeit(lambda: prob.run(10, 0.05, w[0], w[1], sm)) / 10
+        out["direct_flow_fused_%s_%s" % (opt, name)] = {"us": us, "alg_GBps": bpv1 * vox / us / 1e3, "bytes_per_voxel": bpv1}
 print(json.dumps({"size": S, "results": out}))

@@ -42,6 +42,7 @@ struct DirectParams {
     float w_mse, w_ncc, lambda, lr;
     int optimiser, step, epoch;
     float beta1, beta2, eps;
+    int complete_prev;      // fused step: moments[5] / the stash belong to the previous call, finish its loss entry
 };
 
 __device__ __forceinline__ float dflow_pos(int S, int i, float f)
@@ -244,6 +245,222 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
     });
 }
 
+// ---- fused single-pass epoch (3-D) -------------------------------------------------------------------------
+// One kernel per epoch instead of two.  A CTA owns a 32x8 (x,y) tile and marches along z over a chunk of
+// slices: the z-1 / z / z+1 flow values of a voxel are the thread's own registers (sliding window), the x+-1 /
+// y+-1 neighbours come from a double-buffered shared tile with a one-cell halo, so every flow value is read from
+// global once (+ halo).  The similarity moments the NEXT epoch's coefficients need are those of the flow this
+// kernel writes, so (NEXT) the new position is sampled right away while its cells are still in L1; the MSE-only
+// case (coefficients independent of the moments) accumulates the moments of the incoming flow instead.
+//   moments[0..4]: in  = similarity sums of flow_in over the whole volume (all-reduced when sharded; NEXT only)
+//                  out = this slab's sums of flow_out (NEXT) / of flow_in (!NEXT)
+//   moments[5]   : out = this slab's smoothness sum of flow_in
+// loss_log[e] = similarity(flow_e) + lambda * smooth(flow_e) is therefore complete one call later: the prologue
+// of epoch e+1 (or trb_flow_direct_finish after the last epoch) writes it; NEXT keeps similarity(flow_e) in a
+// workspace scalar meanwhile.  Algorithmic traffic: 32 B/voxel (SGD), 80 B/voxel (Adam).
+constexpr int kTX = 32, kTY = 8;
+
+__device__ __forceinline__ void direct_log_losses(const DirectParams &p, const double *m, bool next, bool new_epoch,
+                                                  double *stash)
+{
+    const double n = (double)p.D * p.H * p.W;
+    const double sim = loss_coefficients(n, m[0], m[1], m[2], m[3], m[4], (double)p.w_mse, (double)p.w_ncc).loss;
+    if (!p.loss_log) return;
+    const bool prev = p.complete_prev && p.epoch > 0;
+    if (next) {
+        if (prev) p.loss_log[p.epoch - 1] = (float)(*stash + (double)p.lambda * m[5]);
+        if (new_epoch) { *stash = sim; p.loss_log[p.epoch] = (float)sim; }
+    } else if (prev) {
+        p.loss_log[p.epoch - 1] = (float)(sim + (double)p.lambda * m[5]);
+    }
+}
+
+template <bool NEXT, bool ADAM, bool SMOOTH>
+__global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectParams p, const int tiles_x, const int tiles_y,
+                                                               const int zc)
+{
+    const int W = p.W, H = p.H, D = p.D, Ds = p.Ds;
+    const int HW = H * W, slab = HW * Ds;              // host guarantees 3*slab < 2^31
+    __shared__ float tile[2][3][kTY + 2][kTX + 2];
+    __shared__ float coef[3];
+    __shared__ double red[8][6];
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        const double n = (double)D * H * W;
+        const LossCoef lc = loss_coefficients(n, p.moments[0], p.moments[1], p.moments[2], p.moments[3], p.moments[4],
+                                              (double)p.w_mse, (double)p.w_ncc);
+        coef[0] = (float)lc.cw; coef[1] = (float)lc.ct; coef[2] = (float)lc.c0;
+        if (blockIdx.x == 0) direct_log_losses(p, p.moments, NEXT, true, (double *)p.ticket + 1);
+    }
+    __syncthreads();
+    const float cw = coef[0], ct = coef[1], c0 = coef[2];
+    const float wx = smooth_weight<3>(p, 0), wy = smooth_weight<3>(p, 1), wz = smooth_weight<3>(p, 2);
+    const float sx = 2.f * p.lambda * wx, sy = 2.f * p.lambda * wy, sz = 2.f * p.lambda * wz;
+    float step_size = p.lr, inv_bc2s = 1.f;           // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+    if (ADAM) {
+        step_size = p.lr / (1.f - powf(p.beta1, (float)p.step));
+        inv_bc2s = 1.f / sqrtf(1.f - powf(p.beta2, (float)p.step));
+    }
+    const float b1 = p.beta1, b2 = p.beta2, ob1 = 1.f - p.beta1, ob2 = 1.f - p.beta2;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    // halo cell of the shared tile this thread refreshes every slice (240 cells: 3 channels x (2 rows + 2 columns))
+    int hc = 0, hx = 0, hy = 0;
+    const bool halo_thread = SMOOTH && threadIdx.x < 240;
+    if (halo_thread) {
+        hc = threadIdx.x / 80;
+        const int r = threadIdx.x - hc * 80;
+        if (r < 32) { hy = -1; hx = r; }
+        else if (r < 64) { hy = kTY; hx = r - 32; }
+        else if (r < 72) { hx = -1; hy = r - 64; }
+        else { hx = kTX; hy = r - 72; }
+    }
+    const int tiles_xy = tiles_x * tiles_y;
+    const int chunks = (Ds + zc - 1) / zc;
+    const int items = tiles_xy * chunks;
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (int item = blockIdx.x; item < items; item += gridDim.x) {
+        const int chunk = item / tiles_xy, t2 = item - chunk * tiles_xy;
+        const int by = t2 / tiles_x, bx = t2 - by * tiles_x;
+        const int x = bx * kTX + tx, y = by * kTY + ty;
+        const bool active = x < W && y < H;
+        const int xy = y * W + x;
+        const int zl0 = chunk * zc, zl1 = min(zl0 + zc, Ds);
+        int hoff = -1;
+        if (halo_thread) {
+            const int gx = bx * kTX + hx, gy = by * kTY + hy;
+            if (gx >= 0 && gx < W && gy >= 0 && gy < H) hoff = hc * slab + gy * W + gx;
+        }
+        float fm[3] = {0.f, 0.f, 0.f}, fc[3] = {0.f, 0.f, 0.f}, fp[3] = {0.f, 0.f, 0.f}, hcur = 0.f;
+        if (active) {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) {
+                fc[c] = ld_stream_f(p.flow_in + c * slab + zl0 * HW + xy);
+                if (SMOOTH) {
+                    if (zl0 > 0) fm[c] = __ldg(p.flow_in + c * slab + (zl0 - 1) * HW + xy);
+                    else if (p.z_off > 0) fm[c] = __ldg(p.halo_lo + c * HW + xy);
+                    else fm[c] = fc[c];
+                }
+            }
+        }
+        if (hoff >= 0) hcur = __ldg(p.flow_in + hoff + zl0 * HW);
+        __syncthreads();                                   // the previous item's readers are done with the tile
+        for (int zl = zl0; zl < zl1; ++zl) {
+            const int z = p.z_off + zl, b = zl & 1;
+            const int o = zl * HW + xy;
+            float t = 0.f, am[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f};
+            if (active) {
+                t = ld_stream_f(p.target + o);
+                if (ADAM) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { am[c] = __ldcs(p.adam_m + c * slab + o); av[c] = __ldcs(p.adam_v + c * slab + o); }
+                }
+                // next slice into registers while this one is processed
+                if (zl + 1 < Ds) {
+                    if (SMOOTH || zl + 1 < zl1) {
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) fp[c] = ld_stream_f(p.flow_in + c * slab + o + HW);
+                    }
+                } else if (SMOOTH) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) fp[c] = (z + 1 < D) ? __ldg(p.halo_hi + c * HW + xy) : fc[c];
+                }
+            }
+            if (SMOOTH) {
+                if (active) {
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) tile[b][c][ty + 1][tx + 1] = fc[c];
+                }
+                if (hoff >= 0) {
+                    tile[b][hc][hy + 1][hx + 1] = hcur;
+                    if (zl + 1 < zl1) hcur = __ldg(p.flow_in + hoff + (zl + 1) * HW);
+                }
+                __syncthreads();
+            }
+            if (active) {
+                const float pz = dflow_pos(D, z, fc[0]), py = dflow_pos(H, y, fc[1]), px = dflow_pos(W, x, fc[2]);
+                float val, g[3];
+                sample3<3>(p.moving, D, H, W, px, py, pz, val, g);
+                const float r = fmaf(cw, val, fmaf(ct, t, c0));
+                float nv[3];
+                float sm = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    float gr = r * g[2 - c];               // channel c <-> sampling coordinate 2-c
+                    if (SMOOTH) {
+                        const float f = fc[c];
+                        const float xm = x > 0 ? tile[b][c][ty + 1][tx] : f, xp = x + 1 < W ? tile[b][c][ty + 1][tx + 2] : f;
+                        const float ym = y > 0 ? tile[b][c][ty][tx + 1] : f, yp = y + 1 < H ? tile[b][c][ty + 2][tx + 1] : f;
+                        const float zm = fm[c], zp = fp[c];
+                        const float dxp = xp - f, dyp = yp - f, dzp = zp - f;
+                        float st = sx * ((f - xm) - dxp);
+                        st = fmaf(sy, (f - ym) - dyp, st);
+                        st = fmaf(sz, (f - zm) - dzp, st);
+                        gr += st;
+                        sm = fmaf(wx * dxp, dxp, sm);
+                        sm = fmaf(wy * dyp, dyp, sm);
+                        sm = fmaf(wz * dzp, dzp, sm);
+                    }
+                    if (!ADAM) {
+                        nv[c] = fc[c] - p.lr * gr;
+                    } else {
+                        am[c] = fmaf(b1, am[c], ob1 * gr);
+                        av[c] = fmaf(b2, av[c], ob2 * gr * gr);
+                        nv[c] = fmaf(-step_size, __fdividef(am[c], fmaf(sqrtf(av[c]), inv_bc2s, p.eps)), fc[c]);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    __stcs(p.flow_out + c * slab + o, nv[c]);
+                    if (ADAM) { __stcs(p.adam_m + c * slab + o, am[c]); __stcs(p.adam_v + c * slab + o, av[c]); }
+                }
+                float wv = val;
+                if (NEXT) {
+                    const float qz = dflow_pos(D, z, nv[0]), qy = dflow_pos(H, y, nv[1]), qx = dflow_pos(W, x, nv[2]);
+                    float g2[3];
+                    sample3<3>(p.moving, D, H, W, qx, qy, qz, wv, g2);
+                }
+                s[0] += t; s[1] += wv;
+                s[2] = fmaf(t, t, s[2]); s[3] = fmaf(wv, wv, s[3]); s[4] = fmaf(t, wv, s[4]);
+                s[5] += sm;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) { fm[c] = fc[c]; fc[c] = fp[c]; }
+            }
+        }
+    }
+    // fp32 per thread (tens of voxels), fp64 above; deterministic grid reduction (see the stats kernel)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum((double)s[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        __stcg(p.partials + (size_t)blockIdx.x * 6 + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < 6) {
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(p.partials + (size_t)b * 6 + warp);
+        v = warp_sum(v);
+        if (lane == 0) p.moments[warp] = v;
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
+__global__ void flow_direct_finish_kernel(const DirectParams p, const int next)
+{
+    if (threadIdx.x == 0 && blockIdx.x == 0) direct_log_losses(p, p.moments, next != 0, false, (double *)p.ticket + 1);
+}
+
 constexpr int kDirectMaxBlocks = 4096;
 
 static unsigned direct_grid(size_t n)
@@ -260,13 +477,13 @@ static unsigned direct_grid(size_t n)
 
 static int fill_direct(DirectParams &p, int ndim, const float *moving, const float *target, const float *flow_in,
                        const float *halo_lo, const float *halo_hi, int D, int H, int W, int z_off, int Ds,
-                       double *moments, void *ws, size_t ws_bytes)
+                       double *moments, void *ws, size_t ws_bytes, float lambda)
 {
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
     if (H < 2 || W < 2 || (ndim == 3 && D < 2)) { set_error("flow needs every axis >= 2"); return TRB_ERR_ARG; }
     if (!moving || !target || !flow_in || !moments) { set_error("null pointer"); return TRB_ERR_ARG; }
     if (ndim == 3 && (z_off < 0 || Ds < 1 || z_off + Ds > D)) { set_error("bad slab [%d,%d) of %d", z_off, z_off + Ds, D); return TRB_ERR_ARG; }
-    if (ndim == 3 && ((z_off > 0 && !halo_lo) || (z_off + Ds < D && !halo_hi))) { set_error("interior slab needs both halos"); return TRB_ERR_ARG; }
+    if (ndim == 3 && lambda != 0.f && ((z_off > 0 && !halo_lo) || (z_off + Ds < D && !halo_hi))) { set_error("interior slab needs both halos"); return TRB_ERR_ARG; }
     if (!ws || ws_bytes < (size_t)(kDirectMaxBlocks * 6 + 2) * sizeof(double)) { set_error("workspace too small"); return TRB_ERR_WORKSPACE; }
     p.moving = moving; p.target = target; p.flow_in = flow_in; p.halo_lo = halo_lo; p.halo_hi = halo_hi;
     p.D = ndim == 3 ? D : 1; p.H = H; p.W = W; p.z_off = ndim == 3 ? z_off : 0; p.Ds = ndim == 3 ? Ds : 1;
@@ -289,7 +506,7 @@ extern "C" int trb_flow_direct_stats(int ndim, const float *moving_dev, const fl
 {
     DirectParams p{};
     int rc = fill_direct(p, ndim, moving_dev, target_slab_dev, flow_slab_dev, halo_lo_dev, halo_hi_dev, D, H, W, z_off, Ds,
-                         moments6_dev, workspace_dev, workspace_bytes);
+                         moments6_dev, workspace_dev, workspace_bytes, smooth_lambda);
     if (rc) return rc;
     p.lambda = smooth_lambda;
     const size_t n = (size_t)p.Ds * H * W;
@@ -328,4 +545,85 @@ extern "C" int trb_flow_direct_update(int ndim, const float *moving_dev, const f
     if (ndim == 3) flow_direct_update_kernel<3><<<direct_grid(n), 256, 0, s>>>(p);
     else flow_direct_update_kernel<2><<<direct_grid(n), 256, 0, s>>>(p);
     return check_cuda(cudaGetLastError(), "flow_direct_update");
+}
+
+namespace trb {
+template <bool NEXT, bool ADAM>
+static void launch_step(const DirectParams &p, bool smooth, unsigned grid, int tiles_x, int tiles_y, int zc, cudaStream_t s)
+{
+    if (smooth) flow_direct_step_kernel<NEXT, ADAM, true><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y, zc);
+    else flow_direct_step_kernel<NEXT, ADAM, false><<<grid, 256, 0, s>>>(p, tiles_x, tiles_y, zc);
+}
+template <bool NEXT, bool ADAM>
+static int step_occupancy()
+{
+    int a = 0, b = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&a, flow_direct_step_kernel<NEXT, ADAM, true>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, flow_direct_step_kernel<NEXT, ADAM, false>, 256, 0);
+    const int o = a < b ? a : b;
+    return o < 1 ? 1 : o;
+}
+}  // namespace trb
+
+extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
+                                    const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                                    const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                                    double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                                    int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                                    float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
+                                    void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    DirectParams p{};
+    int rc = fill_direct(p, 3, moving_dev, target_slab_dev, flow_in_slab_dev, halo_lo_dev, halo_hi_dev, D, H, W, z_off, Ds,
+                         moments6_dev, workspace_dev, workspace_bytes, smooth_lambda);
+    if (rc) return rc;
+    if (!flow_out_slab_dev || flow_in_slab_dev == flow_out_slab_dev) { set_error("step is out of place: flow_out must differ from flow_in"); return TRB_ERR_ARG; }
+    if (optimiser != TRB_OPT_SGD && optimiser != TRB_OPT_ADAM) { set_error("bad optimiser"); return TRB_ERR_ARG; }
+    if (optimiser == TRB_OPT_ADAM && (!adam_m_dev || !adam_v_dev || step_index < 1)) { set_error("Adam needs m, v and step_index >= 1"); return TRB_ERR_ARG; }
+    if (3ull * (unsigned long long)Ds * H * W >= (1ull << 31) || (unsigned long long)D * H * W >= (1ull << 31)) {
+        set_error("fused step needs 3*Ds*H*W < 2^31 (use stats + update)");
+        return TRB_ERR_ARG;
+    }
+    if (epoch < 0) { set_error("bad epoch"); return TRB_ERR_ARG; }
+    p.flow_out = flow_out_slab_dev;
+    p.w_mse = w_mse; p.w_ncc = w_ncc; p.lambda = smooth_lambda; p.lr = lr;
+    p.optimiser = optimiser; p.beta1 = beta1; p.beta2 = beta2; p.eps = adam_eps; p.step = step_index;
+    p.adam_m = adam_m_dev; p.adam_v = adam_v_dev; p.loss_log = loss_log_dev; p.epoch = epoch;
+    p.complete_prev = complete_prev;
+    const bool next = w_ncc != 0.f, adam = optimiser == TRB_OPT_ADAM, smooth = smooth_lambda != 0.f;
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    static int occ[2][2] = {{0, 0}, {0, 0}};
+    int &oc = occ[next][adam];
+    if (!oc) oc = next ? (adam ? step_occupancy<true, true>() : step_occupancy<true, false>())
+                       : (adam ? step_occupancy<false, true>() : step_occupancy<false, false>());
+    const int tiles_x = (W + kTX - 1) / kTX, tiles_y = (H + kTY - 1) / kTY;
+    int cap = sms * oc;
+    if (cap > kDirectMaxBlocks) cap = kDirectMaxBlocks;
+    // z-chunk length: long chunks amortise the chunk prologue, short ones balance the grid (>= ~6 items per CTA)
+    int zc = 32;
+    while (zc > 4 && (long long)tiles_x * tiles_y * ((p.Ds + zc - 1) / zc) < 6ll * cap) zc >>= 1;
+    const long long items = (long long)tiles_x * tiles_y * ((p.Ds + zc - 1) / zc);
+    const unsigned grid = (unsigned)(items < cap ? items : cap);
+    cudaStream_t s = (cudaStream_t)stream;
+    if (next) { if (adam) launch_step<true, true>(p, smooth, grid, tiles_x, tiles_y, zc, s); else launch_step<true, false>(p, smooth, grid, tiles_x, tiles_y, zc, s); }
+    else { if (adam) launch_step<false, true>(p, smooth, grid, tiles_x, tiles_y, zc, s); else launch_step<false, false>(p, smooth, grid, tiles_x, tiles_y, zc, s); }
+    return check_cuda(cudaGetLastError(), "flow_direct_step");
+}
+
+extern "C" int trb_flow_direct_finish(const double *moments6_dev, int D, int H, int W, float w_mse, float w_ncc,
+                                      float smooth_lambda, float *loss_log_dev, int epochs_done,
+                                      void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    if (!moments6_dev || !workspace_dev || workspace_bytes < 2 * sizeof(double)) { set_error("null pointer / workspace"); return TRB_ERR_ARG; }
+    if (epochs_done < 1 || !loss_log_dev) return TRB_OK;
+    DirectParams p{};
+    p.D = D; p.H = H; p.W = W;
+    p.moments = const_cast<double *>(moments6_dev);
+    p.ticket = (unsigned *)workspace_dev;
+    p.w_mse = w_mse; p.w_ncc = w_ncc; p.lambda = smooth_lambda; p.loss_log = loss_log_dev; p.epoch = epochs_done;
+    p.complete_prev = 1;
+    flow_direct_finish_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(p, w_ncc != 0.f ? 1 : 0);
+    return check_cuda(cudaGetLastError(), "flow_direct_finish");
 }

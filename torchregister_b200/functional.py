@@ -345,6 +345,8 @@ class DirectFlowProblem:
         self.workspace = torch.zeros(int(self.lib.trb_flow_direct_workspace_bytes()), dtype=torch.uint8, device=self.device)
         self.max_epochs = int(max_epochs)
         self.epoch = 0
+        self._pending = False          # a fused step whose loss entry is not complete yet (see `finish`)
+        self._sums_epoch = -1          # epoch whose (all-reduced) similarity sums `moments` holds
 
     def boundary_slices(self):
         """(first, last) z-slices of the current flow, [ndim, H, W] each — what the neighbours need as halos."""
@@ -371,8 +373,60 @@ class DirectFlowProblem:
         self.flow, self._other = self._other, self.flow
         self.epoch += 1
 
+    @property
+    def fused(self):
+        """3-D volumes below 2^31/3 voxels take the one-pass-per-epoch kernel (trb_flow_direct_step)."""
+        return self.ndim == 3 and 3 * self.Ds * self.H * self.W < 2 ** 31 and self.D * self.H * self.W < 2 ** 31
+
+    def step(self, lr, w_mse, w_ncc, smooth, halo_lo=None, halo_hi=None, betas=(0.9, 0.999), eps=1e-8):
+        """One fused epoch.  `self.moments` must hold the (all-reduced) similarity sums of the current flow when
+        w_ncc != 0 (see `prime`); on return it holds this slab's sums for the next call."""
+        if self.epoch >= self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_flow_direct_step(
+                self.moving.data_ptr(), self.target.data_ptr(), self.flow.data_ptr(), self._other.data_ptr(),
+                _ptr(halo_lo), _ptr(halo_hi), self.D, self.H, self.W, self.z_off, self.Ds, self.moments.data_ptr(),
+                float(w_mse), float(w_ncc), float(smooth), float(lr), OPT[self.optimiser], float(betas[0]), float(betas[1]),
+                float(eps), self.epoch + 1, _ptr(self.adam_m), _ptr(self.adam_v), self.loss_log.data_ptr(), self.epoch,
+                int(self._pending), self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "flow_direct_step")
+        self.flow, self._other = self._other, self.flow
+        self.epoch += 1
+        self._pending = True
+
+    def prime(self, w_ncc):
+        """Similarity sums of the current flow (this slab) into `self.moments` — what the first fused epoch of an
+        NCC-weighted run reads.  Returns True if the caller has to all-reduce them."""
+        self._pending = False
+        if w_ncc == 0 or self._sums_epoch == self.epoch:
+            return False
+        self.stats(0.0)
+        return True
+
+    def finish(self, w_mse, w_ncc, smooth):
+        """Complete the loss log of the last fused epoch from the (all-reduced) moments."""
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_flow_direct_finish(
+                self.moments.data_ptr(), self.D, self.H, self.W, float(w_mse), float(w_ncc), float(smooth),
+                self.loss_log.data_ptr(), self.epoch, self.workspace.data_ptr(), self.workspace.numel(),
+                _stream(self.device)), "flow_direct_finish")
+        self._pending = False
+        self._sums_epoch = self.epoch if w_ncc != 0 else -1      # moments[0..4] describe the current flow
+
     def run(self, n_epochs, lr, w_mse, w_ncc, smooth=0.0, betas=(0.9, 0.999), eps=1e-8):
         """Single-GPU epochs (whole volume in this problem): no host synchronisation."""
+        if self.fused and n_epochs > 0:
+            self.prime(w_ncc)
+            for _ in range(n_epochs):
+                self.step(lr, w_mse, w_ncc, smooth, betas=betas, eps=eps)
+            self.finish(w_mse, w_ncc, smooth)
+            return
+        for _ in range(n_epochs):
+            self.stats(smooth)
+            self.update(lr, w_mse, w_ncc, smooth, betas=betas, eps=eps)
+
+    def run_two_pass(self, n_epochs, lr, w_mse, w_ncc, smooth=0.0, betas=(0.9, 0.999), eps=1e-8):
+        """The stats + update form of `run` (2-D, very large slabs, and the cross-check of the fused kernel)."""
         for _ in range(n_epochs):
             self.stats(smooth)
             self.update(lr, w_mse, w_ncc, smooth, betas=betas, eps=eps)

@@ -105,6 +105,17 @@ class ShardedDirectFlow:
             req.wait()
 
     def run(self, n_epochs, lr, w_mse, w_ncc, smooth=0.0, betas=(0.9, 0.999), eps=1e-8):
+        if self.prob.fused and n_epochs > 0:
+            # one kernel + one 6-value all-reduce (+ one halo slice each way) per epoch
+            if self.prob.prime(w_ncc):
+                allreduce_moments(self.prob.moments, self.group)
+            for _ in range(n_epochs):
+                if smooth:
+                    self._exchange()
+                self.prob.step(lr, w_mse, w_ncc, smooth, self.halo_lo, self.halo_hi, betas, eps)
+                allreduce_moments(self.prob.moments, self.group)
+            self.prob.finish(w_mse, w_ncc, smooth)
+            return
         for _ in range(n_epochs):
             if smooth:
                 self._exchange()
