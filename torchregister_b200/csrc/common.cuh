@@ -59,6 +59,142 @@ __device__ __forceinline__ void for_each_voxel(int D, int H, int W, F f)
     }
 }
 
+// ---- flow sample positions and zero-padded (tri|bi)linear sampling (flow.cu, flow_direct.cu) ----------------
+// The reference normalises voxel position + flow to [-1,1] (utils.py:354-356) and grid_sample(align_corners=True)
+// un-normalises again; the fp32 round trip is kept op for op.  Its IEEE division by the loop-invariant S-1 is done
+// with the hoisted correctly rounded reciprocal: q0 = RN(a*r), q = RN(q0 + (a - d*q0)*r) is the correctly rounded
+// quotient (Markstein), 3 instructions instead of the ~14 of the generic division sequence.
+struct AxisMap {
+    float d, r;      // S-1 and RN(1/(S-1))
+};
+__device__ __forceinline__ AxisMap axis_map(int S)
+{
+    AxisMap a;
+    a.d = (float)(S - 1);
+    a.r = __frcp_rn(a.d);
+    return a;
+}
+__device__ __forceinline__ float flow_pos(const AxisMap &m, int i, float f)
+{
+    const float loc = (float)i + f;
+    const float q0 = __fmul_rn(loc, m.r);
+    const float q = __fmaf_rn(__fmaf_rn(-m.d, q0, loc), m.r, q0);
+    const float nrm = 2.f * (q - 0.5f);
+    return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.f), 0.5f), m.d);
+}
+
+// floor and fraction without the quarter-rate conversion pipe: adding 1.5*2^23 rounding down leaves floor(p) in the
+// low mantissa bits (exact for |p| < 2^22; anything further out — inf and NaN included — lands on an index no volume
+// reaches, i.e. on the zero padding).
+__device__ __forceinline__ void floor_frac(float p, int &i0, float &t)
+{
+    const float m = __fadd_rd(p, 12582912.f);
+    i0 = __float_as_int(m) - 0x4B400000;
+    t = p - (m - 12582912.f);
+}
+
+// cells that straddle the volume boundary (rare: kept out of line so the common path stays small)
+static __device__ __noinline__ void gather_border3(const float *__restrict__ m, int D, int H, int W, int x0, int y0, int z0,
+                                            float (&c)[8])
+{
+    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+    const long long HW = (long long)H * W;
+    const float *q = m + (((long long)z0 * H + y0) * W + x0);
+    c[0] = (vz0 & vy0 & vx0) ? __ldg(q) : 0.f;
+    c[1] = (vz0 & vy0 & vx1) ? __ldg(q + 1) : 0.f;
+    c[2] = (vz0 & vy1 & vx0) ? __ldg(q + W) : 0.f;
+    c[3] = (vz0 & vy1 & vx1) ? __ldg(q + W + 1) : 0.f;
+    c[4] = (vz1 & vy0 & vx0) ? __ldg(q + HW) : 0.f;
+    c[5] = (vz1 & vy0 & vx1) ? __ldg(q + HW + 1) : 0.f;
+    c[6] = (vz1 & vy1 & vx0) ? __ldg(q + HW + W) : 0.f;
+    c[7] = (vz1 & vy1 & vx1) ? __ldg(q + HW + W + 1) : 0.f;
+}
+
+template <int NDIM>
+struct Sample {
+    float val;
+    float g[NDIM];      // d val / d (x, y[, z]) in voxel units
+};
+
+// The 8 corners of the cell around (px,py,pz) + the fractions: the loads can be issued early and blended later.
+struct Cell3 {
+    float c[8];
+    float tx, ty, tz;
+};
+__device__ __forceinline__ Cell3 gather_cell3(const float *__restrict__ m, int D, int H, int W, float px, float py, float pz)
+{
+    Cell3 k;
+    int x0, y0, z0;
+    floor_frac(px, x0, k.tx);
+    floor_frac(py, y0, k.ty);
+    floor_frac(pz, z0, k.tz);
+    if ((unsigned)x0 < (unsigned)(W - 1) && (unsigned)y0 < (unsigned)(H - 1) && (unsigned)z0 < (unsigned)(D - 1)) {
+        const float *q = m + ((z0 * H + y0) * W + x0);          // the whole cell is inside: no predicates
+        k.c[0] = __ldg(q); k.c[1] = __ldg(q + 1); k.c[2] = __ldg(q + W); k.c[3] = __ldg(q + W + 1);
+        q += H * W;
+        k.c[4] = __ldg(q); k.c[5] = __ldg(q + 1); k.c[6] = __ldg(q + W); k.c[7] = __ldg(q + W + 1);
+    } else {
+        float b[8];                                             // only this rare path touches local memory
+        gather_border3(m, D, H, W, x0, y0, z0, b);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) k.c[i] = b[i];
+    }
+    return k;
+}
+template <bool WANT_GRAD>
+__device__ __forceinline__ Sample<3> blend_cell3(const Cell3 &k)
+{
+    Sample<3> s;
+    const float d00 = k.c[1] - k.c[0], d01 = k.c[3] - k.c[2], d10 = k.c[5] - k.c[4], d11 = k.c[7] - k.c[6];
+    const float v00 = fmaf(k.tx, d00, k.c[0]), v01 = fmaf(k.tx, d01, k.c[2]);
+    const float v10 = fmaf(k.tx, d10, k.c[4]), v11 = fmaf(k.tx, d11, k.c[6]);
+    const float e0 = v01 - v00, e1 = v11 - v10;
+    const float w0 = fmaf(k.ty, e0, v00), w1 = fmaf(k.ty, e1, v10);
+    const float gz = w1 - w0;
+    s.val = fmaf(k.tz, gz, w0);
+    if (WANT_GRAD) {
+        s.g[2] = gz;
+        s.g[1] = fmaf(k.tz, e1 - e0, e0);
+        const float dx0 = fmaf(k.ty, d01 - d00, d00), dx1 = fmaf(k.ty, d11 - d10, d10);
+        s.g[0] = fmaf(k.tz, dx1 - dx0, dx0);
+    }
+    return s;
+}
+
+// grid_sample(mode='bilinear', padding_mode='zeros') at voxel coordinates (px,py,pz).  Needs D*H*W < 2^31 (hosts check).
+template <int NDIM, bool WANT_GRAD>
+__device__ __forceinline__ Sample<NDIM> sample_zero_pad(const float *__restrict__ m, int D, int H, int W,
+                                                        float px, float py, float pz)
+{
+    if constexpr (NDIM == 3) {
+        return blend_cell3<WANT_GRAD>(gather_cell3(m, D, H, W, px, py, pz));
+    } else {
+        Sample<NDIM> s;
+        int x0, y0;
+        float tx, ty;
+        floor_frac(px, x0, tx);
+        floor_frac(py, y0, ty);
+        const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+        const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+        const float *q = m + ((long long)y0 * W + x0);
+        const float c00 = (vy0 & vx0) ? __ldg(q) : 0.f;
+        const float c01 = (vy0 & vx1) ? __ldg(q + 1) : 0.f;
+        const float c10 = (vy1 & vx0) ? __ldg(q + W) : 0.f;
+        const float c11 = (vy1 & vx1) ? __ldg(q + W + 1) : 0.f;
+        const float d0 = c01 - c00, d1 = c11 - c10;
+        const float v0 = fmaf(tx, d0, c00), v1 = fmaf(tx, d1, c10);
+        const float gy = v1 - v0;
+        s.val = fmaf(ty, gy, v0);
+        if (WANT_GRAD) {
+            s.g[1] = gy;
+            s.g[0] = fmaf(ty, d1 - d0, d0);
+        }
+        return s;
+    }
+}
+
 // ---- similarity coefficients from the five global moments -------------------
 // dL/dw_v = cw*w_v + ct*t_v + c0   (reference utils.py:197-205,
 // nn.MSELoss at warpings.py:37,124; weighted sum warpings.py:78-79,144-145)

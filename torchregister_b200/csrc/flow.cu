@@ -14,101 +14,40 @@
 
 namespace trb {
 
-// sample position for one axis: the reference normalises to [-1,1] (utils.py:354-356) and
-// grid_sample(align_corners=True) un-normalises again; the fp32 round trip is kept op for op.
-__device__ __forceinline__ float flow_pos(int S, int i, float f)
-{
-    const float loc = (float)i + f;
-    const float nrm = 2.f * (__fdiv_rn(loc, (float)(S - 1)) - 0.5f);
-    return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.f), 0.5f), (float)(S - 1));
-}
-
-template <int NDIM>
-struct Sample {
-    float val;
-    float g[NDIM];      // d val / d (x, y[, z]) in voxel units
-};
-
-template <int NDIM, bool WANT_GRAD>
-__device__ __forceinline__ Sample<NDIM> sample_zero_pad(const float *__restrict__ m, int D, int H, int W,
-                                                        float px, float py, float pz)
-{
-    Sample<NDIM> s;
-    const float fx = floorf(px), fy = floorf(py);
-    const float tx = px - fx, ty = py - fy;
-    const int x0 = (int)fx, y0 = (int)fy;
-    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
-    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
-    if (NDIM == 3) {
-        const float fz = floorf(pz);
-        const float tz = pz - fz;
-        const int z0 = (int)fz;
-        const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
-        const long long HW = (long long)H * W;
-        const long long o = ((long long)z0 * H + y0) * W + x0;
-        const float c000 = (vz0 & vy0 & vx0) ? __ldg(m + o) : 0.f;
-        const float c001 = (vz0 & vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
-        const float c010 = (vz0 & vy1 & vx0) ? __ldg(m + o + W) : 0.f;
-        const float c011 = (vz0 & vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
-        const float c100 = (vz1 & vy0 & vx0) ? __ldg(m + o + HW) : 0.f;
-        const float c101 = (vz1 & vy0 & vx1) ? __ldg(m + o + HW + 1) : 0.f;
-        const float c110 = (vz1 & vy1 & vx0) ? __ldg(m + o + HW + W) : 0.f;
-        const float c111 = (vz1 & vy1 & vx1) ? __ldg(m + o + HW + W + 1) : 0.f;
-        const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
-        const float v00 = fmaf(tx, d00, c000), v01 = fmaf(tx, d01, c010);
-        const float v10 = fmaf(tx, d10, c100), v11 = fmaf(tx, d11, c110);
-        const float e0 = v01 - v00, e1 = v11 - v10;
-        const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
-        const float gz = w1 - w0;
-        s.val = fmaf(tz, gz, w0);
-        if (WANT_GRAD) {
-            s.g[NDIM - 1] = gz;
-            s.g[1] = fmaf(tz, e1 - e0, e0);
-            const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
-            s.g[0] = fmaf(tz, dx1 - dx0, dx0);
-        }
-    } else {
-        const long long o = (long long)y0 * W + x0;
-        const float c00 = (vy0 & vx0) ? __ldg(m + o) : 0.f;
-        const float c01 = (vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
-        const float c10 = (vy1 & vx0) ? __ldg(m + o + W) : 0.f;
-        const float c11 = (vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
-        const float d0 = c01 - c00, d1 = c11 - c10;
-        const float v0 = fmaf(tx, d0, c00), v1 = fmaf(tx, d1, c10);
-        const float gy = v1 - v0;
-        s.val = fmaf(ty, gy, v0);
-        if (WANT_GRAD) {
-            s.g[1] = gy;
-            s.g[0] = fmaf(ty, d1 - d0, d0);
-        }
-    }
-    return s;
-}
-
 // voxel (x,y,z) -> the sample position displaced by the flow
+struct FlowAxes {
+    AxisMap x, y, z;
+};
+__device__ __forceinline__ FlowAxes flow_axes(int D, int H, int W)
+{
+    FlowAxes a;
+    a.x = axis_map(W); a.y = axis_map(H); a.z = axis_map(D > 1 ? D : 2);
+    return a;
+}
 template <int NDIM>
 __device__ __forceinline__ void flow_position(const float *__restrict__ flow, size_t vol, size_t idx, int x, int y, int z,
-                                              int D, int H, int W, float &px, float &py, float &pz)
+                                              const FlowAxes &ax, float &px, float &py, float &pz)
 {
     if (NDIM == 3) {
-        pz = flow_pos(D, z, ld_stream_f(flow + idx));
-        py = flow_pos(H, y, ld_stream_f(flow + vol + idx));
-        px = flow_pos(W, x, ld_stream_f(flow + 2 * vol + idx));
+        pz = flow_pos(ax.z, z, ld_stream_f(flow + idx));
+        py = flow_pos(ax.y, y, ld_stream_f(flow + vol + idx));
+        px = flow_pos(ax.x, x, ld_stream_f(flow + 2 * vol + idx));
     } else {
         pz = 0.f;
-        py = flow_pos(H, y, ld_stream_f(flow + idx));
-        px = flow_pos(W, x, ld_stream_f(flow + vol + idx));
+        py = flow_pos(ax.y, y, ld_stream_f(flow + idx));
+        px = flow_pos(ax.x, x, ld_stream_f(flow + vol + idx));
     }
 }
 
 template <int NDIM>
-__global__ void __launch_bounds__(256) warp_flow_kernel(const float *__restrict__ src, const float *__restrict__ flow,
+__global__ void __launch_bounds__(256, 4) warp_flow_kernel(const float *__restrict__ src, const float *__restrict__ flow,
                                                          float *__restrict__ out, int n_channels, int D, int H, int W)
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
+    const FlowAxes ax = flow_axes(D, H, W);
     for_each_voxel<2>(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
         for (int c = 0; c < n_channels; ++c)
             out[(size_t)c * vol + idx] = sample_zero_pad<NDIM, false>(src + (size_t)c * vol, D, H, W, px, py, pz).val;
     });
@@ -128,9 +67,10 @@ __global__ void __launch_bounds__(256) warp_flow_vjp_kernel(const float *__restr
                                                              int D, int H, int W)
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
+    const FlowAxes ax = flow_axes(D, H, W);
     for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
         const Sample<NDIM> s = sample_zero_pad<NDIM, true>(src, D, H, W, px, py, pz);
         store_dflow<NDIM>(dflow, vol, idx, ld_stream_f(gout + idx), s.g);
     });
@@ -146,13 +86,14 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
                                                           double *ws, float *loss_out)
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
+    const FlowAxes ax = flow_axes(D, H, W);
     // a thread sums ~50-60 voxels (grid = 8 CTAs per SM): fp32 partials are exact enough (values in [0,1],
     // relative error < 4e-6 worst case) and keep the register count low enough for full occupancy; everything
     // above the thread level is fp64
     float s[5] = {0.f, 0.f, 0.f, 0.f, 0.f};
     for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
         const float w = sample_zero_pad<NDIM, false>(moving, D, H, W, px, py, pz).val;
         const float t = ld_stream_f(target + idx);
         if (warped) warped[idx] = w;
@@ -207,10 +148,11 @@ __global__ void __launch_bounds__(256) flow_grad_kernel(const float *__restrict_
                                                          int D, int H, int W, const double *__restrict__ ws)
 {
     const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
+    const FlowAxes ax = flow_axes(D, H, W);
     const float cw = (float)ws[0], ct = (float)ws[1], c0 = (float)ws[2];
     for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
-        flow_position<NDIM>(flow, vol, idx, x, y, z, D, H, W, px, py, pz);
+        flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
         const Sample<NDIM> s = sample_zero_pad<NDIM, true>(moving, D, H, W, px, py, pz);
         const float t = ld_stream_f(target + idx);
         const float r = fmaf(cw, s.val, fmaf(ct, t, c0));
@@ -234,6 +176,7 @@ static int validate_flow(int ndim, int D, int H, int W)
 {
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3 (got %d)", ndim); return TRB_ERR_ARG; }
     if (H < 2 || W < 2 || (ndim == 3 && D < 2)) { set_error("flow warp needs every axis >= 2 (got %dx%dx%d)", D, H, W); return TRB_ERR_ARG; }
+    if ((unsigned long long)(ndim == 3 ? D : 1) * H * W >= (1ull << 31)) { set_error("flow kernels index volumes with 32 bits: D*H*W must stay below 2^31"); return TRB_ERR_ARG; }
     return TRB_OK;
 }
 

@@ -15,6 +15,7 @@
 // volume; `moving` is the full [D][H][W] volume; halo_lo / halo_hi are the neighbour ranks' flow slices
 // z_off-1 and z_off+Ds ([ndim][H][W]) or NULL at the volume boundary.
 #include "common.cuh"
+#include <math.h>
 
 namespace trb {
 
@@ -43,55 +44,11 @@ struct DirectParams {
     int optimiser, step, epoch;
     float beta1, beta2, eps;
     int complete_prev;      // fused step: moments[5] / the stash belong to the previous call, finish its loss entry
+    // fused step: launch-invariant values computed on the host so they are constant-bank operands, not registers
+    AxisMap ax, ay, az;
+    float wsm[3], ssm[3];   // smoothness weights per axis (x, y, z) and 2*lambda*weight
+    float step_size, inv_bc2s, ob1, ob2;
 };
-
-__device__ __forceinline__ float dflow_pos(int S, int i, float f)
-{
-    const float loc = (float)i + f;
-    const float nrm = 2.f * (__fdiv_rn(loc, (float)(S - 1)) - 0.5f);
-    return __fmul_rn(__fmul_rn(__fadd_rn(nrm, 1.f), 0.5f), (float)(S - 1));
-}
-
-template <int NDIM>
-__device__ __forceinline__ void sample3(const float *__restrict__ m, int D, int H, int W, float px, float py, float pz,
-                                        float &val, float (&g)[3])
-{
-    const float fx = floorf(px), fy = floorf(py);
-    const float tx = px - fx, ty = py - fy;
-    const int x0 = (int)fx, y0 = (int)fy;
-    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
-    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
-    if (NDIM == 3) {
-        const float fz = floorf(pz);
-        const float tz = pz - fz;
-        const int z0 = (int)fz;
-        const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
-        const long long HW = (long long)H * W, o = ((long long)z0 * H + y0) * W + x0;
-        const float c000 = (vz0 & vy0 & vx0) ? __ldg(m + o) : 0.f, c001 = (vz0 & vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
-        const float c010 = (vz0 & vy1 & vx0) ? __ldg(m + o + W) : 0.f, c011 = (vz0 & vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
-        const float c100 = (vz1 & vy0 & vx0) ? __ldg(m + o + HW) : 0.f, c101 = (vz1 & vy0 & vx1) ? __ldg(m + o + HW + 1) : 0.f;
-        const float c110 = (vz1 & vy1 & vx0) ? __ldg(m + o + HW + W) : 0.f, c111 = (vz1 & vy1 & vx1) ? __ldg(m + o + HW + W + 1) : 0.f;
-        const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
-        const float v00 = fmaf(tx, d00, c000), v01 = fmaf(tx, d01, c010), v10 = fmaf(tx, d10, c100), v11 = fmaf(tx, d11, c110);
-        const float e0 = v01 - v00, e1 = v11 - v10;
-        const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
-        g[2] = w1 - w0;
-        val = fmaf(tz, g[2], w0);
-        g[1] = fmaf(tz, e1 - e0, e0);
-        const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
-        g[0] = fmaf(tz, dx1 - dx0, dx0);
-    } else {
-        const long long o = (long long)y0 * W + x0;
-        const float c00 = (vy0 & vx0) ? __ldg(m + o) : 0.f, c01 = (vy0 & vx1) ? __ldg(m + o + 1) : 0.f;
-        const float c10 = (vy1 & vx0) ? __ldg(m + o + W) : 0.f, c11 = (vy1 & vx1) ? __ldg(m + o + W + 1) : 0.f;
-        const float d0 = c01 - c00, d1 = c11 - c10;
-        const float v0 = fmaf(tx, d0, c00), v1 = fmaf(tx, d1, c10);
-        g[1] = v1 - v0;
-        val = fmaf(ty, g[1], v0);
-        g[0] = fmaf(ty, d1 - d0, d0);
-        g[2] = 0.f;
-    }
-}
 
 // flow value of channel c at slab-local (zl, y, x) with zl in [-1, Ds] resolved through the halos
 template <int NDIM>
@@ -121,6 +78,7 @@ __global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectPara
 {
     const int W = p.W, H = p.H, D = NDIM == 3 ? p.D : 1, Ds = NDIM == 3 ? p.Ds : 1;
     const size_t HW = (size_t)H * W, slab = HW * Ds;
+    const AxisMap ax = axis_map(W), ay = axis_map(H), az = axis_map(D > 1 ? D : 2);
     const float wx = smooth_weight<NDIM>(p, 0), wy = smooth_weight<NDIM>(p, 1), wz = NDIM == 3 ? smooth_weight<NDIM>(p, 2) : 0.f;
     float s[6] = {0, 0, 0, 0, 0, 0};          // fp32 per thread (~50 voxels), fp64 above (see flow.cu)
     for_each_slab_voxel(Ds, H, W, [&](size_t idx, int x, int y, int zl) {
@@ -129,10 +87,11 @@ __global__ void __launch_bounds__(256) flow_direct_stats_kernel(const DirectPara
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) f[c] = ld_stream_f(p.flow_in + (size_t)c * slab + idx);
         float px, py, pz = 0.f;
-        if (NDIM == 3) { pz = dflow_pos(D, z, f[0]); py = dflow_pos(H, y, f[1]); px = dflow_pos(W, x, f[2]); }
-        else { py = dflow_pos(H, y, f[0]); px = dflow_pos(W, x, f[1]); }
-        float val, g[3];
-        sample3<NDIM>(p.moving, D, H, W, px, py, pz, val, g);
+        if (NDIM == 3) { pz = flow_pos(az, z, f[0]); py = flow_pos(ay, y, f[1]); px = flow_pos(ax, x, f[2]); }
+        else { py = flow_pos(ay, y, f[0]); px = flow_pos(ax, x, f[1]); }
+        const Sample<NDIM> sp = sample_zero_pad<NDIM, true>(p.moving, D, H, W, px, py, pz);
+        const float val = sp.val;
+        const float g[3] = {sp.g[0], sp.g[1], NDIM == 3 ? sp.g[NDIM - 1] : 0.f};
         const float t = ld_stream_f(p.target + idx);
         s[0] += t; s[1] += val;
         s[2] = fmaf(t, t, s[2]); s[3] = fmaf(val, val, s[3]); s[4] = fmaf(t, val, s[4]);
@@ -185,6 +144,7 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
 {
     const int W = p.W, H = p.H, D = NDIM == 3 ? p.D : 1, Ds = NDIM == 3 ? p.Ds : 1;
     const size_t HW = (size_t)H * W, slab = HW * Ds;
+    const AxisMap ax = axis_map(W), ay = axis_map(H), az = axis_map(D > 1 ? D : 2);
     __shared__ float coef[3];
     if (threadIdx.x == 0) {
         const double n = (double)D * H * W;
@@ -208,10 +168,11 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
 #pragma unroll
         for (int c = 0; c < NDIM; ++c) f[c] = ld_stream_f(p.flow_in + (size_t)c * slab + idx);
         float px, py, pz = 0.f;
-        if (NDIM == 3) { pz = dflow_pos(D, z, f[0]); py = dflow_pos(H, y, f[1]); px = dflow_pos(W, x, f[2]); }
-        else { py = dflow_pos(H, y, f[0]); px = dflow_pos(W, x, f[1]); }
-        float val, g[3];
-        sample3<NDIM>(p.moving, D, H, W, px, py, pz, val, g);
+        if (NDIM == 3) { pz = flow_pos(az, z, f[0]); py = flow_pos(ay, y, f[1]); px = flow_pos(ax, x, f[2]); }
+        else { py = flow_pos(ay, y, f[0]); px = flow_pos(ax, x, f[1]); }
+        const Sample<NDIM> sp = sample_zero_pad<NDIM, true>(p.moving, D, H, W, px, py, pz);
+        const float val = sp.val;
+        const float g[3] = {sp.g[0], sp.g[1], NDIM == 3 ? sp.g[NDIM - 1] : 0.f};
         const float t = ld_stream_f(p.target + idx);
         const float r = fmaf(cw, val, fmaf(ct, t, c0));
 #pragma unroll
@@ -293,15 +254,6 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
         if (blockIdx.x == 0) direct_log_losses(p, p.moments, NEXT, true, (double *)p.ticket + 1);
     }
     __syncthreads();
-    const float cw = coef[0], ct = coef[1], c0 = coef[2];
-    const float wx = smooth_weight<3>(p, 0), wy = smooth_weight<3>(p, 1), wz = smooth_weight<3>(p, 2);
-    const float sx = 2.f * p.lambda * wx, sy = 2.f * p.lambda * wy, sz = 2.f * p.lambda * wz;
-    float step_size = p.lr, inv_bc2s = 1.f;           // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
-    if (ADAM) {
-        step_size = p.lr / (1.f - powf(p.beta1, (float)p.step));
-        inv_bc2s = 1.f / sqrtf(1.f - powf(p.beta2, (float)p.step));
-    }
-    const float b1 = p.beta1, b2 = p.beta2, ob1 = 1.f - p.beta1, ob2 = 1.f - p.beta2;
     const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     // halo cell of the shared tile this thread refreshes every slice (240 cells: 3 channels x (2 rows + 2 columns))
     int hc = 0, hx = 0, hy = 0;
@@ -365,6 +317,9 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
                     for (int c = 0; c < 3; ++c) fp[c] = (z + 1 < D) ? __ldg(p.halo_hi + c * HW + xy) : fc[c];
                 }
             }
+            Cell3 cell;
+            if (active)          // the gather goes out before the barrier: its latency overlaps the stencil exchange
+                cell = gather_cell3(p.moving, D, H, W, flow_pos(p.ax, x, fc[2]), flow_pos(p.ay, y, fc[1]), flow_pos(p.az, z, fc[0]));
             if (SMOOTH) {
                 if (active) {
 #pragma unroll
@@ -377,10 +332,10 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
                 __syncthreads();
             }
             if (active) {
-                const float pz = dflow_pos(D, z, fc[0]), py = dflow_pos(H, y, fc[1]), px = dflow_pos(W, x, fc[2]);
-                float val, g[3];
-                sample3<3>(p.moving, D, H, W, px, py, pz, val, g);
-                const float r = fmaf(cw, val, fmaf(ct, t, c0));
+                const Sample<3> sp = blend_cell3<true>(cell);
+                const float val = sp.val;
+                const float *g = sp.g;
+                const float r = fmaf(coef[0], val, fmaf(coef[1], t, coef[2]));
                 float nv[3];
                 float sm = 0.f;
 #pragma unroll
@@ -392,20 +347,21 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
                         const float ym = y > 0 ? tile[b][c][ty][tx + 1] : f, yp = y + 1 < H ? tile[b][c][ty + 2][tx + 1] : f;
                         const float zm = fm[c], zp = fp[c];
                         const float dxp = xp - f, dyp = yp - f, dzp = zp - f;
-                        float st = sx * ((f - xm) - dxp);
-                        st = fmaf(sy, (f - ym) - dyp, st);
-                        st = fmaf(sz, (f - zm) - dzp, st);
+                        float st = p.ssm[0] * ((f - xm) - dxp);
+                        st = fmaf(p.ssm[1], (f - ym) - dyp, st);
+                        st = fmaf(p.ssm[2], (f - zm) - dzp, st);
                         gr += st;
-                        sm = fmaf(wx * dxp, dxp, sm);
-                        sm = fmaf(wy * dyp, dyp, sm);
-                        sm = fmaf(wz * dzp, dzp, sm);
+                        sm = fmaf(p.wsm[0] * dxp, dxp, sm);
+                        sm = fmaf(p.wsm[1] * dyp, dyp, sm);
+                        sm = fmaf(p.wsm[2] * dzp, dzp, sm);
                     }
                     if (!ADAM) {
                         nv[c] = fc[c] - p.lr * gr;
                     } else {
-                        am[c] = fmaf(b1, am[c], ob1 * gr);
-                        av[c] = fmaf(b2, av[c], ob2 * gr * gr);
-                        nv[c] = fmaf(-step_size, __fdividef(am[c], fmaf(sqrtf(av[c]), inv_bc2s, p.eps)), fc[c]);
+                        // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
+                        am[c] = fmaf(p.beta1, am[c], p.ob1 * gr);
+                        av[c] = fmaf(p.beta2, av[c], p.ob2 * gr * gr);
+                        nv[c] = fmaf(-p.step_size, __fdividef(am[c], fmaf(sqrtf(av[c]), p.inv_bc2s, p.eps)), fc[c]);
                     }
                 }
 #pragma unroll
@@ -415,9 +371,8 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
                 }
                 float wv = val;
                 if (NEXT) {
-                    const float qz = dflow_pos(D, z, nv[0]), qy = dflow_pos(H, y, nv[1]), qx = dflow_pos(W, x, nv[2]);
-                    float g2[3];
-                    sample3<3>(p.moving, D, H, W, qx, qy, qz, wv, g2);
+                    const float qz = flow_pos(p.az, z, nv[0]), qy = flow_pos(p.ay, y, nv[1]), qx = flow_pos(p.ax, x, nv[2]);
+                    wv = sample_zero_pad<3, false>(p.moving, D, H, W, qx, qy, qz).val;
                 }
                 s[0] += t; s[1] += wv;
                 s[2] = fmaf(t, t, s[2]); s[3] = fmaf(wv, wv, s[3]); s[4] = fmaf(t, wv, s[4]);
@@ -482,6 +437,7 @@ static int fill_direct(DirectParams &p, int ndim, const float *moving, const flo
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
     if (H < 2 || W < 2 || (ndim == 3 && D < 2)) { set_error("flow needs every axis >= 2"); return TRB_ERR_ARG; }
     if (!moving || !target || !flow_in || !moments) { set_error("null pointer"); return TRB_ERR_ARG; }
+    if ((unsigned long long)(ndim == 3 ? D : 1) * H * W >= (1ull << 31)) { set_error("flow kernels index volumes with 32 bits: D*H*W must stay below 2^31"); return TRB_ERR_ARG; }
     if (ndim == 3 && (z_off < 0 || Ds < 1 || z_off + Ds > D)) { set_error("bad slab [%d,%d) of %d", z_off, z_off + Ds, D); return TRB_ERR_ARG; }
     if (ndim == 3 && lambda != 0.f && ((z_off > 0 && !halo_lo) || (z_off + Ds < D && !halo_hi))) { set_error("interior slab needs both halos"); return TRB_ERR_ARG; }
     if (!ws || ws_bytes < (size_t)(kDirectMaxBlocks * 6 + 2) * sizeof(double)) { set_error("workspace too small"); return TRB_ERR_WORKSPACE; }
@@ -529,6 +485,7 @@ extern "C" int trb_flow_direct_update(int ndim, const float *moving_dev, const f
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
     if (!moving_dev || !target_slab_dev || !flow_in_slab_dev || !flow_out_slab_dev || !moments6_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
     if (flow_in_slab_dev == flow_out_slab_dev) { set_error("update is out of place: flow_out must differ from flow_in"); return TRB_ERR_ARG; }
+    if ((unsigned long long)(ndim == 3 ? D : 1) * H * W >= (1ull << 31)) { set_error("flow kernels index volumes with 32 bits: D*H*W must stay below 2^31"); return TRB_ERR_ARG; }
     if (optimiser != TRB_OPT_SGD && optimiser != TRB_OPT_ADAM) { set_error("bad optimiser"); return TRB_ERR_ARG; }
     if (optimiser == TRB_OPT_ADAM && (!adam_m_dev || !adam_v_dev || step_index < 1)) { set_error("Adam needs m, v and step_index >= 1"); return TRB_ERR_ARG; }
     if (ndim == 3 && (z_off < 0 || Ds < 1 || z_off + Ds > D)) { set_error("bad slab"); return TRB_ERR_ARG; }
@@ -590,6 +547,20 @@ extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target
     p.optimiser = optimiser; p.beta1 = beta1; p.beta2 = beta2; p.eps = adam_eps; p.step = step_index;
     p.adam_m = adam_m_dev; p.adam_v = adam_v_dev; p.loss_log = loss_log_dev; p.epoch = epoch;
     p.complete_prev = complete_prev;
+    p.ax.d = (float)(W - 1); p.ay.d = (float)(H - 1); p.az.d = (float)(D - 1);
+    p.ax.r = 1.f / p.ax.d; p.ay.r = 1.f / p.ay.d; p.az.r = 1.f / p.az.d;       // IEEE: what __frcp_rn gives on the device
+    const double dims[3] = {(double)W, (double)H, (double)D};
+    for (int a = 0; a < 3; ++a) {                                             // smooth_weight<3>, on the host
+        double n = 3.0;
+        for (int k = 0; k < 3; ++k) n *= (k == a) ? dims[k] - 1.0 : dims[k];
+        p.wsm[a] = (float)(1.0 / (n * 3.0));
+        p.ssm[a] = 2.f * smooth_lambda * p.wsm[a];
+    }
+    p.step_size = lr; p.inv_bc2s = 1.f; p.ob1 = 1.f - beta1; p.ob2 = 1.f - beta2;
+    if (optimiser == TRB_OPT_ADAM) {
+        p.step_size = lr / (1.f - powf(beta1, (float)step_index));
+        p.inv_bc2s = 1.f / sqrtf(1.f - powf(beta2, (float)step_index));
+    }
     const bool next = w_ncc != 0.f, adam = optimiser == TRB_OPT_ADAM, smooth = smooth_lambda != 0.f;
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
