@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(256) flow_stats_kernel(const float *__restrict
     for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
         flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
-        const float w = sample_zero_pad<NDIM, false>(moving, D, H, W, px, py, pz).val;
+        const float w = sample_zero_pad<NDIM, false, false>(moving, D, H, W, px, py, pz).val;
         const float t = ld_stream_f(target + idx);
         if (warped) warped[idx] = w;
         s[0] += t; s[1] += w;
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(256) flow_grad_kernel(const float *__restrict_
     for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         float px, py, pz;
         flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
-        const Sample<NDIM> s = sample_zero_pad<NDIM, true>(moving, D, H, W, px, py, pz);
+        const Sample<NDIM> s = sample_zero_pad<NDIM, true, false>(moving, D, H, W, px, py, pz);
         const float t = ld_stream_f(target + idx);
         const float r = fmaf(cw, s.val, fmaf(ct, t, c0));
         store_dflow<NDIM>(dflow, vol, idx, r, s.g);
