@@ -221,6 +221,14 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
 // workspace scalar meanwhile.  Algorithmic traffic: 32 B/voxel (SGD), 80 B/voxel (Adam).
 constexpr int kTX = 32, kTY = 8;
 
+// MUFU.SQRT (2 ulp): the Adam denominator does not need the ~10-instruction IEEE sequence with its slow-path branch
+__device__ __forceinline__ float sqrt_approx(float v)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+    return r;
+}
+
 __device__ __forceinline__ void direct_log_losses(const DirectParams &p, const double *m, bool next, bool new_epoch,
                                                   double *stash)
 {
@@ -361,7 +369,7 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
                         // torch.optim.Adam: p -= lr/bc1 * m / (sqrt(v)/sqrt(bc2) + eps)
                         am[c] = fmaf(p.beta1, am[c], p.ob1 * gr);
                         av[c] = fmaf(p.beta2, av[c], p.ob2 * gr * gr);
-                        nv[c] = fmaf(-p.step_size, __fdividef(am[c], fmaf(sqrtf(av[c]), p.inv_bc2s, p.eps)), fc[c]);
+                        nv[c] = fmaf(-p.step_size, __fdividef(am[c], fmaf(sqrt_approx(av[c]), p.inv_bc2s, p.eps)), fc[c]);
                     }
                 }
 #pragma unroll
