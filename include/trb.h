@@ -221,6 +221,21 @@ int trb_flow_direct_finish(const double *moments6_dev, int D, int H, int W, floa
                            float smooth_lambda, float *loss_log_dev, int epochs_done,
                            void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ---- NMI/KDE term of the reference's default loss -----------------------------------
+ * Replaces utils.py:18-79 (K_gauss, PDF_xis, get_pdf, NMI) + utils.py:224-259 (NMILoss.forward with its default
+ * bins=256, patch_size=100) and autograd's backward down to the warped volume, for ONE pair [1,1,(D,)H,W]:
+ * nearest resample to 200^n, 2^n chunks of 100^n values, 256-bin Gaussian KDE (bandwidth h) of target, warped
+ * and their concatenation over swapped/detached ranges, loss = alpha * mean_k |NMI_k - 1|.
+ * trb_nmi_prepare: once per target (resample + the target's own marginal, cached in the workspace).
+ * trb_nmi_loss_grad: per epoch; *loss_dev = weight*loss (fp64), gout_dev[D][H][W] = weight * d loss / d warped
+ * (NULL: forward only).  Chain gout to theta with trb_warp_affine_vjp or to a flow with trb_warp_flow_vjp. */
+size_t trb_nmi_workspace_bytes(int ndim, int D, int H, int W);
+int trb_nmi_prepare(int ndim, const float *target_dev, int D, int H, int W, float bandwidth,
+                    void *workspace_dev, size_t workspace_bytes, void *stream);
+int trb_nmi_loss_grad(int ndim, const float *warped_dev, int D, int H, int W, float bandwidth, float alpha,
+                      float weight, double *loss_dev, float *gout_dev, void *workspace_dev,
+                      size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

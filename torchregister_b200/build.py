@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_lib")
 LIB_PATH = os.path.join(OUT_DIR, "libtrb_b200.so")
-SOURCES = ["abi.cu", "affine.cu", "affine_tma.cu", "flow.cu", "flow_direct.cu"]
+SOURCES = ["abi.cu", "affine.cu", "affine_tma.cu", "flow.cu", "flow_direct.cu", "nmi.cu"]
 HEADERS = ["common.cuh", "affine_shared.cuh", os.path.join("..", "..", "include", "trb.h")]
 
 NVCC_FLAGS = [

@@ -1,0 +1,378 @@
+// nmi.cu — SURVEY.md §8 f-1: the NMI/KDE term of the reference's DEFAULT loss (weights .33/.33/.33) as CUDA
+// kernels, forward and backward (sm_100a).
+//
+// Replaces, from the reference (paths relative to /root/reference/src/TorchRegister/):
+//   K_gauss / PDF_xis / PDF / get_pdf / NMI            utils.py:18-79
+//   NMILoss.forward (nearest resample to 200^n, 2^n chunks of 100^n, |NMI-1|*alpha)   utils.py:224-259
+//   and autograd's backward of all of it down to the warped volume.
+//
+// Semantics kept (all of them quirks of the reference, see oracle/torch_port.py:nmi_loss):
+//   * both images are nearest-resampled to 200^n and VIEWED as K = 2^n chunks of P = 100^n consecutive values;
+//   * the 256 bin centres are linspace(max, min) (swapped, descending), the range taken over ALL chunks with
+//     .item(), i.e. detached; the "joint" density is a 1-D KDE of the concatenation (target chunk, warped chunk)
+//     over the joint range, not a 2-D histogram;
+//   * kernel exp(-((s-c)/h)^2/2) (its 1/(2 pi), 1/h and 1/P factors cancel in p = pdf/sum(pdf));
+//   * E = sum p*log2(p + 1e-10) (negative entropy), MI = E1+E2-EJ, NMI = 2*MI/(E1+E2), loss = alpha*mean|NMI-1|.
+//
+// Work per epoch (3-D): 8e6 resampled values x 256 bins x (warped: own + joint range, target: joint range) =
+// 6.1e9 Gaussians forward + 4.1e9 backward.  That is MUFU.EX2 work (16 lanes/clk/SM -> 4.65e12/s on 148 SMs):
+// the roofline of this term is the special-function unit, ~2.2 ms per epoch, not HBM (the three resampled
+// arrays are 96 MB).  The target's own marginal is constant over the epochs and computed once (prepare).
+// Histograms are reduced in a fixed order (tile partials -> fp64), min/max by order-independent integer
+// atomics: results are deterministic.
+#include "common.cuh"
+#include <limits.h>
+
+namespace trb {
+
+constexpr int kBins = 256, kRes = 200, kPatch = 100;
+constexpr int kTile = 2000;                  // values per histogram block: divides 100^2 and 100^3, 16-byte rows
+
+struct NmiLayout {
+    int ndim, K, P, N, tiles;
+    size_t off_rs_t, off_rs_w, off_grs, off_part, off_hist, off_gtab, off_range, off_tabs, off_scal, total;
+    int S[3];                                // source extent per axis (x, y, z)
+};
+
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static NmiLayout nmi_layout(int ndim, int D, int H, int W)
+{
+    NmiLayout L{};
+    L.ndim = ndim;
+    L.K = ndim == 3 ? 8 : 4;
+    L.P = ndim == 3 ? kPatch * kPatch * kPatch : kPatch * kPatch;
+    L.N = L.K * L.P;
+    L.tiles = L.P / kTile;
+    L.S[0] = W; L.S[1] = H; L.S[2] = ndim == 3 ? D : 1;
+    size_t o = 0;
+    L.off_rs_t = o; o = align256(o + (size_t)L.N * 4);
+    L.off_rs_w = o; o = align256(o + (size_t)L.N * 4);
+    L.off_grs = o; o = align256(o + (size_t)L.N * 4);
+    L.off_part = o; o = align256(o + (size_t)3 * L.K * L.tiles * kBins * 4);      // streams: (w,W) (w,J) (t,J|T)
+    L.off_hist = o; o = align256(o + (size_t)4 * L.K * kBins * 8);                // fp64: T marginal, W, J(w), J(t)
+    L.off_gtab = o; o = align256(o + (size_t)L.K * kBins * 16);                   // float4 (c2*k, g2, cJ*k, gJ)
+    L.off_range = o; o = align256(o + 4 * sizeof(int));                           // keys: t_min t_max w_min w_max
+    L.off_tabs = o; o = align256(o + (size_t)2 * ((size_t)W + H + (ndim == 3 ? D : 1)) * sizeof(int));
+    L.off_scal = o; o = align256(o + 8 * sizeof(double));
+    L.total = o;
+    return L;
+}
+
+// monotone float <-> int key so min/max can use integer atomics (order independent = deterministic)
+__device__ __forceinline__ int float_key(float f)
+{
+    const int i = __float_as_int(f);
+    return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key_float(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// torch 'nearest' source index (UpSample.h nearest_neighbor_compute_source_index): floor(dst * scale), clamped
+__device__ __forceinline__ int nearest_src(int i, float scale, int S) { return min((int)floorf((float)i * scale), S - 1); }
+
+// bin centre b of torch.linspace(start, end, 256) in fp32 (RangeFactories: symmetric evaluation from both ends)
+__device__ __forceinline__ float bin_centre(float start, float end, int b)
+{
+    const float step = (end - start) / (float)(kBins - 1);
+    return b < kBins / 2 ? start + step * (float)b : end - step * (float)(kBins - 1 - b);
+}
+
+enum { kRangeT = 0, kRangeW = 1, kRangeJ = 2 };
+// (start, end) = (max, min): the reference swaps them (utils.py:45-46)
+__device__ __forceinline__ void bin_range(const int *__restrict__ keys, int which, float &start, float &end)
+{
+    const float tmin = key_float(keys[0]), tmax = key_float(keys[1]), wmin = key_float(keys[2]), wmax = key_float(keys[3]);
+    if (which == kRangeT) { start = tmax; end = tmin; }
+    else if (which == kRangeW) { start = wmax; end = wmin; }
+    else { start = fmaxf(tmax, wmax); end = fminf(tmin, wmin); }
+}
+
+__global__ void nmi_reset_kernel(int *keys2)
+{
+    if (threadIdx.x == 0) { keys2[0] = INT_MAX; keys2[1] = INT_MIN; }
+}
+
+// per axis: the range [lo, hi) of resampled indices that read source index x (empty: lo = hi = 0)
+__global__ void nmi_tables_kernel(int S, float scale, int *__restrict__ lo, int *__restrict__ hi)
+{
+    const int x = blockIdx.x * blockDim.x + threadIdx.x;
+    if (x >= S) return;
+    int l = kRes, h = 0;
+    for (int i = 0; i < kRes; ++i)
+        if (nearest_src(i, scale, S) == x) { l = min(l, i); h = max(h, i + 1); }
+    if (h == 0) l = 0;
+    lo[x] = l; hi[x] = h;
+}
+
+// F.interpolate(mode='nearest', size=200^n) + global min/max of the resampled values (utils.py:238-250, :45-46)
+template <int NDIM>
+__global__ void __launch_bounds__(256) nmi_resample_kernel(const float *__restrict__ src, int D, int H, int W, float sz, float sy,
+                                                            float sx, float *__restrict__ rs, int *__restrict__ keys2)
+{
+    const int N = NDIM == 3 ? kRes * kRes * kRes : kRes * kRes;
+    float mn = INFINITY, mx = -INFINITY;
+    for (int i = blockIdx.x * 256 + threadIdx.x; i < N; i += gridDim.x * 256) {
+        const int ix = i % kRes, r = i / kRes;
+        const int iy = r % kRes, iz = r / kRes;
+        const int x = nearest_src(ix, sx, W), y = nearest_src(iy, sy, H);
+        const int z = NDIM == 3 ? nearest_src(iz, sz, D) : 0;
+        const float v = __ldg(src + ((size_t)z * H + y) * W + x);
+        rs[i] = v;
+        mn = fminf(mn, v); mx = fmaxf(mx, v);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        mn = fminf(mn, __shfl_xor_sync(kFull, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(kFull, mx, o));
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicMin(keys2, float_key(mn));
+        atomicMax(keys2 + 1, float_key(mx));
+    }
+}
+
+// One block = one tile of kTile values of chunk k; thread b owns bin b.  NSETS bin ranges are evaluated on the same
+// staged values (the warped stream needs its own range and the joint one).  part[set][(k*tiles+tile)*256 + b].
+template <int NSETS>
+__global__ void __launch_bounds__(256) nmi_hist_kernel(const float *__restrict__ rs, int P, int tiles, const int *__restrict__ keys,
+                                                        int range0, int range1, float kappa, float *__restrict__ part0,
+                                                        float *__restrict__ part1)
+{
+    __shared__ float4 vals[kTile / 4];
+    const int k = blockIdx.x / tiles, tile = blockIdx.x - k * tiles;
+    const float4 *g = reinterpret_cast<const float4 *>(rs + (size_t)k * P + (size_t)tile * kTile);
+    for (int i = threadIdx.x; i < kTile / 4; i += 256) vals[i] = g[i];
+    float s0, e0, s1 = 0.f, e1 = 0.f;
+    bin_range(keys, range0, s0, e0);
+    if (NSETS == 2) bin_range(keys, range1, s1, e1);
+    const float c0 = bin_centre(s0, e0, threadIdx.x) * kappa;
+    const float c1 = NSETS == 2 ? bin_centre(s1, e1, threadIdx.x) * kappa : 0.f;
+    __syncthreads();
+    float a0[4] = {0.f, 0.f, 0.f, 0.f}, a1[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll 2
+    for (int i = 0; i < kTile / 4; ++i) {
+        const float4 v = vals[i];
+        const float s[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float t0 = fmaf(s[j], kappa, -c0);
+            a0[j] += ex2_approx(-t0 * t0);
+            if (NSETS == 2) {
+                const float t1 = fmaf(s[j], kappa, -c1);
+                a1[j] += ex2_approx(-t1 * t1);
+            }
+        }
+    }
+    const size_t o = (size_t)blockIdx.x * kBins + threadIdx.x;
+    part0[o] = (a0[0] + a0[1]) + (a0[2] + a0[3]);
+    if (NSETS == 2) part1[o] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
+}
+
+// hist[k][b] = sum over tiles, fixed order, fp64.  grid = (K, n_streams)
+__global__ void __launch_bounds__(256) nmi_reduce_kernel(const float *__restrict__ part, int tiles, size_t stream_stride,
+                                                          double *__restrict__ hist, size_t hist_stride)
+{
+    const int k = blockIdx.x;
+    const float *p = part + (size_t)blockIdx.y * stream_stride + (size_t)k * tiles * kBins + threadIdx.x;
+    double acc = 0.0;
+    for (int t = 0; t < tiles; ++t) acc += (double)p[(size_t)t * kBins];
+    hist[(size_t)blockIdx.y * hist_stride + (size_t)k * kBins + threadIdx.x] = acc;
+}
+
+__device__ __forceinline__ double block_sum256(double v, double *sh)
+{
+    v = warp_sum(v);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) sh[threadIdx.x >> 5] = v;
+    __syncthreads();
+    double r = 0.0;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) r += sh[w];
+    return r;
+}
+
+// Entropies, NMI, loss and the table the backward needs.  One block, thread b = bin b, chunks in sequence.
+// hist layout: [0] target marginal (prepare), [1] warped marginal, [2] joint (warped half), [3] joint (target half).
+__global__ void __launch_bounds__(256) nmi_epilogue_kernel(const double *__restrict__ hist, int K, const int *__restrict__ keys,
+                                                            float kappa, float h, double alpha, double weight,
+                                                            float4 *__restrict__ gtab, double *__restrict__ loss_out)
+{
+    __shared__ double sh[8];
+    const int b = threadIdx.x;
+    const size_t hs = (size_t)K * kBins;
+    const double eps = 1e-10, ln2 = 0.6931471805599453;
+    float sW, eW, sJ, eJ;
+    bin_range(keys, kRangeW, sW, eW);
+    bin_range(keys, kRangeJ, sJ, eJ);
+    const float cW = bin_centre(sW, eW, b) * kappa, cJ = bin_centre(sJ, eJ, b) * kappa;
+    double loss = 0.0;
+    for (int k = 0; k < K; ++k) {
+        const double H1 = hist[(size_t)k * kBins + b], H2 = hist[hs + (size_t)k * kBins + b];
+        const double HJ = hist[2 * hs + (size_t)k * kBins + b] + hist[3 * hs + (size_t)k * kBins + b];
+        const double S1 = block_sum256(H1, sh), S2 = block_sum256(H2, sh), SJ = block_sum256(HJ, sh);
+        const double p1 = H1 / S1, p2 = H2 / S2, pj = HJ / SJ;
+        const double l2 = log2(p2 + eps), lj = log2(pj + eps);
+        const double E1 = block_sum256(p1 * log2(p1 + eps), sh);
+        const double E2 = block_sum256(p2 * l2, sh), EJ = block_sum256(pj * lj, sh);
+        const double d2 = l2 + p2 / ((p2 + eps) * ln2), dj = lj + pj / ((pj + eps) * ln2);      // dE/dp_b
+        const double A2 = block_sum256(p2 * d2, sh), AJ = block_sum256(pj * dj, sh);
+        const double den = E1 + E2, mi = den - EJ;
+        const double nmi = 2.0 * mi / den;
+        const double dev = nmi - 1.0;
+        loss += fabs(dev);
+        const double dl = weight * alpha / (double)K * (dev > 0.0 ? 1.0 : (dev < 0.0 ? -1.0 : 0.0));
+        const double dn_e2 = 2.0 / den - 2.0 * mi / (den * den), dn_ej = -2.0 / den;
+        // dL/dH_b = dl * dn * (dE/dp_b - sum_c p_c dE/dp_c) / S ;  dH_b/ds = exp(-u^2/2) * (-u/h), u = t/(kappa*h)
+        const double to_s = -1.0 / ((double)kappa * (double)h * (double)h);
+        const double g2 = dl * dn_e2 * (d2 - A2) / S2 * to_s;
+        const double gj = dl * dn_ej * (dj - AJ) / SJ * to_s;
+        gtab[(size_t)k * kBins + b] = make_float4(cW, (float)g2, cJ, (float)gj);
+    }
+    if (b == 0) *loss_out = weight * alpha * loss / (double)K;
+}
+
+// d loss / d (resampled warped value): 2 x 256 Gaussians per value.  grid = (ceil(P/256), K)
+__global__ void __launch_bounds__(256) nmi_grad_kernel(const float *__restrict__ rs_w, int P, const float4 *__restrict__ gtab,
+                                                        float kappa, float *__restrict__ grs)
+{
+    __shared__ float4 tab[kBins];
+    const int k = blockIdx.y;
+    tab[threadIdx.x] = gtab[(size_t)k * kBins + threadIdx.x];
+    __syncthreads();
+    const int i = blockIdx.x * 256 + threadIdx.x;
+    if (i >= P) return;
+    const float s = rs_w[(size_t)k * P + i];
+    float acc0 = 0.f, acc1 = 0.f;
+#pragma unroll 4
+    for (int b = 0; b < kBins; ++b) {
+        const float4 q = tab[b];
+        const float t0 = fmaf(s, kappa, -q.x), t1 = fmaf(s, kappa, -q.z);
+        acc0 = fmaf(q.y * t0, ex2_approx(-t0 * t0), acc0);
+        acc1 = fmaf(q.w * t1, ex2_approx(-t1 * t1), acc1);
+    }
+    grs[(size_t)k * P + i] = acc0 + acc1;
+}
+
+// backward of the nearest resample: every source voxel sums the resampled positions that read it (fixed order)
+template <int NDIM>
+__global__ void __launch_bounds__(256) nmi_scatter_kernel(const float *__restrict__ grs, int D, int H, int W,
+                                                           const int *__restrict__ tabs, float *__restrict__ gout)
+{
+    const int *xlo = tabs, *xhi = tabs + W, *ylo = tabs + 2 * W, *yhi = tabs + 2 * W + H;
+    const int *zlo = tabs + 2 * W + 2 * H, *zhi = zlo + (NDIM == 3 ? D : 1);
+    for_each_voxel<1>(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
+        const int x0 = xlo[x], x1 = xhi[x], y0 = ylo[y], y1 = yhi[y];
+        const int z0 = NDIM == 3 ? zlo[z] : 0, z1 = NDIM == 3 ? zhi[z] : 1;
+        float acc = 0.f;
+        for (int iz = z0; iz < z1; ++iz)
+            for (int iy = y0; iy < y1; ++iy)
+                for (int ix = x0; ix < x1; ++ix) acc += grs[((size_t)iz * kRes + iy) * kRes + ix];
+        gout[idx] = acc;
+    });
+}
+
+static int nmi_validate(int ndim, int D, int H, int W, const void *ws, size_t ws_bytes)
+{
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3 (got %d)", ndim); return TRB_ERR_ARG; }
+    if (H < 1 || W < 1 || (ndim == 3 && D < 1)) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
+    if ((unsigned long long)(ndim == 3 ? D : 1) * H * W >= (1ull << 31)) { set_error("volume too large"); return TRB_ERR_UNSUPPORTED; }
+    const NmiLayout L = nmi_layout(ndim, D, H, W);
+    if (!ws || ws_bytes < L.total) { set_error("workspace too small: need %zu bytes", L.total); return TRB_ERR_WORKSPACE; }
+    return TRB_OK;
+}
+
+static float nmi_kappa(float h) { return (float)(sqrt(0.5 * 1.4426950408889634) / (double)h); }   // exp(-u^2/2) = 2^-(kappa*(s-c))^2
+
+template <int NDIM>
+static void nmi_resample(const float *src, int D, int H, int W, float *rs, int *keys2, cudaStream_t s)
+{
+    const int N = NDIM == 3 ? kRes * kRes * kRes : kRes * kRes;
+    // torch computes the scale in fp32 as input_size / output_size (UpSample.h compute_scales_value)
+    const float sz = (float)(NDIM == 3 ? D : 1) / (float)kRes, sy = (float)H / (float)kRes, sx = (float)W / (float)kRes;
+    int nb = (N + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    nmi_reset_kernel<<<1, 32, 0, s>>>(keys2);
+    nmi_resample_kernel<NDIM><<<nb, 256, 0, s>>>(src, D, H, W, sz, sy, sx, rs, keys2);
+}
+
+}  // namespace trb
+
+using namespace trb;
+
+extern "C" size_t trb_nmi_workspace_bytes(int ndim, int D, int H, int W)
+{
+    if ((ndim != 2 && ndim != 3) || H < 1 || W < 1 || (ndim == 3 && D < 1)) return 0;
+    return nmi_layout(ndim, D, H, W).total;
+}
+
+extern "C" int trb_nmi_prepare(int ndim, const float *target_dev, int D, int H, int W, float bandwidth,
+                               void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    int rc = nmi_validate(ndim, D, H, W, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (!target_dev) { set_error("null target"); return TRB_ERR_ARG; }
+    if (!(bandwidth > 0.f)) { set_error("bandwidth must be positive"); return TRB_ERR_ARG; }
+    const NmiLayout L = nmi_layout(ndim, D, H, W);
+    char *ws = (char *)workspace_dev;
+    float *rs_t = (float *)(ws + L.off_rs_t), *part = (float *)(ws + L.off_part);
+    double *hist = (double *)(ws + L.off_hist);
+    int *keys = (int *)(ws + L.off_range), *tabs = (int *)(ws + L.off_tabs);
+    cudaStream_t s = (cudaStream_t)stream;
+    // resampled-index ranges per source index, axis order x, y, z
+    int *t = tabs;
+    for (int a = 0; a < ndim; ++a) {
+        const int S = L.S[a];
+        nmi_tables_kernel<<<(S + 127) / 128, 128, 0, s>>>(S, (float)S / (float)kRes, t, t + S);
+        t += 2 * S;
+    }
+    if (ndim == 3) nmi_resample<3>(target_dev, D, H, W, rs_t, keys, s);
+    else nmi_resample<2>(target_dev, 1, H, W, rs_t, keys, s);
+    // the target's own marginal (range = target range): constant over the epochs
+    const size_t stream_stride = (size_t)L.K * L.tiles * kBins;
+    nmi_hist_kernel<1><<<L.K * L.tiles, 256, 0, s>>>(rs_t, L.P, L.tiles, keys, kRangeT, kRangeT, nmi_kappa(bandwidth),
+                                                     part + 2 * stream_stride, nullptr);
+    nmi_reduce_kernel<<<dim3(L.K, 1), 256, 0, s>>>(part + 2 * stream_stride, L.tiles, stream_stride, hist, (size_t)L.K * kBins);
+    return check_cuda(cudaGetLastError(), "nmi_prepare");
+}
+
+extern "C" int trb_nmi_loss_grad(int ndim, const float *warped_dev, int D, int H, int W, float bandwidth, float alpha,
+                                 float weight, double *loss_dev, float *gout_dev, void *workspace_dev,
+                                 size_t workspace_bytes, void *stream)
+{
+    int rc = nmi_validate(ndim, D, H, W, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (!warped_dev || !loss_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    if (!(bandwidth > 0.f)) { set_error("bandwidth must be positive"); return TRB_ERR_ARG; }
+    const NmiLayout L = nmi_layout(ndim, D, H, W);
+    char *ws = (char *)workspace_dev;
+    float *rs_t = (float *)(ws + L.off_rs_t), *rs_w = (float *)(ws + L.off_rs_w), *grs = (float *)(ws + L.off_grs);
+    float *part = (float *)(ws + L.off_part);
+    double *hist = (double *)(ws + L.off_hist);
+    float4 *gtab = (float4 *)(ws + L.off_gtab);
+    int *keys = (int *)(ws + L.off_range), *tabs = (int *)(ws + L.off_tabs);
+    cudaStream_t s = (cudaStream_t)stream;
+    const float kappa = nmi_kappa(bandwidth);
+    const size_t stream_stride = (size_t)L.K * L.tiles * kBins, hs = (size_t)L.K * kBins;
+    if (ndim == 3) nmi_resample<3>(warped_dev, D, H, W, rs_w, keys + 2, s);
+    else nmi_resample<2>(warped_dev, 1, H, W, rs_w, keys + 2, s);
+    nmi_hist_kernel<2><<<L.K * L.tiles, 256, 0, s>>>(rs_w, L.P, L.tiles, keys, kRangeW, kRangeJ, kappa, part, part + stream_stride);
+    nmi_hist_kernel<1><<<L.K * L.tiles, 256, 0, s>>>(rs_t, L.P, L.tiles, keys, kRangeJ, kRangeJ, kappa, part + 2 * stream_stride, nullptr);
+    nmi_reduce_kernel<<<dim3(L.K, 3), 256, 0, s>>>(part, L.tiles, stream_stride, hist + hs, hs);
+    nmi_epilogue_kernel<<<1, 256, 0, s>>>(hist, L.K, keys, kappa, bandwidth, (double)alpha, (double)weight, gtab, loss_dev);
+    if (gout_dev) {
+        nmi_grad_kernel<<<dim3((L.P + 255) / 256, L.K), 256, 0, s>>>(rs_w, L.P, gtab, kappa, grs);
+        const size_t vol = (size_t)(ndim == 3 ? D : 1) * H * W;
+        size_t nb = (vol + 255) / 256;
+        if (nb > 148 * 16) nb = 148 * 16;
+        if (ndim == 3) nmi_scatter_kernel<3><<<(unsigned)nb, 256, 0, s>>>(grs, D, H, W, tabs, gout_dev);
+        else nmi_scatter_kernel<2><<<(unsigned)nb, 256, 0, s>>>(grs, 1, H, W, tabs, gout_dev);
+    }
+    return check_cuda(cudaGetLastError(), "nmi_loss_grad");
+}

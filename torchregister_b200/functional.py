@@ -309,6 +309,41 @@ def flow_loss_grad(moving: torch.Tensor, target: torch.Tensor, flow: torch.Tenso
 # --------------------------------------------------------------------------- #
 # EXTENSION: direct per-voxel flow optimisation (no reference counterpart)
 # --------------------------------------------------------------------------- #
+class NmiTerm:
+    """NMI/KDE term of the reference's default loss for ONE pair, on CUDA kernels (trb_nmi_prepare once per target,
+    trb_nmi_loss_grad per call).  Reference: NMILoss.forward utils.py:224-259 + NMI/get_pdf utils.py:18-79 with the
+    module's default bins=256, patch_size=100."""
+
+    def __init__(self, target: torch.Tensor, bandwidth: float = 3.0, alpha: float = 1000.0):
+        require_cuda(target, "target")
+        self.lib = _lib.load()
+        self.ndim, self.D, self.H, self.W = _vol_dims(target)
+        if target.shape[0] != 1 or target.shape[1] != 1:
+            raise ValueError("NmiTerm expects a [1,1,...] target")
+        self.device = target.device
+        self.bandwidth, self.alpha = float(bandwidth), float(alpha)
+        n = int(self.lib.trb_nmi_workspace_bytes(self.ndim, self.D, self.H, self.W))
+        self.workspace = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.loss = torch.zeros(1, dtype=torch.float64, device=self.device)
+        t = target.detach().contiguous().float()
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_nmi_prepare(self.ndim, t.data_ptr(), self.D, self.H, self.W, self.bandwidth,
+                                           self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "nmi_prepare")
+
+    def loss_grad(self, warped: torch.Tensor, weight: float = 1.0, want_grad: bool = True):
+        """-> (weight*loss as a [1] fp64 device tensor (overwritten by the next call), weight * d loss / d warped or None)."""
+        require_cuda(warped, "warped")
+        if tuple(warped.shape[2:]) != ((self.D, self.H, self.W) if self.ndim == 3 else (self.H, self.W)) or warped.shape[0] != 1 or warped.shape[1] != 1:
+            raise ValueError("warped must have the target's [1,1,...] shape")
+        w = warped.detach().contiguous().float()
+        gout = torch.empty_like(w) if want_grad else None
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_nmi_loss_grad(self.ndim, w.data_ptr(), self.D, self.H, self.W, self.bandwidth, self.alpha,
+                                             float(weight), self.loss.data_ptr(), _ptr(gout), self.workspace.data_ptr(),
+                                             self.workspace.numel(), _stream(self.device)), "nmi_loss_grad")
+        return self.loss, gout
+
+
 class DirectFlowProblem:
     """Per-voxel flow field optimised with SGD or Adam on
     loss = w_mse*MSE + w_ncc*100*(1-NCC) + smooth * mean_axes(mean(forward_diff(flow)^2)).

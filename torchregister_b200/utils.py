@@ -120,8 +120,9 @@ class _KDEMutualInfoFn(torch.autograd.Function):
 class NMILoss(nn.Module):
     """Normalised-mutual-information term of the reference's default loss (utils.py:224-259): nearest-resample
     both images to (2*patch)^n, view as 2^n chunks of patch^n, 256-bin Gaussian KDE (bandwidth 3) of target,
-    warped and their concatenation, loss = mean(|NMI - 1|) * alpha.  Evaluated with PyTorch ops (host code):
-    fusing it into the CUDA step is the first "next" row of SURVEY.md §8f."""
+    warped and their concatenation, loss = mean(|NMI - 1|) * alpha.  One fp32 CUDA pair with the default bins/patch
+    runs on the kernels of csrc/nmi.cu; anything else (CPU tensors, batches, other bin counts)
+    on the PyTorch restatement below (the GPU tests check the kernels against it)."""
 
     def __init__(self, alpha=1000, bins=256, patch_size=100, bandwidth=3, block=8):
         super().__init__()
@@ -133,9 +134,37 @@ class NMILoss(nn.Module):
         v = F.interpolate(v, size=(r,) * nd, mode='nearest')
         return v.reshape((2 ** nd) * v.shape[0] * v.shape[1], -1)
 
+    def _cuda_term(self, y):
+        """CUDA kernels (csrc/nmi.cu) for one fp32 [1,1,...] pair with the default bins/patch; the target's resample
+        and marginal are cached while the same target tensor comes back (every epoch of a registration)."""
+        from . import functional as TF
+        key = (y.data_ptr(), y._version, tuple(y.shape), float(self.bandwidth), float(self.alpha))
+        if getattr(self, "_term_key", None) != key:
+            self._term = TF.NmiTerm(y, self.bandwidth, self.alpha)
+            self._term_key = key
+        return self._term
+
     def forward(self, y, yp):
+        if (y.is_cuda and yp.is_cuda and y.dtype == torch.float32 and yp.dtype == torch.float32 and y.shape == yp.shape
+                and y.shape[0] == 1 and y.shape[1] == 1 and self.bins == 256 and self.patch == 100 and y.dim() in (4, 5)):
+            return _NmiCudaFn.apply(yp, self._cuda_term(y))
         return _KDEMutualInfoFn.apply(self._chunks(y), self._chunks(yp), self.bins, float(self.bandwidth),
                                       float(self.alpha), self.block)
+
+
+class _NmiCudaFn(torch.autograd.Function):
+    """autograd node around trb_nmi_loss_grad: the backward w.r.t. the warped image is produced with the forward."""
+
+    @staticmethod
+    def forward(ctx, yp, term):
+        loss, gout = term.loss_grad(yp, 1.0, want_grad=yp.requires_grad)
+        ctx.save_for_backward(gout if gout is not None else torch.empty(0, device=yp.device))
+        return loss[0].float().clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (gout,) = ctx.saved_tensors
+        return gout * grad_out, None
 
 
 def norm(x):

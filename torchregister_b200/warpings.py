@@ -91,24 +91,23 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
     if w_nmi == 0:
         prob.run(epochs, lr, w_mse, w_ncc)               # one fused launch per epoch, no host round trips
     else:
-        # Default weights of the reference include the NMI/KDE term (utils.py:224-259).  It is not fused yet
-        # (SURVEY.md §8f-1): per epoch the MSE/NCC moments come from the CUDA pass, the NMI term and its
-        # gradient w.r.t. the warped volume from PyTorch ops, chained to theta by trb_warp_affine_vjp, and the
-        # update is applied on the device by trb_affine_apply.  Still no host synchronisation.
-        nmi = NMILoss()
+        # Default weights of the reference include the NMI/KDE term (utils.py:224-259).  Per epoch: the MSE/NCC
+        # moments from the CUDA pass, the warped volume, the NMI term and its gradient w.r.t. the warped volume
+        # from the KDE kernels (csrc/nmi.cu: MUFU bound, ~2 ms in 3-D), chained to theta by trb_warp_affine_vjp,
+        # and the update applied on the device by trb_affine_apply.  No host synchronisation.
         nd = moving.dim() - 2
         n_slices = int(moving.shape[2])
         n_pairs = int(moving.shape[0])
+        terms = [TF.NmiTerm(target[i:i + 1]) for i in range(n_pairs)]     # NMILoss() defaults: bandwidth 3, alpha 1000
         extra = torch.zeros(n_pairs, 13, dtype=torch.float64, device=moving.device)
         for _ in range(epochs):
             theta = prob.theta
             mom = prob.moments(0, n_slices)
             for i in range(n_pairs):
-                warped = TF.warp_affine(theta[i], moving[i:i + 1]).requires_grad_(True)
-                term = w_nmi * nmi(target[i:i + 1], warped)
-                (gw,) = torch.autograd.grad(term, warped)
-                extra[i, 0] = term.detach().double()
-                extra[i, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta[i], moving[i:i + 1], gw.contiguous()).reshape(-1)
+                warped = TF.warp_affine(theta[i], moving[i:i + 1])
+                term, gw = terms[i].loss_grad(warped, w_nmi)
+                extra[i, 0:1] = term
+                extra[i, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta[i], moving[i:i + 1], gw).reshape(-1)
             prob.apply(mom, lr, w_mse, w_ncc, extra=extra)
     final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
     # the reference keeps the warped volumes of the final and best epochs; we never write them during
