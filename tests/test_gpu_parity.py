@@ -512,11 +512,13 @@ def _nmi_restatement(y, yp, dtype):
 
 
 @pytest.mark.parametrize("shape,scale", [((24, 32, 40), 1.0), ((24, 32, 40), 255.0), ((64, 48), 1.0), ((256, 256), 255.0),
-                                         ((300, 180), 40.0), ((210, 96, 230), 255.0), ((7, 9), 3.0)])
+                                         ((300, 180), 40.0), ((210, 96, 230), 255.0), ((7, 9), 3.0),
+                                         ((24, 32, 40), 4000.0), ((256, 256), 65535.0)])
 def test_nmi_kernels_vs_torch_restatement(shape, scale):
     """Up- and down-sampling shapes, 2-D and 3-D, data in [0,1] (where |NMI-1| ~ 1e-6 and the fp32 PyTorch evaluation
-    is rounding noise — the kernels reduce in fp64 and land closer to the fp64 value) and wide-range data (a real
-    histogram).  Tolerance: 1e-4 relative, or twice the fp32 restatement's own distance from fp64."""
+    is rounding noise — the kernels reduce in fp64 and land closer to the fp64 value), 8-bit-range data (a real
+    histogram, grouped-bin path) and 12/16-bit ranges (bin spacing above 1.7 bandwidths: direct path).
+    Tolerance: 1e-4 relative, or twice the fp32 restatement's own distance from fp64."""
     TF = _tf()
     from torchregister_b200.synth import make_pair
     mov, tgt = make_pair(shape, "rigid", device=DEV)
@@ -533,7 +535,7 @@ def test_nmi_kernels_vs_torch_restatement(shape, scale):
     assert err <= max(1e-4 * gmax, 2 * err32), (err, err32, gmax)
     # weight scales both outputs; forward-only call leaves the loss unchanged
     loss2, g2 = term.loss_grad(yp, 0.25)
-    assert abs(loss2.item() - 0.25 * loss) <= 1e-12 + 1e-9 * abs(loss) and torch.allclose(g2, 0.25 * g, rtol=1e-6, atol=0)
+    assert abs(loss2.item() - 0.25 * loss) <= 1e-12 + 1e-9 * abs(loss) and torch.allclose(g2, 0.25 * g, rtol=1e-5, atol=1e-9 * gmax)
     loss3, none = term.loss_grad(yp, 1.0, want_grad=False)
     assert none is None and loss3.item() == loss
 
