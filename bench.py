@@ -342,6 +342,17 @@ def main():
         us = a0.elapsed_time(a1) * 1e3 / 100
         extra["batch_8x192x192x160_mse_only"] = {"us_per_epoch": us, "voxel_warps_per_s": PAIRS_PER_GPU * vox / (us * 1e-6),
                                                  "algorithmic_GBps": 8.0 * PAIRS_PER_GPU * vox / (us * 1e-6) / 1e9}
+        # the reference's DEFAULT loss (weights .33/.33/.33 incl. the NMI/KDE term, csrc/nmi.cu) on one pair
+        one_m, one_t = mov[:1].contiguous(), tgt[:1].contiguous()
+        rd = tr.Register(mode="affine", device=dev)
+        rd.optim(one_m, one_t, lr=1e-5, max_epochs=3)
+        torch.cuda.synchronize(dev)
+        t0 = time.perf_counter()
+        rd.optim(one_m, one_t, lr=1e-5, max_epochs=30)
+        torch.cuda.synchronize(dev)
+        us = (time.perf_counter() - t0) / 30 * 1e6
+        extra["single_pair_default_loss_mse+ncc+nmi"] = {"us_per_epoch": us, "voxel_warps_per_s": vox / (us * 1e-6),
+                                                         "note": "wall clock through Register (8 + ~14 launches per epoch)"}
         line["extra"] = extra
 
     if not args.no_cpu_baseline and world == 1:
