@@ -309,15 +309,31 @@ __global__ void __launch_bounds__(256) nmi_hist_kernel(const float *__restrict__
     if (NSETS == 2) part1[o] = (a1[0] + a1[1]) + (a1[2] + a1[3]);
 }
 
-// hist[k][b] = sum over tiles, fixed order, fp64.  grid = (K, n_streams)
+// hist[k][b] = sum over tiles, fixed order, fp64.  grid = (K, n_streams).  16 columns x 16 tile lanes at a time;
+// slots in moment form only carry kMom columns.
 __global__ void __launch_bounds__(256) nmi_reduce_kernel(const float *__restrict__ part, int tiles, size_t stream_stride,
-                                                          double *__restrict__ hist, size_t hist_stride)
+                                                          double *__restrict__ hist, size_t hist_stride,
+                                                          const int *__restrict__ keys, int range_first, int range_rest, float h)
 {
+    __shared__ double sh[16][17];
     const int k = blockIdx.x;
-    const float *p = part + (size_t)blockIdx.y * stream_stride + (size_t)k * tiles * kBins + threadIdx.x;
-    double acc = 0.0;
-    for (int t = 0; t < tiles; ++t) acc += (double)p[(size_t)t * kBins];
-    hist[(size_t)blockIdx.y * hist_stride + (size_t)k * kBins + threadIdx.x] = acc;
+    const int cols = moment_ok(keys, blockIdx.y == 0 ? range_first : range_rest, h) ? 16 : kBins;
+    const float *p = part + (size_t)blockIdx.y * stream_stride + (size_t)k * tiles * kBins;
+    double *out = hist + (size_t)blockIdx.y * hist_stride + (size_t)k * kBins;
+    const int col = threadIdx.x & 15, lane = threadIdx.x >> 4;
+    for (int c0 = 0; c0 < cols; c0 += 16) {
+        double acc = 0.0;
+        for (int t = lane; t < tiles; t += 16) acc += (double)p[(size_t)t * kBins + c0 + col];
+        sh[lane][col] = acc;
+        __syncthreads();
+        if (threadIdx.x < 16) {
+            double v = 0.0;
+#pragma unroll
+            for (int l = 0; l < 16; ++l) v += sh[l][threadIdx.x];
+            out[c0 + threadIdx.x] = v;
+        }
+        __syncthreads();
+    }
 }
 
 __device__ __forceinline__ double block_sum256(double v, double *sh)
@@ -464,13 +480,20 @@ __global__ void __launch_bounds__(256) nmi_grad_kernel(const float *__restrict__
 {
     __shared__ __align__(16) float tab[6 * kBins];
     const int k = blockIdx.y;
-    for (int i = threadIdx.x; i < 6 * kBins; i += 256) tab[i] = gtab[(size_t)k * 6 * kBins + i];
+    const bool mom = moment_ok(keys, kRangeJ, h);
+    const float *gt = gtab + (size_t)k * 6 * kBins;
+    if (mom) {                                   // 2 x (centre + kMom coefficients) instead of the 6 KB table
+        if (threadIdx.x <= kMom) { tab[kBins - 1 + threadIdx.x] = gt[kBins - 1 + threadIdx.x]; tab[4 * kBins - 1 + threadIdx.x] = gt[4 * kBins - 1 + threadIdx.x]; }
+        if (threadIdx.x == 0) { tab[0] = gt[0]; tab[3 * kBins] = gt[3 * kBins]; }
+    } else {
+        for (int i = threadIdx.x; i < 6 * kBins; i += 256) tab[i] = gt[i];
+    }
     const float dW = bin_delta(keys, kRangeW, kappa), dJ = bin_delta(keys, kRangeJ, kappa);
     __syncthreads();
     const int i = blockIdx.x * 256 + threadIdx.x;
     if (i >= P) return;
     const float s = rs_w[(size_t)k * P + i];
-    if (moment_ok(keys, kRangeJ, h)) {
+    if (mom) {
         float acc = 0.f;
         const float inv_h = 1.f / h;
         hermite_chain<kMom + 1>(s, tab[0], inv_h, [&](int m, float x) { if (m > 0) acc = fmaf(tab[kBins + m - 1], x, acc); });
@@ -561,7 +584,8 @@ extern "C" int trb_nmi_prepare(int ndim, const float *target_dev, int D, int H, 
     nmi_hist_kernel<1><<<L.K * L.tiles, 256, 0, s>>>(rs_t, L.P, L.tiles, keys, kRangeT, kRangeT, nmi_kappa(bandwidth), bandwidth,
                                                      part + 2 * stream_stride, nullptr);
     cudaMemsetAsync(ws + L.off_scal, 0, 16 * sizeof(double), s);        // chunk terms + the epilogue's ticket
-    nmi_reduce_kernel<<<dim3(L.K, 1), 256, 0, s>>>(part + 2 * stream_stride, L.tiles, stream_stride, hist, (size_t)L.K * kBins);
+    nmi_reduce_kernel<<<dim3(L.K, 1), 256, 0, s>>>(part + 2 * stream_stride, L.tiles, stream_stride, hist, (size_t)L.K * kBins, keys,
+                                                 kRangeT, kRangeT, bandwidth);
     return check_cuda(cudaGetLastError(), "nmi_prepare");
 }
 
@@ -587,7 +611,7 @@ extern "C" int trb_nmi_loss_grad(int ndim, const float *warped_dev, int D, int H
     else nmi_resample<2>(warped_dev, 1, H, W, rs_w, keys + 2, s);
     nmi_hist_kernel<2><<<L.K * L.tiles, 256, 0, s>>>(rs_w, L.P, L.tiles, keys, kRangeW, kRangeJ, kappa, bandwidth, part, part + stream_stride);
     nmi_hist_kernel<1><<<L.K * L.tiles, 256, 0, s>>>(rs_t, L.P, L.tiles, keys, kRangeJ, kRangeJ, kappa, bandwidth, part + 2 * stream_stride, nullptr);
-    nmi_reduce_kernel<<<dim3(L.K, 3), 256, 0, s>>>(part, L.tiles, stream_stride, hist + hs, hs);
+    nmi_reduce_kernel<<<dim3(L.K, 3), 256, 0, s>>>(part, L.tiles, stream_stride, hist + hs, hs, keys, kRangeJ, kRangeJ, bandwidth);
     nmi_epilogue_kernel<<<L.K, 256, 0, s>>>(hist, L.K, keys, kappa, bandwidth, (double)alpha, (double)weight, gtab,
                                            (double *)(ws + L.off_scal), loss_dev);
     if (gout_dev) {
