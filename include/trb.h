@@ -112,6 +112,20 @@ int trb_affine_optim(int ndim, int mode,
                      int optimiser, float beta1, float beta2, float adam_eps,
                      void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* One volume sharded into z-slabs over up to 8 GPUs of one box, fused form (replaces the trb_affine_moments ->
+ * all-reduce -> trb_affine_apply triple): n_epochs launches of the epoch kernel on slices [s_begin, s_end); the last
+ * CTA of every rank pushes its 41 partial moments into every rank's mailbox with peer stores over NVLink, waits for
+ * the others' (bounded spin: a missing peer yields NaN losses, not a hang), adds them in rank order and runs the
+ * epilogue, so every rank applies the identical update.  mailbox_ptrs[r] = rank r's mailbox (2*8*48 doubles, zeroed
+ * once) as mapped into THIS process (CUDA IPC / symmetric memory; peer access enabled).  Every rank must make the
+ * same calls with the same seq0 (>= 1, advance it by n_epochs per call).  3-D, shapes the TMA kernel accepts. */
+int trb_affine_optim_peer(const float *moving_dev, const float *target_dev, int D, int H, int W, int s_begin, int s_end,
+                          const float *xb_dev, const float *yb_dev, const float *zb_dev, int mode,
+                          float *state_dev, float *loss_log_dev, int log_stride, int epoch0, int n_epochs,
+                          float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2, float adam_eps,
+                          void *const *mailbox_ptrs, int rank, int world, unsigned long long seq0,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* Sharded variant for one large volume split into z-slabs (2-D: y-slabs) across
  * GPUs: accumulate the TRB_MOMENTS fp64 moments of output slices [s_begin,s_end)
  * into moments_dev[n_pairs][TRB_MOMENTS] (overwritten), no update.  After the

@@ -24,13 +24,17 @@ def main():
     p0 = torch.tensor([0.03, -0.02, 0.04, 0.05, -0.05, 0.02], device=dev)
     single = TF.AffineProblem(mov, tgt, "rigid", p0, 5)
     single.run(5, 1e-3, 0.5, 0.5)
-    sh = ShardedAffine(mov, tgt, "rigid", p0, 5)
-    sh.run(5, 1e-3, 0.5, 0.5)
-    assert torch.allclose(sh.losses, single.losses, rtol=2e-5), (sh.losses, single.losses)
-    assert torch.allclose(sh.final_theta, single.final_theta, atol=1e-6)
-    thetas = [torch.empty_like(sh.final_theta) for _ in range(world)]
-    dist.all_gather(thetas, sh.final_theta)
-    assert all(torch.equal(t, thetas[0]) for t in thetas), "ranks diverged"      # identical redundant update
+    paths = []
+    for peer in (False, None):          # NCCL all-reduce between two kernels / fused epoch kernel with the peer-memory all-reduce
+        sh = ShardedAffine(mov, tgt, "rigid", p0, 5, peer=peer)
+        sh.run(2, 1e-3, 0.5, 0.5)
+        sh.run(3, 1e-3, 0.5, 0.5)       # a second call continues the mailbox sequence
+        assert torch.allclose(sh.losses, single.losses, rtol=2e-5), (peer, sh.losses, single.losses)
+        assert torch.allclose(sh.final_theta, single.final_theta, atol=1e-6)
+        thetas = [torch.empty_like(sh.final_theta) for _ in range(world)]
+        dist.all_gather(thetas, sh.final_theta)
+        assert all(torch.equal(t, thetas[0]) for t in thetas), "ranks diverged"      # identical redundant update
+        paths.append("peer-memory" if sh.mailbox is not None else "nccl (%s)" % sh.peer_error)
 
     # (c) one volume, direct flow, z-slabs + halo exchange + all-reduce of 6 moments
     shape = (48, 40, 44)
@@ -60,7 +64,7 @@ def main():
     assert torch.allclose(out, ref.final_theta, atol=2e-6)
     dist.barrier()
     if rank == 0:
-        print("MGPU OK world=%d" % world)
+        print("MGPU OK world=%d; sharded affine paths checked: %s" % (world, paths))
     dist.destroy_process_group()
 
 

@@ -400,6 +400,36 @@ extern "C" int trb_affine_optim(int ndim, int mode, const float *moving_dev, con
     return check_cuda(cudaGetLastError(), "affine_optim");
 }
 
+extern "C" int trb_affine_optim_peer(const float *moving_dev, const float *target_dev, int D, int H, int W, int s_begin, int s_end,
+                                     const float *xb_dev, const float *yb_dev, const float *zb_dev, int mode,
+                                     float *state_dev, float *loss_log_dev, int log_stride, int epoch0, int n_epochs,
+                                     float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2, float adam_eps,
+                                     void *const *mailbox_ptrs, int rank, int world, unsigned long long seq0,
+                                     void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    AffineParams p{};
+    int rc = fill_params(p, 3, moving_dev, target_dev, 0, 1, D, H, W, xb_dev, yb_dev, zb_dev, workspace_dev, workspace_bytes);
+    if (rc) return rc;
+    if (!state_dev) { set_error("null state"); return TRB_ERR_ARG; }
+    if (mode != TRB_MODE_RIGID && mode != TRB_MODE_AFFINE) { set_error("bad mode %d", mode); return TRB_ERR_ARG; }
+    if (optimiser != TRB_OPT_SGD && optimiser != TRB_OPT_ADAM) { set_error("bad optimiser %d", optimiser); return TRB_ERR_ARG; }
+    if (loss_log_dev && epoch0 + n_epochs > log_stride) { set_error("loss log too short"); return TRB_ERR_ARG; }
+    if (s_begin < 0 || s_end > D || s_begin >= s_end) { set_error("bad slab [%d,%d) of %d", s_begin, s_end, D); return TRB_ERR_ARG; }
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !mailbox_ptrs || seq0 < 1) { set_error("bad peer set (world 1..8, seq0 >= 1)"); return TRB_ERR_ARG; }
+    for (int r = 0; r < world; ++r) {
+        if (!mailbox_ptrs[r]) { set_error("null mailbox pointer for rank %d", r); return TRB_ERR_ARG; }
+        p.peer.mailbox[r] = (double *)mailbox_ptrs[r];
+    }
+    p.peer.rank = rank; p.peer.world = world; p.peer.seq = seq0;
+    p.s_begin = s_begin; p.s_end = s_end;
+    p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride;
+    p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
+    p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
+    if (!tma_path_eligible(3, p, 1)) { set_error("the fused sharded epoch needs the TMA kernel (3-D, W %% 4 == 0, W >= 32, H >= 16)"); return TRB_ERR_UNSUPPORTED; }
+    if (n_epochs <= 0) return TRB_OK;             // validation only
+    return launch_affine3d_tma(p, 1, true, epoch0, n_epochs, (cudaStream_t)stream);
+}
+
 extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
                                   int n_pairs, int D, int H, int W, int s_begin, int s_end,
                                   const float *xb_dev, const float *yb_dev, const float *zb_dev,

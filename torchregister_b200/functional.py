@@ -139,6 +139,30 @@ class AffineProblem:
                 self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "affine_optim")
         self.epoch += n_epochs
 
+    # -- sharded (z-slab) form, fused: the epoch kernel all-reduces the moments itself through peer memory
+    def run_peer(self, n_epochs: int, s_begin: int, s_end: int, mailbox_ptrs, rank: int, world: int, seq0: int,
+                 lr: float, w_mse: float, w_ncc: float, optimiser: str = "sgd", betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        """`mailbox_ptrs[r]`: rank r's mailbox (2*8*48 float64, zeroed) as mapped into this process.  Every rank makes
+        the same calls; `seq0` >= 1 advances by n_epochs per call (parallel.PeerMailbox keeps it).  n_epochs == 0 only
+        validates (raises if this shape / slab cannot take the fused path)."""
+        if n_epochs < 0:
+            return
+        if self.ndim != 3 or self.n_pairs != 1:
+            raise ValueError("the fused sharded epoch handles one 3-D pair")
+        if self.epoch + n_epochs > self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        import ctypes
+        arr = (ctypes.c_void_p * world)(*[int(v) for v in mailbox_ptrs])
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_affine_optim_peer(
+                self.moving.data_ptr(), self.target.data_ptr(), self.D, self.H, self.W, int(s_begin), int(s_end),
+                self.xb.data_ptr(), self.yb.data_ptr(), _ptr(self.zb), MODE[self.mode],
+                self.state.data_ptr(), self.loss_log.data_ptr(), self.loss_log.shape[1], self.epoch, n_epochs,
+                float(w_mse), float(w_ncc), float(lr), OPT[optimiser], float(betas[0]), float(betas[1]), float(eps),
+                arr, int(rank), int(world), int(seq0), self.workspace.data_ptr(), self.workspace.numel(),
+                _stream(self.device)), "affine_optim_peer")
+        self.epoch += n_epochs
+
     # -- sharded (z-slab) form: moments -> [all-reduce by the caller] -> apply
     def moments(self, s_begin: int, s_end: int, out: Optional[torch.Tensor] = None) -> torch.Tensor:
         if out is None:

@@ -38,12 +38,39 @@ def allreduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:
     return moments
 
 
+class PeerMailbox:
+    """Peer-mapped mailbox for the fused all-reduce of the sharded affine epoch (include/trb.h: trb_affine_optim_peer).
+    Every rank allocates 2*8*48 float64 in symmetric memory (torch.distributed._symmetric_memory: the buffer of every
+    rank is mapped into every process, peer access over NVLink); `ptrs[r]` is rank r's buffer in this process."""
+
+    DOUBLES = 2 * 8 * 48
+
+    def __init__(self, device, group=None):
+        import torch.distributed._symmetric_memory as symm_mem
+        grp = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(grp), dist.get_rank(grp)
+        if self.world > 8:
+            raise ValueError("the peer mailbox holds up to 8 ranks (one NVSwitch box)")
+        self.buf = symm_mem.empty(self.DOUBLES, dtype=torch.float64, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, grp)
+        self.ptrs = [int(p) for p in self.handle.buffer_ptrs]
+        torch.cuda.synchronize(device)
+        dist.barrier(grp)                       # every mailbox is zeroed and mapped before the first push
+        self.seq = 1
+
+    def take(self, n):
+        s = self.seq
+        self.seq += int(n)
+        return s
+
+
 class ShardedAffine:
     """Rigid/affine registration of ONE large pair with the output volume split into slabs over the
     ranks of `group`.  Every rank holds the full moving volume and (for simplicity of addressing) the
     full target; only its own target slab is read."""
 
-    def __init__(self, moving, target, mode, params0, max_epochs, group=None):
+    def __init__(self, moving, target, mode, params0, max_epochs, group=None, peer=None):
         from . import functional as TF
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -52,8 +79,28 @@ class ShardedAffine:
         n_slices = self.prob.D if self.prob.ndim == 3 else self.prob.H
         self.s_begin, self.s_end = slab_range(n_slices, self.world, self.rank)
         self._mom = torch.empty(self.prob.n_pairs, TF.MOMENTS, dtype=torch.float64, device=self.prob.device)
+        # fused form (one kernel per epoch, moments all-reduced inside it through peer memory) when the box allows
+        # it; otherwise moments kernel -> NCCL all-reduce -> apply kernel
+        self.mailbox, self.peer_error = None, None
+        if peer is not False and self.world > 1 and self.prob.ndim == 3 and self.prob.n_pairs == 1:
+            ok = 1
+            try:
+                self.mailbox = PeerMailbox(self.prob.device, group)
+                self.prob.run_peer(0, self.s_begin, self.s_end, self.mailbox.ptrs, self.rank, self.world, 1, 0.0, 0.0, 1.0)
+            except Exception as e:                       # no symmetric memory on this box / shape the TMA kernel rejects
+                ok, self.peer_error = 0, repr(e)
+            flag = torch.tensor([ok], device=self.prob.device, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
+            if int(flag.item()) == 0:
+                self.mailbox = None
+                if peer is True:
+                    raise RuntimeError("fused sharded epoch unavailable: %s" % (self.peer_error or "another rank declined"))
 
     def run(self, n_epochs, lr, w_mse, w_ncc, optimiser="sgd"):
+        if self.mailbox is not None:
+            self.prob.run_peer(n_epochs, self.s_begin, self.s_end, self.mailbox.ptrs, self.rank, self.world,
+                               self.mailbox.take(n_epochs), lr, w_mse, w_ncc, optimiser)
+            return
         for _ in range(n_epochs):
             self.prob.moments(self.s_begin, self.s_end, out=self._mom)
             allreduce_moments(self._mom, self.group)
