@@ -308,7 +308,7 @@ def main():
         "gpu_launches": K,
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                     "kernel": "trb::affine3d_tma_kernel<40,20,12,4,true> (csrc/affine_tma.cu)",
+                     "kernel": "trb::affine3d_tma_kernel<40,20,12,4,true,false> (csrc/affine_tma.cu)",
                      "algorithmic_bytes_per_launch": BYTES_PER_VOXEL_WARP * PAIRS_PER_GPU * vox,
                      "kernel_us": kernel_s * 1e6,
                      "frac_of_nominal_8TBps": achieved / 8000.0},
