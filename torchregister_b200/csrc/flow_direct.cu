@@ -244,8 +244,15 @@ __device__ __forceinline__ void direct_log_losses(const DirectParams &p, const d
     }
 }
 
+#ifndef TRB_STEP_MINB
+#define TRB_STEP_MINB 4
+#endif
+#ifndef TRB_STEP_UNROLL
+#define TRB_STEP_UNROLL 1
+#endif
+constexpr int kStepUnroll = TRB_STEP_UNROLL;
 template <bool NEXT, bool ADAM, bool SMOOTH>
-__global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectParams p, const int tiles_x, const int tiles_y,
+__global__ void __launch_bounds__(256, TRB_STEP_MINB) flow_direct_step_kernel(const DirectParams p, const int tiles_x, const int tiles_y,
                                                                const int zc)
 {
     const int W = p.W, H = p.H, D = p.D, Ds = p.Ds;
@@ -304,6 +311,7 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_kernel(const DirectPa
         }
         if (hoff >= 0) hcur = __ldg(p.flow_in + hoff + zl0 * HW);
         __syncthreads();                                   // the previous item's readers are done with the tile
+#pragma unroll kStepUnroll
         for (int zl = zl0; zl < zl1; ++zl) {
             const int z = p.z_off + zl, b = zl & 1;
             const int o = zl * HW + xy;
