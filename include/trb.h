@@ -231,6 +231,9 @@ int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
                          float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
                          void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* A/B switch for the smoothness variants of trb_flow_direct_step: 0 (default) = TMA-staged tiles, 1 = register-staged. */
+void trb_flow_direct_set_path(int no_tma);
+
 int trb_flow_direct_finish(const double *moments6_dev, int D, int H, int W, float w_mse, float w_ncc,
                            float smooth_lambda, float *loss_log_dev, int epochs_done,
                            void *workspace_dev, size_t workspace_bytes, void *stream);

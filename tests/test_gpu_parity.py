@@ -415,12 +415,13 @@ def test_direct_flow_slabs_equal_whole_volume():
         assert torch.allclose(slabs[0].losses, whole.losses, rtol=1e-5)
 
 
-@pytest.mark.parametrize("shape", [(13, 19, 37), (40, 33, 70)])
+@pytest.mark.parametrize("shape", [(13, 19, 37), (40, 33, 70), (21, 33, 72), (9, 10, 40)])
 @pytest.mark.parametrize("opt,weights,smooth", [("sgd", (1.0, 0.0), 0.0), ("sgd", (1.0, 0.0), 4.0), ("sgd", (0.5, 0.5), 4.0),
                                                 ("sgd", (0.0, 1.0), 0.0), ("adam", (0.5, 0.5), 4.0), ("adam", (1.0, 0.0), 0.0)])
 def test_direct_flow_fused_epoch_equals_two_pass(shape, opt, weights, smooth):
     """trb_flow_direct_step (one pass per epoch, z-marching tiles) against stats + update on ragged shapes: several
-    x/y tiles with inactive threads, several z chunks, every template variant."""
+    x/y tiles with inactive threads, several z chunks, every template variant; W % 4 == 0 shapes take the TMA-staged
+    kernel when smoothing is on (the others the register-staged one)."""
     TF = _tf()
     from torchregister_b200.synth import make_pair, smooth_flow
     mov, tgt = (t.to(DEV) for t in make_pair(shape, "flow"))

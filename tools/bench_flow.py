@@ -30,4 +30,12 @@ for opt, bpv2, bpv1 in (("sgd", 52, 32), ("adam", 100, 80)):
         prob = TF.DirectFlowProblem(mov, tgt, 1000000, optimiser=opt)
         us = timeit(lambda: prob.run(10, 0.05, w[0], w[1], sm)) / 10
         out["direct_flow_fused_%s_%s" % (opt, name)] = {"us": us, "alg_GBps": bpv1 * vox / us / 1e3, "bytes_per_voxel": bpv1}
+lib = TF._lib.load()
+lib.trb_flow_direct_set_path(1)
+for opt, bpv1 in (("sgd", 32), ("adam", 80)):
+    for name, w, sm in (("mse+ncc_smooth", (0.5, 0.5), 2.0), ("mse_smooth", (1.0, 0.0), 2.0)):
+        prob = TF.DirectFlowProblem(mov, tgt, 1000000, optimiser=opt)
+        us = timeit(lambda: prob.run(10, 0.05, w[0], w[1], sm)) / 10
+        out["direct_flow_fused_noTMA_%s_%s" % (opt, name)] = {"us": us, "alg_GBps": bpv1 * vox / us / 1e3, "bytes_per_voxel": bpv1}
+lib.trb_flow_direct_set_path(0)
 print(json.dumps({"size": S, "results": out}))

@@ -15,6 +15,7 @@
 // volume; `moving` is the full [D][H][W] volume; halo_lo / halo_hi are the neighbour ranks' flow slices
 // z_off-1 and z_off+Ds ([ndim][H][W]) or NULL at the volume boundary.
 #include "common.cuh"
+#include "tma_utils.cuh"
 #include <math.h>
 
 namespace trb {
@@ -427,6 +428,202 @@ __global__ void __launch_bounds__(256, TRB_STEP_MINB) flow_direct_step_kernel(co
     if (threadIdx.x == 0) *p.ticket = 0u;
 }
 
+// ---- the same epoch with the flow and target tiles staged by TMA (smoothness variants) ---------------------------
+// The stencil halo made the register/LDG version pay 168 L1 sectors per 256 voxels (48 of them single-float column
+// loads).  Here one elected thread issues, per slice, ONE tensor load of the 3-channel flow tile with its halo
+// (box 40 x 10 x 1 x 3 at (x0-4, y0-1, z, 0): 16-byte aligned start, out-of-range rows/columns zero-filled) and one of
+// the 32 x 8 target tile into a ring of kStepStages stages; all threads wait on the stage's mbarrier and read centre,
+// x/y neighbours, the next slice's centre (z+1) and the target from shared memory.  The ring runs ahead across work
+// items, so only the gathers of the moving volume (and Adam's m, v) are register-staged global loads.
+constexpr int kStepStages = 4;
+constexpr int kSX = kTX + 8, kSY = kTY + 2;              // staged flow tile: 4 extra floats left/right (alignment), 1 row up/down
+struct __align__(128) StepStage {
+    float flow[3][kSY][kSX];                             // 4800 B
+    float pad[16];                                       // next member on a 128-byte boundary
+    float tgt[kTY][kTX];                                 // 1024 B
+};
+constexpr unsigned kStageTx = 3 * kSY * kSX * 4 + kTY * kTX * 4;
+
+struct StepCursor {                                      // position in this CTA's flat sequence of (item, slice)
+    int item, i, nsl, x0, y0, zl0;
+};
+__device__ __forceinline__ void cursor_load(StepCursor &c, int items, int tiles_x, int tiles_xy, int zc, int Ds)
+{
+    if (c.item >= items) { c.nsl = 0; return; }
+    const int chunk = c.item / tiles_xy, t2 = c.item - chunk * tiles_xy;
+    const int by = t2 / tiles_x, bx = t2 - by * tiles_x;
+    c.x0 = bx * kTX; c.y0 = by * kTY; c.zl0 = chunk * zc;
+    c.nsl = min(zc, Ds - c.zl0);
+    c.i = 0;
+}
+__device__ __forceinline__ void cursor_next(StepCursor &c, int items, int tiles_x, int tiles_xy, int zc, int Ds, int stride)
+{
+    if (++c.i < c.nsl) return;
+    c.item += stride;
+    cursor_load(c, items, tiles_x, tiles_xy, zc, Ds);
+}
+
+template <bool NEXT, bool ADAM>
+__global__ void __launch_bounds__(256, 4) flow_direct_step_tma_kernel(const DirectParams p, const int tiles_x, const int tiles_y,
+                                                                      const int zc, const __grid_constant__ CUtensorMap map_flow,
+                                                                      const __grid_constant__ CUtensorMap map_tgt)
+{
+    const int W = p.W, H = p.H, D = p.D, Ds = p.Ds;
+    const int HW = H * W, slab = HW * Ds;
+    __shared__ StepStage stages[kStepStages];
+    __shared__ __align__(8) uint64_t full[kStepStages];
+    __shared__ float coef[3];
+    __shared__ double red[8][6];
+    __shared__ bool is_last;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kStepStages; ++i) tma::mbar_init(full + i, 1);
+        tma::fence_barrier_init();
+        const double n = (double)D * H * W;
+        const LossCoef lc = loss_coefficients(n, p.moments[0], p.moments[1], p.moments[2], p.moments[3], p.moments[4],
+                                              (double)p.w_mse, (double)p.w_ncc);
+        coef[0] = (float)lc.cw; coef[1] = (float)lc.ct; coef[2] = (float)lc.c0;
+        if (blockIdx.x == 0) direct_log_losses(p, p.moments, NEXT, true, (double *)p.ticket + 1);
+    }
+    __syncthreads();
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const int tiles_xy = tiles_x * tiles_y;
+    const int items = tiles_xy * ((Ds + zc - 1) / zc);
+    const int stride = gridDim.x;
+    StepCursor cons, prod;
+    cons.item = prod.item = blockIdx.x;
+    cursor_load(cons, items, tiles_x, tiles_xy, zc, Ds);
+    prod = cons;
+    unsigned issued = 0, consumed = 0;                   // slices issued / consumed by this CTA: stage = n % kStepStages
+    auto issue_one = [&]() {                             // thread 0 only
+        StepStage &st = stages[issued % kStepStages];
+        uint64_t *bar = full + issued % kStepStages;
+        tma::mbar_arrive_expect_tx(bar, kStageTx);
+        tma::load_4d(&st.flow[0][0][0], &map_flow, bar, prod.x0 - 4, prod.y0 - 1, prod.zl0 + prod.i, 0);
+        tma::load_4d(&st.tgt[0][0], &map_tgt, bar, prod.x0, prod.y0, prod.zl0 + prod.i, 0);
+        ++issued;
+        cursor_next(prod, items, tiles_x, tiles_xy, zc, Ds, stride);
+    };
+    if (threadIdx.x == 0)
+        for (int k = 0; k < kStepStages && prod.nsl > 0; ++k) issue_one();
+    float s[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    while (cons.nsl > 0) {
+        // per item: everything that does not change along z
+        const int x = cons.x0 + tx, y = cons.y0 + ty;
+        const bool active = x < W && y < H;
+        const int xy = y * W + x;
+        const int nsl = cons.nsl, zl0 = cons.zl0;
+        // volume-boundary neighbours: the staged halo holds zeros there; a 0/1 factor on the difference is the
+        // replicate boundary (difference 0) without per-slice predicates
+        const float mxm = x > 0 ? 1.f : 0.f, mxp = x + 1 < W ? 1.f : 0.f, mym = y > 0 ? 1.f : 0.f, myp = y + 1 < H ? 1.f : 0.f;
+        float fprev[3] = {0.f, 0.f, 0.f};
+        int o = zl0 * HW + xy;
+        for (int i = 0; i < nsl; ++i, o += HW) {
+            const int zl = zl0 + i, z = p.z_off + zl;
+            const bool last_of_item = i + 1 == nsl;
+            const StepStage &st = stages[consumed % kStepStages];
+            tma::mbar_wait(full + consumed % kStepStages, (consumed / kStepStages) & 1u);
+            const StepStage &nx = stages[(consumed + 1) % kStepStages];
+            if (!last_of_item) tma::mbar_wait(full + (consumed + 1) % kStepStages, ((consumed + 1) / kStepStages) & 1u);
+            if (active) {
+                float fc[3], fm[3], fp[3], am[3] = {0.f, 0.f, 0.f}, av[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+                for (int c = 0; c < 3; ++c) fc[c] = st.flow[c][ty + 1][tx + 4];
+                const Cell3 cell = gather_cell3(p.moving, D, H, W, flow_pos(p.ax, x, fc[2]), flow_pos(p.ay, y, fc[1]), flow_pos(p.az, z, fc[0]));
+                // z neighbours: inside an item the previous slice's centre is still in registers and the next one is the
+                // next stage's centre; at the item's ends they come from global memory / the neighbour rank's halo slice
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    if (i > 0) fm[c] = fprev[c];
+                    else if (zl > 0) fm[c] = __ldg(p.flow_in + c * slab + o - HW);
+                    else if (p.z_off > 0) fm[c] = __ldg(p.halo_lo + c * HW + xy);
+                    else fm[c] = fc[c];
+                    if (!last_of_item) fp[c] = nx.flow[c][ty + 1][tx + 4];
+                    else if (zl + 1 < Ds) fp[c] = __ldg(p.flow_in + c * slab + o + HW);
+                    else if (z + 1 < D) fp[c] = __ldg(p.halo_hi + c * HW + xy);
+                    else fp[c] = fc[c];
+                }
+                const float t = st.tgt[ty][tx];
+                const Sample<3> sp = blend_cell3<true>(cell);
+                const float val = sp.val;
+                const float r = fmaf(coef[0], val, fmaf(coef[1], t, coef[2]));
+                if (ADAM) {                                 // after the gathered cell is consumed: 11 registers fewer live
+#pragma unroll
+                    for (int c = 0; c < 3; ++c) { am[c] = __ldcs(p.adam_m + c * slab + o); av[c] = __ldcs(p.adam_v + c * slab + o); }
+                }
+                float nv[3], sm = 0.f;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    const float f = fc[c];
+                    const float dxm = (f - st.flow[c][ty + 1][tx + 3]) * mxm, dxp = (st.flow[c][ty + 1][tx + 5] - f) * mxp;
+                    const float dym = (f - st.flow[c][ty][tx + 4]) * mym, dyp = (st.flow[c][ty + 2][tx + 4] - f) * myp;
+                    const float dzp = fp[c] - f;
+                    float stn = p.ssm[0] * (dxm - dxp);
+                    stn = fmaf(p.ssm[1], dym - dyp, stn);
+                    stn = fmaf(p.ssm[2], (f - fm[c]) - dzp, stn);
+                    const float gr = fmaf(r, sp.g[2 - c], stn);             // channel c <-> sampling coordinate 2-c
+                    sm = fmaf(p.wsm[0] * dxp, dxp, sm);
+                    sm = fmaf(p.wsm[1] * dyp, dyp, sm);
+                    sm = fmaf(p.wsm[2] * dzp, dzp, sm);
+                    if (!ADAM) {
+                        nv[c] = f - p.lr * gr;
+                    } else {
+                        am[c] = fmaf(p.beta1, am[c], p.ob1 * gr);
+                        av[c] = fmaf(p.beta2, av[c], p.ob2 * gr * gr);
+                        nv[c] = fmaf(-p.step_size, __fdividef(am[c], fmaf(sqrt_approx(av[c]), p.inv_bc2s, p.eps)), f);
+                    }
+                }
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    __stcs(p.flow_out + c * slab + o, nv[c]);
+                    if (ADAM) { __stcs(p.adam_m + c * slab + o, am[c]); __stcs(p.adam_v + c * slab + o, av[c]); }
+                }
+                float wv = val;
+                if (NEXT) {
+                    const float qz = flow_pos(p.az, z, nv[0]), qy = flow_pos(p.ay, y, nv[1]), qx = flow_pos(p.ax, x, nv[2]);
+                    wv = sample_zero_pad<3, false>(p.moving, D, H, W, qx, qy, qz).val;
+                }
+                s[0] += t; s[1] += wv;
+                s[2] = fmaf(t, t, s[2]); s[3] = fmaf(wv, wv, s[3]); s[4] = fmaf(t, wv, s[4]);
+                s[5] += sm;
+#pragma unroll
+                for (int c = 0; c < 3; ++c) fprev[c] = fc[c];
+            }
+            ++consumed;
+            __syncthreads();                              // everybody is done with the stage just consumed
+            if (threadIdx.x == 0 && prod.nsl > 0) issue_one();
+        }
+        cons.item += stride;
+        cursor_load(cons, items, tiles_x, tiles_xy, zc, Ds);
+    }
+    // fp32 per thread, fp64 above; deterministic grid reduction (as in flow_direct_step_kernel)
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int i = 0; i < 6; ++i) {
+        const double v = warp_sum((double)s[i]);
+        if (lane == 0) red[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += red[w][threadIdx.x];
+        __stcg(p.partials + (size_t)blockIdx.x * 6 + threadIdx.x, v);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) is_last = (atomicAdd(p.ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp < 6) {
+        double v = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(p.partials + (size_t)b * 6 + warp);
+        v = warp_sum(v);
+        if (lane == 0) p.moments[warp] = v;
+    }
+    if (threadIdx.x == 0) *p.ticket = 0u;
+}
+
 __global__ void flow_direct_finish_kernel(const DirectParams p, const int next)
 {
     if (threadIdx.x == 0 && blockIdx.x == 0) direct_log_losses(p, p.moments, next != 0, false, (double *)p.ticket + 1);
@@ -521,6 +718,7 @@ extern "C" int trb_flow_direct_update(int ndim, const float *moving_dev, const f
 }
 
 namespace trb {
+static int g_step_no_tma = 0;        // trb_flow_direct_set_path: 1 = register-staged kernel for the smoothness variants too (A/B)
 template <bool NEXT, bool ADAM>
 static void launch_step(const DirectParams &p, bool smooth, unsigned grid, int tiles_x, int tiles_y, int zc, cudaStream_t s)
 {
@@ -537,6 +735,8 @@ static int step_occupancy()
     return o < 1 ? 1 : o;
 }
 }  // namespace trb
+
+extern "C" void trb_flow_direct_set_path(int no_tma) { trb::g_step_no_tma = no_tma ? 1 : 0; }
 
 extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
                                     const float *flow_in_slab_dev, float *flow_out_slab_dev,
@@ -594,6 +794,25 @@ extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target
     const long long items = (long long)tiles_x * tiles_y * ((p.Ds + zc - 1) / zc);
     const unsigned grid = (unsigned)(items < cap ? items : cap);
     cudaStream_t s = (cudaStream_t)stream;
+    // smoothness variants: flow + halo and target tiles staged by TMA (needs 16-byte row pitch and base alignment)
+    // (Adam + NCC is the one variant where the register-staged kernel measures 2 % faster: 64 registers are too few)
+    if (smooth && !(next && adam) && !g_step_no_tma && W % 4 == 0 && W >= kSX && H >= kSY && ((uintptr_t)flow_in_slab_dev & 15) == 0 && ((uintptr_t)target_slab_dev & 15) == 0) {
+        CUtensorMap map_flow, map_tgt;
+        const cuuint64_t fdims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.Ds, 3};
+        const cuuint64_t fstr[3] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4, (cuuint64_t)W * H * p.Ds * 4};
+        const cuuint32_t fbox[4] = {(cuuint32_t)kSX, (cuuint32_t)kSY, 1, 3};
+        const cuuint64_t tdims[4] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)p.Ds, 1};
+        const cuuint32_t tbox[4] = {(cuuint32_t)kTX, (cuuint32_t)kTY, 1, 1};
+        if (tma::make_map_f32(&map_flow, flow_in_slab_dev, fdims, fstr, fbox) && tma::make_map_f32(&map_tgt, target_slab_dev, tdims, fstr, tbox)) {
+            int occ_t = 4;
+            const unsigned tgrid = (unsigned)(items < (long long)sms * occ_t ? items : (long long)sms * occ_t);
+            if (next) { if (adam) flow_direct_step_tma_kernel<true, true><<<tgrid, 256, 0, s>>>(p, tiles_x, tiles_y, zc, map_flow, map_tgt);
+                        else flow_direct_step_tma_kernel<true, false><<<tgrid, 256, 0, s>>>(p, tiles_x, tiles_y, zc, map_flow, map_tgt); }
+            else { if (adam) flow_direct_step_tma_kernel<false, true><<<tgrid, 256, 0, s>>>(p, tiles_x, tiles_y, zc, map_flow, map_tgt);
+                   else flow_direct_step_tma_kernel<false, false><<<tgrid, 256, 0, s>>>(p, tiles_x, tiles_y, zc, map_flow, map_tgt); }
+            return check_cuda(cudaGetLastError(), "flow_direct_step(tma)");
+        }
+    }
     if (next) { if (adam) launch_step<true, true>(p, smooth, grid, tiles_x, tiles_y, zc, s); else launch_step<true, false>(p, smooth, grid, tiles_x, tiles_y, zc, s); }
     else { if (adam) launch_step<false, true>(p, smooth, grid, tiles_x, tiles_y, zc, s); else launch_step<false, false>(p, smooth, grid, tiles_x, tiles_y, zc, s); }
     return check_cuda(cudaGetLastError(), "flow_direct_step");
