@@ -160,3 +160,21 @@ def test_nmi_loss_matches_port():
         a.backward(); b.backward()
         assert abs(a.item() - b.item()) <= 1e-3 * abs(b.item()) + 1e-4
         assert (w1.grad - w2.grad).abs().max() <= 2e-3 * w2.grad.abs().max()
+
+
+def test_compose_theta_matches_chained_matrices():
+    """EXTENSION f-2: compose_theta(first, second) is the homogeneous product T_first @ T_second (2-D and 3-D, batched)."""
+    import torch
+    from torchregister_b200.warpings import compose_theta
+    g = torch.Generator().manual_seed(3)
+    for nd in (2, 3):
+        a = torch.eye(nd, nd + 1).repeat(4, 1, 1) + 0.1 * torch.randn(4, nd, nd + 1, generator=g)
+        b = torch.eye(nd, nd + 1).repeat(4, 1, 1) + 0.1 * torch.randn(4, nd, nd + 1, generator=g)
+        c = compose_theta(a, b)
+        assert tuple(c.shape) == (4, nd, nd + 1)
+        bottom = torch.zeros(4, 1, nd + 1); bottom[:, 0, nd] = 1
+        ha, hb = torch.cat([a, bottom], 1), torch.cat([b, bottom], 1)
+        assert torch.allclose(c, (ha @ hb)[:, :nd], atol=1e-6)
+        x = torch.randn(4, nd, 1, generator=g)
+        chained = a[:, :, :nd] @ (b[:, :, :nd] @ x + b[:, :, nd:]) + a[:, :, nd:]
+        assert torch.allclose(c[:, :, :nd] @ x + c[:, :, nd:], chained, atol=1e-5)

@@ -614,3 +614,24 @@ def test_register_batch_extension_and_dtype():
         one.optim(mov[i:i + 1], tgt[i:i + 1], lr=1e-3, max_epochs=5, reg0=p0[i])
         assert torch.allclose(one.theta[0], reg.theta[i], atol=2e-6)
         assert torch.allclose(one(mov[i:i + 1]), out[i:i + 1], atol=1e-5)
+
+
+def test_compose_theta_equals_two_warps_on_lattice_shifts():
+    """EXTENSION f-2: with whole-voxel translations both interpolations are exact, so the composed single warp must
+    reproduce warp(second, warp(first, m)) away from the zero-padded border; with a generic pair it stays within the
+    error of the second interpolation."""
+    import torchregister_b200 as tr
+    from torchregister_b200.synth import make_pair
+    shape = (24, 32, 40)
+    mov, _ = make_pair(shape, "rigid", device=DEV)
+    D, H, W = shape
+    first = torch.eye(3, 4, device=DEV).unsqueeze(0); first[0, 0, 3] = 2 * 2.0 / W; first[0, 2, 3] = -2 * 1.0 / D
+    second = torch.eye(3, 4, device=DEV).unsqueeze(0); second[0, 1, 3] = 2 * 3.0 / H; second[0, 0, 3] = -2 * 1.0 / W
+    two = tr.get_affine_warp(second, tr.get_affine_warp(first, mov))
+    one = tr.get_affine_warp(tr.compose_theta(first, second), mov)
+    assert (two - one)[:, :, 4:-4, 4:-4, 4:-4].abs().max().item() <= 2e-6
+    first = torch.tensor([[[1.01, 0.02, -0.01, 0.03], [-0.02, 0.99, 0.01, -0.02], [0.01, -0.01, 1.0, 0.01]]], device=DEV)
+    second = torch.tensor([[[0.99, -0.01, 0.02, -0.01], [0.01, 1.02, 0.0, 0.02], [0.0, 0.01, 0.98, 0.0]]], device=DEV)
+    two = tr.get_affine_warp(second, tr.get_affine_warp(first, mov))
+    one = tr.get_affine_warp(tr.compose_theta(first, second), mov)
+    assert (two - one)[:, :, 4:-4, 4:-4, 4:-4].abs().max().item() <= 2e-2

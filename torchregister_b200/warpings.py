@@ -52,6 +52,22 @@ def get_affine_warp(theta, moving):
     return _AffineWarpFn.apply(theta, moving)
 
 
+def compose_theta(first, second):
+    """EXTENSION (pipeline chaining): the single theta whose warp equals warping with `first` and
+    then warping the result with `second` — `get_affine_warp(second, get_affine_warp(first, m))` — up to the second
+    interpolation, which the composed form avoids (one resampling of the original image instead of two, no
+    intermediate volume).  A warp samples the input at x_in = A x_out + b in normalised coordinates, so the chain
+    samples `m` at A1 (A2 x + b2) + b1.  first, second: [N,nd,nd+1] (or anything reshapeable to it); returns [N,nd,nd+1]."""
+    if first.shape[-1] not in (3, 4, 6, 12):
+        raise ValueError("theta must end in 3 / 6 (2-D) or 4 / 12 (3-D) entries")
+    nd = 3 if first.shape[-1] in (4, 12) else 2
+    a = first.reshape(-1, nd, nd + 1).to(torch.float64)
+    b = second.reshape(-1, nd, nd + 1).to(torch.float64)
+    lin = a[:, :, :nd] @ b[:, :, :nd]
+    off = (a[:, :, :nd] @ b[:, :, nd:]) + a[:, :, nd:]
+    return torch.cat([lin, off], dim=2).to(first.dtype)
+
+
 # --------------------------------------------------------------------------- #
 # criterion bookkeeping
 # --------------------------------------------------------------------------- #
