@@ -505,7 +505,10 @@ __device__ void warp_publish_pair(const float (&acc)[TRB_MOMENTS], float *red /*
         for (int w = 0; w < kConsumerWarps; ++w) s += (double)red[w * kRedLd + v];
         __stcg(mine + v, s);
     }
-    if (p.use_groups) warp_arrive_group(p, pair, G, lane);
+    // the group arrival (fence + global ticket + possibly a 16-slot fold: 2-5 us of round trips) is NOT done here: the
+    // warp that does it would finish its next tile late, and a stage is only refilled when the slowest warp is through —
+    // measured as a 4-5 us bubble of the TMA ring after every pair switch.  The kernel arrives for all its pairs after
+    // the main loop.
 }
 
 // Run by the LAST CTA to complete its tiles (all 16 warps): per pair, add the group slots in index order
@@ -698,6 +701,7 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
 #pragma unroll
     for (int i = 0; i < TRB_MOMENTS; ++i) T[i] = 0.f;
     int n_flush = 0;
+    bool t_dirty = false;                       // T holds sums of earlier columns of the current pair
 
     int it = 0;
     while (cur.phase != 2) {
@@ -730,7 +734,14 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
         while (!col_done) {
             const int stage = it % NSTAGE;
             const unsigned phase = (unsigned)(it / NSTAGE) & 1u;
+#ifdef TRB_TIMING
+            const unsigned long long tw0 = gtime();
+#endif
             mbar_wait(full_bar + stage, phase);
+#ifdef TRB_TIMING
+            if (warp == 0 && lane == 0) { g_dbg[blockIdx.x * 16 + 7] += gtime() - tw0; g_dbg[blockIdx.x * 16 + 8] += 1ull; }
+            if (blockIdx.x == 5 && lane == 0 && (warp == 0 || warp == 15) && it < 1000) { g_dbg[4096 + it * 4 + (warp == 15 ? 2 : 0)] = tw0; g_dbg[4096 + it * 4 + (warp == 15 ? 3 : 1)] = gtime(); }
+#endif
             const TileMeta m = meta[stage];
             unsigned char *stg = smem_raw + (size_t)stage * L::kStageBytes;
             const uint32_t box_addr = smem_u32(stg);
@@ -811,32 +822,58 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
         }
 
         // ---- fold the column's sums with this thread's base coordinates (x, y constant over the column) --
+        // The totals live in local memory, and with 219 KB of the SM given to the TMA ring the L1 left over (~28 KB)
+        // cannot hold 512 x 164 B of them: every access is an L2 round trip.  `T[i] += v` on a volatile is load ->
+        // add -> store per element, 41 SERIALISED round trips (measured: 13 us per column, a quarter of a 24-tile
+        // column).  All loads first, then the arithmetic, then all stores: one round trip.
+        const bool pair_done = cur.phase == 2 || cur.cg / p.cols_per_pair != pair;
+        float acc[TRB_MOMENTS];
+        if (t_dirty) {
+#pragma unroll
+            for (int i = 0; i < TRB_MOMENTS; ++i) acc[i] = T[i];
+        } else {                                // first column of the pair in this CTA: nothing to load
+#pragma unroll
+            for (int i = 0; i < TRB_MOMENTS; ++i) acc[i] = 0.f;
+        }
         if (valid) {
 #pragma unroll
-            for (int i = 0; i < 5; ++i) T[i] += A.s[i].x + A.s[i].y;
+            for (int i = 0; i < 5; ++i) acc[i] += A.s[i].x + A.s[i].y;
 #pragma unroll
             for (int kk = 0; kk < 3; ++kk)
 #pragma unroll
                 for (int r = 0; r < 3; ++r) {
                     const float pp = A.P[kk][r].x + A.P[kk][r].y, qq = A.Q[kk][r].x + A.Q[kk][r].y;
                     const int bi = 5 + kk * 12 + r * 4;
-                    T[bi + 0] = fmaf(xv, pp, T[bi + 0]);
-                    T[bi + 1] = fmaf(yv, pp, T[bi + 1]);
-                    T[bi + 2] += fmaf(inv_d2, qq, zoff * pp);
-                    T[bi + 3] += pp;
+                    acc[bi + 0] = fmaf(xv, pp, acc[bi + 0]);
+                    acc[bi + 1] = fmaf(yv, pp, acc[bi + 1]);
+                    acc[bi + 2] += fmaf(inv_d2, qq, zoff * pp);
+                    acc[bi + 3] += pp;
                 }
         }
-        // ---- pair finished (for this CTA): hand its totals to the grid-level reduction ----------------
-        if (cur.phase == 2 || cur.cg / p.cols_per_pair != pair) {
-            float acc[TRB_MOMENTS];
+        if (!pair_done) {
 #pragma unroll
-            for (int i = 0; i < TRB_MOMENTS; ++i) { acc[i] = T[i]; T[i] = 0.f; }
+            for (int i = 0; i < TRB_MOMENTS; ++i) T[i] = acc[i];
+        }
+        t_dirty = !pair_done;
+        // ---- pair finished (for this CTA): hand its totals to the grid-level reduction ----------------
+        if (pair_done) {
             // a warp can be at most one flush ahead of the slowest warp of its CTA (the TMA ring holds fewer
             // tiles than a pair has), so two scratch buffers alternate safely
+#ifdef TRB_TIMING
+            const unsigned long long tp0 = gtime();
+#endif
             warp_publish_pair(acc, red[n_flush & 1], pair_cnt + (n_flush & 1), p, pair, G, warp, lane);
+#ifdef TRB_TIMING
+            if (warp == 0 && lane == 0) { g_dbg[blockIdx.x * 16 + 9] += gtime() - tp0; g_dbg[blockIdx.x * 16 + 10] += 1ull; }
+#endif
             ++n_flush;
         }
     }
+    // ---- deferred group arrivals of the pairs this CTA published (see warp_publish_pair) -----------
+    __syncthreads();                            // every slot of this CTA has been written
+    if (p.use_groups)
+        for (int pr = warp; pr < p.n_pairs; pr += kConsumerWarps)
+            if (touched[pr >> 5] & (1u << (pr & 31))) warp_arrive_group(p, pr, G, lane);
     TRB_T(1);
     // ---- the last CTA to get here finishes every pair ------------------------------------------------
     __shared__ int is_last_cta;
