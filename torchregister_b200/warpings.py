@@ -17,7 +17,7 @@ from . import functional as TF
 from .utils import Attention_UNet, NCCLoss, NMILoss
 
 __all__ = ["get_affine_warp", "affine_register", "rigid_register", "flow_register", "direct_flow_register",
-           "similarity_weights"]
+           "similarity_weights", "compose_theta"]
 
 
 # --------------------------------------------------------------------------- #
