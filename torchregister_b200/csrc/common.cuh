@@ -86,11 +86,17 @@ __device__ __forceinline__ float flow_pos(const AxisMap &m, int i, float f)
 // floor and fraction without the quarter-rate conversion pipe: adding 1.5*2^23 rounding down leaves floor(p) in the
 // low mantissa bits (exact for |p| < 2^22; anything further out — inf and NaN included — lands on an index no volume
 // reaches, i.e. on the zero padding).
-__device__ __forceinline__ void floor_frac(float p, int &i0, float &t)
+__device__ __forceinline__ void floor_frac(float p, int &i0, float &t, float &fl)
 {
     const float m = __fadd_rd(p, 12582912.f);
     i0 = __float_as_int(m) - 0x4B400000;
-    t = p - (m - 12582912.f);
+    fl = m - 12582912.f;
+    t = p - fl;
+}
+__device__ __forceinline__ void floor_frac(float p, int &i0, float &t)
+{
+    float fl;
+    floor_frac(p, i0, t, fl);
 }
 
 // cells that straddle the volume boundary (rare: kept out of line so the common path stays small)
@@ -122,6 +128,7 @@ struct Sample {
 struct Cell3 {
     float c[8];
     float tx, ty, tz;
+    float fx, fy, fz;       // floor of the position (the cell's origin), for sample_near
 };
 // BRANCH_FREE: predicated loads, no control flow — the compiler can overlap the gathers of neighbouring voxels and
 // phases (what latency-bound kernels want: warp_flow -22 %, fused direct-flow epoch -10 %); otherwise interior cells
@@ -131,9 +138,9 @@ __device__ __forceinline__ Cell3 gather_cell3(const float *__restrict__ m, int D
 {
     Cell3 k;
     int x0, y0, z0;
-    floor_frac(px, x0, k.tx);
-    floor_frac(py, y0, k.ty);
-    floor_frac(pz, z0, k.tz);
+    floor_frac(px, x0, k.tx, k.fx);
+    floor_frac(py, y0, k.ty, k.fy);
+    floor_frac(pz, z0, k.tz, k.fz);
     if constexpr (BRANCH_FREE) {
         const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
         const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
@@ -183,6 +190,11 @@ __device__ __forceinline__ Sample<3> blend_cell3(const Cell3 &k)
     return s;
 }
 
+// Value at a second position that usually lies in the cell already gathered (a gradient step moves a sample by a
+// fraction of a voxel): same corners, new fractions — bit-identical to a fresh gather, without its 8 loads.
+__device__ __forceinline__ float sample_near(const Cell3 &k, const float *__restrict__ m, int D, int H, int W,
+                                             float qx, float qy, float qz);
+
 // grid_sample(mode='bilinear', padding_mode='zeros') at voxel coordinates (px,py,pz).  Needs D*H*W < 2^31 (hosts check).
 template <int NDIM, bool WANT_GRAD, bool BRANCH_FREE = true>
 __device__ __forceinline__ Sample<NDIM> sample_zero_pad(const float *__restrict__ m, int D, int H, int W,
@@ -213,6 +225,18 @@ __device__ __forceinline__ Sample<NDIM> sample_zero_pad(const float *__restrict_
         }
         return s;
     }
+}
+
+__device__ __forceinline__ float sample_near(const Cell3 &k, const float *__restrict__ m, int D, int H, int W,
+                                             float qx, float qy, float qz)
+{
+    const float tx = qx - k.fx, ty = qy - k.fy, tz = qz - k.fz;
+    if (tx >= 0.f && tx < 1.f && ty >= 0.f && ty < 1.f && tz >= 0.f && tz < 1.f) {
+        Cell3 c2 = k;
+        c2.tx = tx; c2.ty = ty; c2.tz = tz;
+        return blend_cell3<false>(c2).val;
+    }
+    return sample_zero_pad<3, false>(m, D, H, W, qx, qy, qz).val;
 }
 
 // ---- similarity coefficients from the five global moments -------------------

@@ -389,7 +389,8 @@ __global__ void __launch_bounds__(256, TRB_STEP_MINB) flow_direct_step_kernel(co
                 float wv = val;
                 if (NEXT) {
                     const float qz = flow_pos(p.az, z, nv[0]), qy = flow_pos(p.ay, y, nv[1]), qx = flow_pos(p.ax, x, nv[2]);
-                    wv = sample_zero_pad<3, false>(p.moving, D, H, W, qx, qy, qz).val;
+                    // SGD: the step stays inside the gathered cell almost always; Adam has no registers to keep the cell (measured)
+                    wv = ADAM ? sample_zero_pad<3, false>(p.moving, D, H, W, qx, qy, qz).val : sample_near(cell, p.moving, D, H, W, qx, qy, qz);
                 }
                 s[0] += t; s[1] += wv;
                 s[2] = fmaf(t, t, s[2]); s[3] = fmaf(wv, wv, s[3]); s[4] = fmaf(t, wv, s[4]);
@@ -580,7 +581,8 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_tma_kernel(const Dire
                 float wv = val;
                 if (NEXT) {
                     const float qz = flow_pos(p.az, z, nv[0]), qy = flow_pos(p.ay, y, nv[1]), qx = flow_pos(p.ax, x, nv[2]);
-                    wv = sample_zero_pad<3, false>(p.moving, D, H, W, qx, qy, qz).val;
+                    // SGD: the step stays inside the gathered cell almost always; Adam has no registers to keep the cell (measured)
+                    wv = ADAM ? sample_zero_pad<3, false>(p.moving, D, H, W, qx, qy, qz).val : sample_near(cell, p.moving, D, H, W, qx, qy, qz);
                 }
                 s[0] += t; s[1] += wv;
                 s[2] = fmaf(t, t, s[2]); s[3] = fmaf(wv, wv, s[3]); s[4] = fmaf(t, wv, s[4]);
