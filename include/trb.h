@@ -231,6 +231,23 @@ int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
                          float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
                          void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* trb_flow_direct_step for ONE volume sharded into z-slabs over up to 8 GPUs of one box, with no NCCL call in the epoch:
+ * halo_lo/halo_hi point INTO the neighbour ranks' flow buffers (their last / first slice, mapped into this process;
+ * channel stride = the neighbour's Ds*H*W elements), and the last CTA all-reduces the 6 sums through the peer mailboxes
+ * of trb_affine_optim_peer, so moments6_dev holds the GLOBAL sums when the kernel ends.  That exchange also orders the
+ * epochs: a rank's flow buffer is only read by its neighbours after it is complete and only overwritten after they have
+ * read it (ping-pong buffers, every rank in the same phase).  seq >= 1, +1 per call, identical on every rank. */
+int trb_flow_direct_step_peer(const float *moving_dev, const float *target_slab_dev,
+                              const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                              const float *halo_lo_dev, long long halo_lo_channel_stride,
+                              const float *halo_hi_dev, long long halo_hi_channel_stride,
+                              int D, int H, int W, int z_off, int Ds,
+                              double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                              int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                              float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
+                              void *const *mailbox_ptrs, int rank, int world, unsigned long long seq,
+                              void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* A/B switch for the smoothness variants of trb_flow_direct_step: 0 (default) = TMA-staged tiles, 1 = register-staged. */
 void trb_flow_direct_set_path(int no_tma);
 

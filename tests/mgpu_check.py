@@ -43,11 +43,14 @@ def main():
     # rounding noise, see test_direct_flow_slabs_equal_whole_volume)
     whole = TF.DirectFlowProblem(mov, tgt, 4, flow0=(0.3 * smooth_flow(shape, 1.0)).to(dev), optimiser="sgd")
     whole.run(4, 0.5, 0.5, 0.5, 3.0)
-    sd = ShardedDirectFlow(mov, tgt, 4, optimiser="sgd")
-    sd.prob.flow.copy_((0.3 * smooth_flow(shape, 1.0)).to(dev)[:, :, sd.z0:sd.z1])
-    sd.run(4, 0.5, 0.5, 0.5, 3.0)
-    assert torch.allclose(sd.flow_slab, whole.flow[:, :, sd.z0:sd.z1], atol=2e-6), (sd.flow_slab - whole.flow[:, :, sd.z0:sd.z1]).abs().max()
-    assert torch.allclose(sd.losses, whole.losses, rtol=2e-5)
+    for peer in (False, None):          # NCCL halo exchange + all-reduce / neighbours' slices read in place + in-kernel all-reduce
+        sd = ShardedDirectFlow(mov, tgt, 4, optimiser="sgd", peer=peer)
+        sd.prob.flow.copy_((0.3 * smooth_flow(shape, 1.0)).to(dev)[:, :, sd.z0:sd.z1])
+        sd.run(1, 0.5, 0.5, 0.5, 3.0)
+        sd.run(3, 0.5, 0.5, 0.5, 3.0)
+        assert torch.allclose(sd.flow_slab, whole.flow[:, :, sd.z0:sd.z1], atol=2e-6), (peer, (sd.flow_slab - whole.flow[:, :, sd.z0:sd.z1]).abs().max())
+        assert torch.allclose(sd.losses, whole.losses, rtol=2e-5), (peer, sd.losses, whole.losses)
+        paths.append("flow: " + ("peer-memory" if sd.mailbox is not None else "nccl (%s)" % sd.peer_error))
 
     # (a) batch of independent pairs sharded by pair, no collective in the loop
     n_pairs = 5

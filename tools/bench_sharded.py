@@ -37,12 +37,16 @@ def main():
         return float(t.item())
 
     for opt, w, lam, bpv in (("sgd", (0.5, 0.5), 2.0, 32), ("adam", (0.5, 0.5), 2.0, 80), ("sgd", (1.0, 0.0), 0.0, 32)):
-        sd = ShardedDirectFlow(mov, tgt, 100000, optimiser=opt)
-        ms = timed(lambda n: sd.run(n, 0.05, w[0], w[1], lam))
-        out["direct_flow_%s_mse%g_ncc%g_smooth%g" % (opt, w[0], w[1], lam)] = {
-            "ms_per_epoch": ms, "voxel_warps_per_s": vox / (ms * 1e-3), "algorithmic_GBps_total": bpv * vox / (ms * 1e-3) / 1e9}
-        del sd
-        torch.cuda.empty_cache()
+        for tag, peer in (("", False), ("_fused_peer", None)):
+            if peer is None and world == 1:
+                continue
+            sd = ShardedDirectFlow(mov, tgt, 100000, optimiser=opt, peer=peer)
+            ms = timed(lambda n: sd.run(n, 0.05, w[0], w[1], lam))
+            out["direct_flow_%s_mse%g_ncc%g_smooth%g%s" % (opt, w[0], w[1], lam, tag)] = {
+                "ms_per_epoch": ms, "voxel_warps_per_s": vox / (ms * 1e-3), "algorithmic_GBps_total": bpv * vox / (ms * 1e-3) / 1e9,
+                "path": "peer-memory" if sd.mailbox is not None else "nccl"}
+            del sd
+            torch.cuda.empty_cache()
     ident = torch.eye(3, 4, device=dev).reshape(1, -1)
     for name, peer in (("affine_ncc_nccl_allreduce", False), ("affine_ncc_fused_peer_allreduce", None)):
         if peer is None and world == 1:

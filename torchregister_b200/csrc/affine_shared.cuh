@@ -5,6 +5,8 @@
 #include "common.cuh"
 #include <math.h>
 
+#include "peer.cuh"
+
 namespace trb {
 
 constexpr int kTicketStride = 128;  // unsigned counters per pair in the workspace (direct kernel uses [127])
@@ -13,16 +15,6 @@ constexpr int kMaxSlots = 1024;      // partial-sum slots per pair in the worksp
 struct AffineParams;
 bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs);
 int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int n_launch, cudaStream_t stream);
-
-// One volume sharded over GPUs, fused form: the last CTA of every rank's epoch kernel pushes its 41 partial moments
-// into every rank's mailbox over NVLink (peer stores), waits for the others' and adds them in rank order, so all
-// ranks run the identical epilogue — no NCCL call and no extra launch in the epoch.
-struct PeerExchange {
-    double *mailbox[8];            // mailbox[r]: rank r's buffer mapped into this process, [2 parities][8 ranks][48] doubles
-    int rank, world;               // world <= 1: off
-    unsigned long long seq;        // sequence number of this epoch's exchange (>= 1, identical on every rank)
-};
-constexpr int kMailSlot = 48;      // 41 moments, flag (u64) at [47]
 
 struct AffineParams {
     const float *moving, *target;

@@ -513,44 +513,6 @@ __device__ void warp_publish_pair(const float (&acc)[TRB_MOMENTS], float *red /*
 
 // Run by the LAST CTA to complete its tiles (all 16 warps): per pair, add the group slots in index order
 // and run the epilogue (FUSED) or publish the moments.  Pairs are spread over the warps.
-// All-reduce of one pair's 41 moments over the ranks through peer memory (see PeerExchange), executed by one warp.
-// Push model: remote stores are posted over NVLink, every rank polls its OWN memory.  Two parities of slots: a rank
-// can only be one epoch ahead of its slowest peer (it needs that peer's previous contribution to finish an epoch).
-// A peer that never shows up (bounded spin, ~seconds) poisons the moments with NaN instead of hanging the GPU.
-__device__ void peer_allreduce_moments(double *row, const PeerExchange &x, int lane)
-{
-    const unsigned long long seq = x.seq;
-    const size_t par = (size_t)(seq & 1ull) * 8 * kMailSlot;
-    for (int r = 0; r < x.world; ++r) {
-        volatile double *dst = x.mailbox[r] + par + (size_t)x.rank * kMailSlot;
-        for (int v = lane; v < TRB_MOMENTS; v += 32) dst[v] = row[v];
-    }
-    __threadfence_system();
-    __syncwarp();
-    if (lane < x.world) {
-        unsigned long long *flag = reinterpret_cast<unsigned long long *>(x.mailbox[lane] + par + (size_t)x.rank * kMailSlot + (kMailSlot - 1));
-        asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
-    }
-    double *mine = x.mailbox[x.rank] + par;
-    bool ok = true;
-    if (lane < x.world) {
-        const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(mine + (size_t)lane * kMailSlot + (kMailSlot - 1));
-        unsigned long long got = 0;
-        long long spins = 0;
-        do {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(flag) : "memory");
-        } while (got != seq && ++spins < (1ll << 23));
-        ok = got == seq;
-    }
-    ok = __all_sync(kFull, ok);
-    for (int v = lane; v < TRB_MOMENTS; v += 32) {
-        double t = 0.0;
-        for (int r = 0; r < x.world; ++r) t += reinterpret_cast<volatile const double *>(mine)[(size_t)r * kMailSlot + v];
-        row[v] = ok ? t : __longlong_as_double(0x7ff8000000000000ll);
-    }
-    __syncwarp();
-}
-
 template <bool FUSED>
 __device__ void final_phase(const TmaParams &p, double *fin_s /*[16][TRB_MOMENTS + 1] smem*/, int G, int warp, int lane)
 {
@@ -592,7 +554,7 @@ __device__ void final_phase(const TmaParams &p, double *fin_s /*[16][TRB_MOMENTS
         }
         __syncwarp();
         if (FUSED) {
-            if (p.a.peer.world > 1) peer_allreduce_moments(row, p.a.peer, lane);
+            if (p.a.peer.world > 1) peer_allreduce(row, TRB_MOMENTS, p.a.peer, lane);
             if (lane == 0) affine_epilogue<3>(row, p.a, warp);
         } else {
             for (int v = lane; v < TRB_MOMENTS; v += 32) p.a.moments_out[(size_t)warp * TRB_MOMENTS + v] = row[v];

@@ -15,6 +15,7 @@
 // volume; `moving` is the full [D][H][W] volume; halo_lo / halo_hi are the neighbour ranks' flow slices
 // z_off-1 and z_off+Ds ([ndim][H][W]) or NULL at the volume boundary.
 #include "common.cuh"
+#include "peer.cuh"
 #include "tma_utils.cuh"
 #include <math.h>
 
@@ -49,6 +50,10 @@ struct DirectParams {
     AxisMap ax, ay, az;
     float wsm[3], ssm[3];   // smoothness weights per axis (x, y, z) and 2*lambda*weight
     float step_size, inv_bc2s, ob1, ob2;
+    // sharded, fused: halo slices read in place from the neighbour ranks' flow buffers (channel stride = their Ds*H*W),
+    // the 6 sums all-reduced by the last CTA through peer mailboxes (peer.cuh)
+    int halo_lo_cs, halo_hi_cs;
+    PeerExchange peer;
 };
 
 // flow value of channel c at slab-local (zl, y, x) with zl in [-1, Ds] resolved through the halos
@@ -222,6 +227,9 @@ __global__ void __launch_bounds__(256) flow_direct_update_kernel(const DirectPar
 // workspace scalar meanwhile.  Algorithmic traffic: 32 B/voxel (SGD), 80 B/voxel (Adam).
 constexpr int kTX = 32, kTY = 8;
 
+// halo values may live in a neighbour GPU's memory and are rewritten every epoch: plain (coherent) load, not __ldg
+__device__ __forceinline__ float ld_halo(const float *p) { return *reinterpret_cast<const volatile float *>(p); }
+
 // MUFU.SQRT (2 ulp): the Adam denominator does not need the ~10-instruction IEEE sequence with its slow-path branch
 __device__ __forceinline__ float sqrt_approx(float v)
 {
@@ -305,7 +313,7 @@ __global__ void __launch_bounds__(256, TRB_STEP_MINB) flow_direct_step_kernel(co
                 fc[c] = ld_stream_f(p.flow_in + c * slab + zl0 * HW + xy);
                 if (SMOOTH) {
                     if (zl0 > 0) fm[c] = __ldg(p.flow_in + c * slab + (zl0 - 1) * HW + xy);
-                    else if (p.z_off > 0) fm[c] = __ldg(p.halo_lo + c * HW + xy);
+                    else if (p.z_off > 0) fm[c] = ld_halo(p.halo_lo + c * p.halo_lo_cs + xy);
                     else fm[c] = fc[c];
                 }
             }
@@ -331,7 +339,7 @@ __global__ void __launch_bounds__(256, TRB_STEP_MINB) flow_direct_step_kernel(co
                     }
                 } else if (SMOOTH) {
 #pragma unroll
-                    for (int c = 0; c < 3; ++c) fp[c] = (z + 1 < D) ? __ldg(p.halo_hi + c * HW + xy) : fc[c];
+                    for (int c = 0; c < 3; ++c) fp[c] = (z + 1 < D) ? ld_halo(p.halo_hi + c * p.halo_hi_cs + xy) : fc[c];
                 }
             }
             Cell3 cell;
@@ -424,9 +432,17 @@ __global__ void __launch_bounds__(256, TRB_STEP_MINB) flow_direct_step_kernel(co
         double v = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(p.partials + (size_t)b * 6 + warp);
         v = warp_sum(v);
-        if (lane == 0) p.moments[warp] = v;
+        if (lane == 0) { p.moments[warp] = v; red[0][warp] = v; }
     }
     if (threadIdx.x == 0) *p.ticket = 0u;
+    if (p.peer.world > 1) {                     // sharded: every rank leaves the kernel with the global sums
+        __syncthreads();
+        if (warp == 0) {
+            __threadfence_system();             // this rank's flow_out is complete before its sums reach the peers
+            peer_allreduce(&red[0][0], 6, p.peer, lane);
+            if (lane < 6) p.moments[lane] = red[0][lane];
+        }
+    }
 }
 
 // ---- the same epoch with the flow and target tiles staged by TMA (smoothness variants) ---------------------------
@@ -536,11 +552,11 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_tma_kernel(const Dire
                 for (int c = 0; c < 3; ++c) {
                     if (i > 0) fm[c] = fprev[c];
                     else if (zl > 0) fm[c] = __ldg(p.flow_in + c * slab + o - HW);
-                    else if (p.z_off > 0) fm[c] = __ldg(p.halo_lo + c * HW + xy);
+                    else if (p.z_off > 0) fm[c] = ld_halo(p.halo_lo + c * p.halo_lo_cs + xy);
                     else fm[c] = fc[c];
                     if (!last_of_item) fp[c] = nx.flow[c][ty + 1][tx + 4];
                     else if (zl + 1 < Ds) fp[c] = __ldg(p.flow_in + c * slab + o + HW);
-                    else if (z + 1 < D) fp[c] = __ldg(p.halo_hi + c * HW + xy);
+                    else if (z + 1 < D) fp[c] = ld_halo(p.halo_hi + c * p.halo_hi_cs + xy);
                     else fp[c] = fc[c];
                 }
                 const float t = st.tgt[ty][tx];
@@ -621,9 +637,17 @@ __global__ void __launch_bounds__(256, 4) flow_direct_step_tma_kernel(const Dire
         double v = 0.0;
         for (int b = lane; b < (int)gridDim.x; b += 32) v += __ldcg(p.partials + (size_t)b * 6 + warp);
         v = warp_sum(v);
-        if (lane == 0) p.moments[warp] = v;
+        if (lane == 0) { p.moments[warp] = v; red[0][warp] = v; }
     }
     if (threadIdx.x == 0) *p.ticket = 0u;
+    if (p.peer.world > 1) {                     // sharded: every rank leaves the kernel with the global sums
+        __syncthreads();
+        if (warp == 0) {
+            __threadfence_system();             // this rank's flow_out is complete before its sums reach the peers
+            peer_allreduce(&red[0][0], 6, p.peer, lane);
+            if (lane < 6) p.moments[lane] = red[0][lane];
+        }
+    }
 }
 
 __global__ void flow_direct_finish_kernel(const DirectParams p, const int next)
@@ -740,13 +764,14 @@ static int step_occupancy()
 
 extern "C" void trb_flow_direct_set_path(int no_tma) { trb::g_step_no_tma = no_tma ? 1 : 0; }
 
-extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
+static int flow_direct_step_impl(const float *moving_dev, const float *target_slab_dev,
                                     const float *flow_in_slab_dev, float *flow_out_slab_dev,
                                     const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
                                     double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
                                     int optimiser, float beta1, float beta2, float adam_eps, int step_index,
                                     float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
-                                    void *workspace_dev, size_t workspace_bytes, void *stream)
+                                    void *workspace_dev, size_t workspace_bytes, void *stream,
+                                    long long halo_lo_cs, long long halo_hi_cs, const PeerExchange *peer)
 {
     DirectParams p{};
     int rc = fill_direct(p, 3, moving_dev, target_slab_dev, flow_in_slab_dev, halo_lo_dev, halo_hi_dev, D, H, W, z_off, Ds,
@@ -765,6 +790,9 @@ extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target
     p.optimiser = optimiser; p.beta1 = beta1; p.beta2 = beta2; p.eps = adam_eps; p.step = step_index;
     p.adam_m = adam_m_dev; p.adam_v = adam_v_dev; p.loss_log = loss_log_dev; p.epoch = epoch;
     p.complete_prev = complete_prev;
+    p.halo_lo_cs = (int)(halo_lo_cs > 0 ? halo_lo_cs : (long long)H * W);
+    p.halo_hi_cs = (int)(halo_hi_cs > 0 ? halo_hi_cs : (long long)H * W);
+    if (peer) p.peer = *peer;
     p.ax.d = (float)(W - 1); p.ay.d = (float)(H - 1); p.az.d = (float)(D - 1);
     p.ax.r = 1.f / p.ax.d; p.ay.r = 1.f / p.ay.d; p.az.r = 1.f / p.az.d;       // IEEE: what __frcp_rn gives on the device
     const double dims[3] = {(double)W, (double)H, (double)D};
@@ -818,6 +846,45 @@ extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target
     if (next) { if (adam) launch_step<true, true>(p, smooth, grid, tiles_x, tiles_y, zc, s); else launch_step<true, false>(p, smooth, grid, tiles_x, tiles_y, zc, s); }
     else { if (adam) launch_step<false, true>(p, smooth, grid, tiles_x, tiles_y, zc, s); else launch_step<false, false>(p, smooth, grid, tiles_x, tiles_y, zc, s); }
     return check_cuda(cudaGetLastError(), "flow_direct_step");
+}
+
+extern "C" int trb_flow_direct_step(const float *moving_dev, const float *target_slab_dev,
+                                    const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                                    const float *halo_lo_dev, const float *halo_hi_dev, int D, int H, int W, int z_off, int Ds,
+                                    double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                                    int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                                    float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
+                                    void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    return flow_direct_step_impl(moving_dev, target_slab_dev, flow_in_slab_dev, flow_out_slab_dev, halo_lo_dev, halo_hi_dev,
+                                 D, H, W, z_off, Ds, moments6_dev, w_mse, w_ncc, smooth_lambda, lr, optimiser, beta1, beta2,
+                                 adam_eps, step_index, adam_m_dev, adam_v_dev, loss_log_dev, epoch, complete_prev,
+                                 workspace_dev, workspace_bytes, stream, 0, 0, nullptr);
+}
+
+extern "C" int trb_flow_direct_step_peer(const float *moving_dev, const float *target_slab_dev,
+                                         const float *flow_in_slab_dev, float *flow_out_slab_dev,
+                                         const float *halo_lo_dev, long long halo_lo_channel_stride,
+                                         const float *halo_hi_dev, long long halo_hi_channel_stride,
+                                         int D, int H, int W, int z_off, int Ds,
+                                         double *moments6_dev, float w_mse, float w_ncc, float smooth_lambda, float lr,
+                                         int optimiser, float beta1, float beta2, float adam_eps, int step_index,
+                                         float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, int complete_prev,
+                                         void *const *mailbox_ptrs, int rank, int world, unsigned long long seq,
+                                         void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    if (world < 1 || world > 8 || rank < 0 || rank >= world || !mailbox_ptrs || seq < 1) { set_error("bad peer set (world 1..8, seq >= 1)"); return TRB_ERR_ARG; }
+    if (halo_lo_channel_stride >= (1ll << 31) || halo_hi_channel_stride >= (1ll << 31)) { set_error("halo channel stride too large"); return TRB_ERR_ARG; }
+    PeerExchange px{};
+    for (int r = 0; r < world; ++r) {
+        if (!mailbox_ptrs[r]) { set_error("null mailbox pointer for rank %d", r); return TRB_ERR_ARG; }
+        px.mailbox[r] = (double *)mailbox_ptrs[r];
+    }
+    px.rank = rank; px.world = world; px.seq = seq;
+    return flow_direct_step_impl(moving_dev, target_slab_dev, flow_in_slab_dev, flow_out_slab_dev, halo_lo_dev, halo_hi_dev,
+                                 D, H, W, z_off, Ds, moments6_dev, w_mse, w_ncc, smooth_lambda, lr, optimiser, beta1, beta2,
+                                 adam_eps, step_index, adam_m_dev, adam_v_dev, loss_log_dev, epoch, complete_prev,
+                                 workspace_dev, workspace_bytes, stream, halo_lo_channel_stride, halo_hi_channel_stride, &px);
 }
 
 extern "C" int trb_flow_direct_finish(const double *moments6_dev, int D, int H, int W, float w_mse, float w_ncc,

@@ -376,7 +376,7 @@ class DirectFlowProblem:
     full volume.  One epoch = stats pass -> (all-reduce hook) -> update pass, ping-ponging two flow buffers.
     """
 
-    def __init__(self, moving, target_slab, max_epochs, z_off=0, flow0=None, optimiser="sgd"):
+    def __init__(self, moving, target_slab, max_epochs, z_off=0, flow0=None, optimiser="sgd", flow_buffers=None):
         require_cuda(moving, "moving")
         require_cuda(target_slab, "target")
         self.lib = _lib.load()
@@ -391,11 +391,20 @@ class DirectFlowProblem:
         if tuple(target_slab.shape[-2:]) != (self.H, self.W):
             raise ValueError("target slab must share H, W with moving")
         shape = (1, self.ndim) + tuple(self.target.shape[2:])
-        self.flow = (torch.zeros(shape, dtype=torch.float32, device=self.device) if flow0 is None
-                     else flow0.detach().to(self.device, torch.float32).contiguous().clone())
-        if tuple(self.flow.shape) != shape:
-            raise ValueError("flow0 must have shape %s" % (shape,))
-        self._other = torch.empty_like(self.flow)
+        if flow_buffers is not None:
+            # caller-owned ping-pong buffers (parallel.ShardedDirectFlow puts them in symmetric memory so the neighbour
+            # ranks can read the boundary slices in place)
+            self.flow, self._other = (b.view(shape) for b in flow_buffers)
+            if flow0 is None:
+                self.flow.zero_()
+            else:
+                self.flow.copy_(flow0.detach().to(self.device, torch.float32))
+        else:
+            self.flow = (torch.zeros(shape, dtype=torch.float32, device=self.device) if flow0 is None
+                         else flow0.detach().to(self.device, torch.float32).contiguous().clone())
+            if tuple(self.flow.shape) != shape:
+                raise ValueError("flow0 must have shape %s" % (shape,))
+            self._other = torch.empty_like(self.flow)
         self.optimiser = optimiser
         self.adam_m = torch.zeros_like(self.flow) if optimiser == "adam" else None
         self.adam_v = torch.zeros_like(self.flow) if optimiser == "adam" else None
@@ -449,6 +458,26 @@ class DirectFlowProblem:
                 float(w_mse), float(w_ncc), float(smooth), float(lr), OPT[self.optimiser], float(betas[0]), float(betas[1]),
                 float(eps), self.epoch + 1, _ptr(self.adam_m), _ptr(self.adam_v), self.loss_log.data_ptr(), self.epoch,
                 int(self._pending), self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "flow_direct_step")
+        self.flow, self._other = self._other, self.flow
+        self.epoch += 1
+        self._pending = True
+
+    def step_peer(self, lr, w_mse, w_ncc, smooth, halo_lo_ptr, halo_lo_cs, halo_hi_ptr, halo_hi_cs, mailbox_ptrs, rank, world, seq,
+                  betas=(0.9, 0.999), eps=1e-8):
+        """One fused epoch of a z-slab with the neighbours' boundary slices read in place (raw device pointers into their
+        flow buffers) and the 6 sums all-reduced inside the kernel (include/trb.h: trb_flow_direct_step_peer)."""
+        if self.epoch >= self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        import ctypes
+        arr = (ctypes.c_void_p * world)(*[int(v) for v in mailbox_ptrs])
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_flow_direct_step_peer(
+                self.moving.data_ptr(), self.target.data_ptr(), self.flow.data_ptr(), self._other.data_ptr(),
+                halo_lo_ptr, int(halo_lo_cs), halo_hi_ptr, int(halo_hi_cs), self.D, self.H, self.W, self.z_off, self.Ds,
+                self.moments.data_ptr(), float(w_mse), float(w_ncc), float(smooth), float(lr), OPT[self.optimiser],
+                float(betas[0]), float(betas[1]), float(eps), self.epoch + 1, _ptr(self.adam_m), _ptr(self.adam_v),
+                self.loss_log.data_ptr(), self.epoch, int(self._pending), arr, int(rank), int(world), int(seq),
+                self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "flow_direct_step_peer")
         self.flow, self._other = self._other, self.flow
         self.epoch += 1
         self._pending = True

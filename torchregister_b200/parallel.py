@@ -125,17 +125,49 @@ class ShardedDirectFlow:
     replicated.  Per epoch: exchange ONE boundary slice of the flow with each neighbour (the smoothness stencil
     and nothing else crosses slabs), stats pass, all-reduce of the 6 loss moments, update pass."""
 
-    def __init__(self, moving, target, max_epochs, optimiser="sgd", group=None):
+    def __init__(self, moving, target, max_epochs, optimiser="sgd", group=None, peer=None):
         from . import functional as TF
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         D = int(moving.shape[2])
         self.z0, self.z1 = slab_range(D, self.world, self.rank)
+        dev = moving.device
+        nd = moving.dim() - 2
+        H, W = int(moving.shape[-2]), int(moving.shape[-1])
+        # Fused form (default when the box offers symmetric memory): the ping-pong flow buffers of every rank are mapped
+        # into every process, so a rank reads its neighbours' boundary slices in place and the epoch kernel all-reduces
+        # its 6 sums through the peer mailboxes — ONE kernel per epoch, no NCCL call.  Otherwise: halo slices by
+        # batch_isend_irecv, fused kernel, NCCL all-reduce.
+        self.mailbox, self.peer_error, self._peer_flow = None, None, None
+        buffers = None
+        if peer is not False and self.world > 1 and nd == 3:
+            ok = 1
+            try:
+                import torch.distributed._symmetric_memory as symm_mem
+                grp = group if group is not None else dist.group.WORLD
+                counts = [3 * (slab_range(D, self.world, r)[1] - slab_range(D, self.world, r)[0]) * H * W for r in range(self.world)]
+                n = max(counts)                                        # symmetric allocations have one size on all ranks
+                bufs = [symm_mem.empty(n, dtype=torch.float32, device=dev) for _ in range(2)]
+                hdls = [symm_mem.rendezvous(b, grp) for b in bufs]
+                self._peer_flow = [[int(p) for p in h.buffer_ptrs] for h in hdls]
+                self._peer_keep = (bufs, hdls)
+                mine = 3 * (self.z1 - self.z0) * H * W
+                buffers = [b[:mine] for b in bufs]
+                self.mailbox = PeerMailbox(dev, group)
+            except Exception as e:
+                ok, self.peer_error = 0, repr(e)
+            flag = torch.tensor([ok], device=dev, dtype=torch.int32)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # all ranks take the same path
+            if int(flag.item()) == 0:
+                self.mailbox, buffers = None, None
+                if peer is True:
+                    raise RuntimeError("fused sharded flow unavailable: %s" % (self.peer_error or "another rank declined"))
         self.prob = TF.DirectFlowProblem(moving, target[:, :, self.z0:self.z1].contiguous(), max_epochs,
-                                         z_off=self.z0, optimiser=optimiser)
-        nd, H, W = self.prob.ndim, self.prob.H, self.prob.W
-        dev = self.prob.device
+                                         z_off=self.z0, optimiser=optimiser, flow_buffers=buffers)
+        self._hw = H * W
+        self._ds = [slab_range(D, self.world, r)[1] - slab_range(D, self.world, r)[0] for r in range(self.world)]
+        self._phase = 0                                                 # which of the two symmetric buffers is `flow`
         self.halo_lo = torch.zeros(nd, H, W, device=dev) if self.rank > 0 else None
         self.halo_hi = torch.zeros(nd, H, W, device=dev) if self.rank < self.world - 1 else None
 
@@ -151,7 +183,31 @@ class ShardedDirectFlow:
         for req in dist.batch_isend_irecv(ops):
             req.wait()
 
+    def _peer_halos(self):
+        """Raw pointers to the neighbours' boundary slices inside their CURRENT flow buffer, and their channel strides."""
+        cur = self._peer_flow[self._phase]
+        lo = hi = None
+        lo_cs = hi_cs = 0
+        if self.rank > 0:
+            ds = self._ds[self.rank - 1]
+            lo, lo_cs = cur[self.rank - 1] + 4 * (ds - 1) * self._hw, ds * self._hw      # its last slice, channel 0
+        if self.rank < self.world - 1:
+            hi, hi_cs = cur[self.rank + 1], self._ds[self.rank + 1] * self._hw            # its first slice
+        return lo, lo_cs, hi, hi_cs
+
     def run(self, n_epochs, lr, w_mse, w_ncc, smooth=0.0, betas=(0.9, 0.999), eps=1e-8):
+        if self.mailbox is not None and n_epochs > 0:
+            if self.prob.prime(w_ncc):
+                allreduce_moments(self.prob.moments, self.group)
+            torch.cuda.current_stream(self.prob.device).synchronize()
+            dist.barrier(self.group)            # every rank's current flow is in place before a neighbour reads it
+            for _ in range(n_epochs):
+                lo, lo_cs, hi, hi_cs = self._peer_halos()
+                self.prob.step_peer(lr, w_mse, w_ncc, smooth, lo, lo_cs, hi, hi_cs, self.mailbox.ptrs, self.rank, self.world,
+                                    self.mailbox.take(1), betas, eps)
+                self._phase ^= 1
+            self.prob.finish(w_mse, w_ncc, smooth)
+            return
         if self.prob.fused and n_epochs > 0:
             # one kernel + one 6-value all-reduce (+ one halo slice each way) per epoch
             if self.prob.prime(w_ncc):
