@@ -116,7 +116,7 @@ int trb_affine_optim(int ndim, int mode,
  * all-reduce -> trb_affine_apply triple): n_epochs launches of the epoch kernel on slices [s_begin, s_end); the last
  * CTA of every rank pushes its 41 partial moments into every rank's mailbox with peer stores over NVLink, waits for
  * the others' (bounded spin: a missing peer yields NaN losses, not a hang), adds them in rank order and runs the
- * epilogue, so every rank applies the identical update.  mailbox_ptrs[r] = rank r's mailbox (2*8*48 doubles, zeroed
+ * epilogue, so every rank applies the identical update.  mailbox_ptrs[r] = rank r's mailbox (2*8*48+8 doubles, zeroed
  * once) as mapped into THIS process (CUDA IPC / symmetric memory; peer access enabled).  Every rank must make the
  * same calls with the same seq0 (>= 1, advance it by n_epochs per call).  3-D, shapes the TMA kernel accepts. */
 int trb_affine_optim_peer(const float *moving_dev, const float *target_dev, int D, int H, int W, int s_begin, int s_end,

@@ -637,3 +637,22 @@ def test_compose_theta_equals_two_warps_on_lattice_shifts():
     diff = (two - one)[:, :, 4:-4, 4:-4, 4:-4].abs()
     # the chained form interpolates twice (blurs): the two agree to the interpolation error of a ~2-voxel-wide feature
     assert diff.mean().item() <= 5e-3 and diff.max().item() <= 0.1, (diff.mean().item(), diff.max().item())
+
+
+def test_peer_exchange_times_out_instead_of_hanging():
+    """trb_affine_optim_peer with a peer that never shows up (its mailbox is a local buffer nobody writes): the bounded
+    spin gives NaN losses after a few seconds, and the poison word makes every later epoch give up at once."""
+    import time
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    mov, tgt = (t.to(DEV) for t in make_pair((32, 32, 64), "rigid"))
+    prob = TF.AffineProblem(mov, tgt, "affine", torch.eye(3, 4, device=DEV).reshape(1, -1), 6)
+    mine = torch.zeros(2 * 8 * 48 + 8, dtype=torch.float64, device=DEV)
+    ghost = torch.zeros_like(mine)
+    t0 = time.perf_counter()
+    prob.run_peer(6, 0, 16, [mine.data_ptr(), ghost.data_ptr()], 0, 2, 1, 1e-5, 0.5, 0.5)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    assert torch.isnan(prob.losses).all(), prob.losses
+    assert dt < 30.0, dt
+    assert mine[2 * 8 * 48:].view(torch.int64)[0].item() == 1          # poisoned

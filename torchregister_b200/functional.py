@@ -142,7 +142,7 @@ class AffineProblem:
     # -- sharded (z-slab) form, fused: the epoch kernel all-reduces the moments itself through peer memory
     def run_peer(self, n_epochs: int, s_begin: int, s_end: int, mailbox_ptrs, rank: int, world: int, seq0: int,
                  lr: float, w_mse: float, w_ncc: float, optimiser: str = "sgd", betas=(0.9, 0.999), eps: float = 1e-8) -> None:
-        """`mailbox_ptrs[r]`: rank r's mailbox (2*8*48 float64, zeroed) as mapped into this process.  Every rank makes
+        """`mailbox_ptrs[r]`: rank r's mailbox (2*8*48+8 float64, zeroed) as mapped into this process.  Every rank makes
         the same calls; `seq0` >= 1 advances by n_epochs per call (parallel.PeerMailbox keeps it).  n_epochs == 0 only
         validates (raises if this shape / slab cannot take the fused path)."""
         if n_epochs < 0:

@@ -40,10 +40,10 @@ def allreduce_moments(moments: torch.Tensor, group=None) -> torch.Tensor:
 
 class PeerMailbox:
     """Peer-mapped mailbox for the fused all-reduce of the sharded affine epoch (include/trb.h: trb_affine_optim_peer).
-    Every rank allocates 2*8*48 float64 in symmetric memory (torch.distributed._symmetric_memory: the buffer of every
+    Every rank allocates 2*8*48+8 float64 in symmetric memory (torch.distributed._symmetric_memory: the buffer of every
     rank is mapped into every process, peer access over NVLink); `ptrs[r]` is rank r's buffer in this process."""
 
-    DOUBLES = 2 * 8 * 48
+    DOUBLES = 2 * 8 * 48 + 8             # slots + the poison word (csrc/peer.cuh)
 
     def __init__(self, device, group=None):
         import torch.distributed._symmetric_memory as symm_mem
