@@ -271,7 +271,7 @@ def main():
     _, _ = e2e_step(fetch(), False)                  # warm-up
     torch.cuda.synchronize(dev)
     barrier()
-    n_e2e = 3
+    n_e2e = 5
     t0 = time.perf_counter()
     cur = fetch()
     for i in range(n_e2e):
