@@ -636,11 +636,12 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
         }
     }
     __syncthreads();
+    // zero slots of the untouched pairs: plain stores now, their group arrivals with everybody else's after the main
+    // loop (an arrival is a fence + a global atomic: ~1.5 us that used to sit in front of the first TMA issue)
     for (int pr = warp; pr < p.n_pairs; pr += kConsumerWarps) {
         if (touched[pr >> 5] & (1u << (pr & 31))) continue;
         double *mine = slot_ptr(p, pr, b);
         for (int v = lane; v < TRB_MOMENTS; v += 32) __stcg(mine + v, 0.0);
-        if (p.use_groups) warp_arrive_group(p, pr, G, lane);
     }
     __shared__ ColConst colc[kConsumerWarps];   // each warp's copy of the footprint constants of `ahead`'s column
     if (threadIdx.x == 0) {                     // prologue: fill the ring
@@ -834,8 +835,7 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
     // ---- deferred group arrivals of the pairs this CTA published (see warp_publish_pair) -----------
     __syncthreads();                            // every slot of this CTA has been written
     if (p.use_groups)
-        for (int pr = warp; pr < p.n_pairs; pr += kConsumerWarps)
-            if (touched[pr >> 5] & (1u << (pr & 31))) warp_arrive_group(p, pr, G, lane);
+        for (int pr = warp; pr < p.n_pairs; pr += kConsumerWarps) warp_arrive_group(p, pr, G, lane);   // touched or zero
     TRB_T(1);
     // ---- the last CTA to get here finishes every pair ------------------------------------------------
     __shared__ int is_last_cta;
