@@ -719,8 +719,6 @@ extern "C" int trb_flow_direct_update(int ndim, const float *moving_dev, const f
                                       float *adam_m_dev, float *adam_v_dev, float *loss_log_dev, int epoch, void *stream)
 {
     DirectParams p{};
-    double dummy_ws[1];
-    (void)dummy_ws;
     if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3"); return TRB_ERR_ARG; }
     if (!moving_dev || !target_slab_dev || !flow_in_slab_dev || !flow_out_slab_dev || !moments6_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
     if (flow_in_slab_dev == flow_out_slab_dev) { set_error("update is out of place: flow_out must differ from flow_in"); return TRB_ERR_ARG; }
