@@ -541,6 +541,30 @@ def test_nmi_kernels_vs_torch_restatement(shape, scale):
     assert none is None and loss3.item() == loss
 
 
+@pytest.mark.parametrize("shape,scale", [((64, 48), 1.0), ((256, 256), 255.0), ((300, 180), 40.0)])
+def test_nmi_kernels_vs_cpu_oracle(shape, scale):
+    """The same kernels against oracle/torch_port.nmi_loss — the line-by-line restatement of utils.py:18-79,224-259 that
+    the golden run `rigid2d_default` of the unmodified reference pins — evaluated on the CPU in fp64 with autograd (whose
+    nearest-resample backward is the exact adjoint).  2-D: the oracle materialises [4, 1e4, 256] tensors."""
+    TF = _tf()
+    from oracle import torch_port as tp
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair(shape, "rigid")
+    y, yp = (tgt * scale).contiguous(), (mov * scale).contiguous()
+    w64 = yp.double().clone().requires_grad_(True)
+    ref = tp.nmi_loss(y.double(), w64)
+    (g64,) = torch.autograd.grad(ref, w64)
+    w32 = yp.clone().requires_grad_(True)
+    ref32 = tp.nmi_loss(y, w32)
+    (g32,) = torch.autograd.grad(ref32, w32)
+    loss, g = TF.NmiTerm(y.to(DEV)).loss_grad(yp.to(DEV), 1.0)
+    assert abs(loss.item() - ref.item()) <= max(1e-4 * abs(ref.item()), 2 * abs(ref32.item() - ref.item())), (loss.item(), ref.item(), ref32.item())
+    gmax = g64.abs().max().item()
+    err = (g.cpu().double() - g64).abs().max().item()
+    err32 = (g32.double() - g64).abs().max().item()
+    assert err <= max(1e-4 * gmax, 2 * err32), (err, err32, gmax)
+
+
 def test_nmi_module_uses_kernels_and_is_differentiable():
     """utils.NMILoss on one fp32 CUDA pair runs csrc/nmi.cu through an autograd node (flow mode's `other` criteria and
     user code reach it this way); batches fall back to the PyTorch restatement."""
