@@ -214,9 +214,10 @@ class AffineProblem:
         return self.loss_log[:, : self.epoch]
 
 
-def warp_affine(theta: torch.Tensor, moving: torch.Tensor) -> torch.Tensor:
+def warp_affine(theta: torch.Tensor, moving: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """out[0, c] = grid_sample(moving[0, c], affine_grid(theta)), align_corners=False,
-    zeros padding (reference get_affine_warp, warpings.py:18-26).  theta: 12|6 values."""
+    zeros padding (reference get_affine_warp, warpings.py:18-26).  theta: 12|6 values.
+    `out`: optional contiguous fp32 destination of moving's shape (e.g. one pair's slice of a batch result)."""
     require_cuda(moving, "moving")
     ndim, D, H, W = _vol_dims(moving)
     if moving.shape[0] != 1:
@@ -227,7 +228,10 @@ def warp_affine(theta: torch.Tensor, moving: torch.Tensor) -> torch.Tensor:
     if th.numel() != ndim * (ndim + 1):
         raise ValueError("theta has %d values, expected %d" % (th.numel(), ndim * (ndim + 1)))
     src = moving.detach().contiguous()
-    out = torch.empty_like(src)
+    if out is None:
+        out = torch.empty_like(src)
+    elif out.shape != src.shape or out.dtype != torch.float32 or not out.is_contiguous() or out.device != dev:
+        raise ValueError("out must be a contiguous fp32 tensor of moving's shape on moving's device")
     xb, yb = base_coords(W, dev), base_coords(H, dev)
     zb = base_coords(D, dev) if ndim == 3 else None
     with torch.cuda.device(dev):

@@ -48,6 +48,13 @@ def get_affine_warp(theta, moving):
     if moving.shape[0] > 1:
         nd = moving.dim() - 2
         th = theta.reshape(moving.shape[0], nd, nd + 1)
+        if not (torch.is_grad_enabled() and th.requires_grad):
+            # plain forward (Register.__call__ on a batch): every pair's kernel writes straight into its slice
+            src = moving.detach().contiguous().float()
+            out = torch.empty_like(src)
+            for i in range(src.shape[0]):
+                TF.warp_affine(th[i], src[i:i + 1], out=out[i:i + 1])
+            return out
         return torch.cat([_AffineWarpFn.apply(th[i:i + 1], moving[i:i + 1]) for i in range(moving.shape[0])], dim=0)
     return _AffineWarpFn.apply(theta, moving)
 
