@@ -72,9 +72,9 @@ const char *trb_last_error(void);
 /* number of SMs of the current device (grid sizing); <0 on error */
 int trb_sm_count(void);
 
-/* Kernel selection for the 3-D rigid/affine epoch: 0 = automatic (TMA-staged kernel whenever the
- * shape/alignment allows, direct-gather kernel otherwise), 1 = always the direct-gather kernel.
- * Process-wide; meant for tests and A/B timing. */
+/* Kernel selection for the 3-D rigid/affine epoch: 0 = automatic (persistent multi-epoch TMA-staged kernel whenever
+ * the shape/alignment allows, direct-gather kernel otherwise), 1 = always the direct-gather kernel, 2 = the
+ * one-launch-per-epoch TMA kernel instead of the persistent one.  Process-wide; meant for tests and A/B timing. */
 int trb_set_kernel_path(int path);
 
 /* ---- rigid / affine registration ---------------------------------------- */

@@ -159,7 +159,7 @@ def weighted_loss(t, w, weights):
 # rigid / affine epoch loop
 # --------------------------------------------------------------------------- #
 def affine_like_loop(moving, target, mode, p0, lr, epochs, weights=(1.0, 0.0, 0.0),
-                     keep_warped=False, record_grads=False):
+                     keep_warped=False, record_grads=False, optimiser="sgd", betas=(0.9, 0.999), eps=1e-8):
     """warpings.py:117-174 (rigid_register) and :30-113 (affine_register).
 
     mode 'rigid': p = Regressor.reg (utils.py:313-322), theta = rigid_theta(p).
@@ -168,9 +168,12 @@ def affine_like_loop(moving, target, mode, p0, lr, epochs, weights=(1.0, 0.0, 0.
     bit-exact), so only its output bias (= p) moves.
     Plain SGD, lr, no momentum (warpings.py:58,131).  Best = strictly lower loss,
     evaluated pre-step (:85-93,151-159).
+    optimiser='adam' (EXTENSION, north_star item 3, no reference counterpart): torch.optim.Adam on the same
+    parameters with the same autograd gradient.
     """
     nd = moving.dim() - 2
     p = p0.clone().detach().to(moving.dtype).requires_grad_(True)
+    opt = torch.optim.Adam([p], lr, betas=betas, eps=eps) if optimiser == "adam" else None
     losses, grads = [], []
     best_loss, best_theta, best_warped = None, None, None
     for _ in range(epochs):
@@ -188,8 +191,11 @@ def affine_like_loop(moving, target, mode, p0, lr, epochs, weights=(1.0, 0.0, 0.
             best_loss, best_theta = lv, theta.detach().clone()
             if keep_warped:
                 best_warped = warped.detach().clone()
-        with torch.no_grad():
-            p -= lr * p.grad
+        if opt is not None:
+            opt.step()
+        else:
+            with torch.no_grad():
+                p -= lr * p.grad
     with torch.no_grad():
         final_theta = (rigid_theta(p) if mode == "rigid" else p.view(1, nd, nd + 1)).clone()
         final_warped = affine_warp(final_theta, moving) if keep_warped else None

@@ -325,8 +325,9 @@ extern "C" int trb_sm_count(void) { return sm_count(); }
 
 extern "C" int trb_set_kernel_path(int path)
 {
-    if (path != 0 && path != 1) { set_error("path must be 0 (auto) or 1 (direct)"); return TRB_ERR_ARG; }
+    if (path < 0 || path > 2) { set_error("path must be 0 (auto), 1 (direct) or 2 (per-epoch TMA kernel)"); return TRB_ERR_ARG; }
     g_force_direct = (path == 1);
+    set_no_persist(path == 2);
     return TRB_OK;
 }
 
@@ -388,8 +389,12 @@ extern "C" int trb_affine_optim(int ndim, int mode, const float *moving_dev, con
     p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs))
-        return launch_affine3d_tma(p, n_pairs, true, epoch0, n_epochs, s);
+    if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
+        if (n_epochs <= 0) return TRB_OK;
+        rc = launch_affine3d_persist(p, n_pairs, epoch0, n_epochs, s);      // all epochs in one cooperative launch
+        if (rc != TRB_ERR_UNSUPPORTED) return rc;
+        return launch_affine3d_tma(p, n_pairs, true, epoch0, n_epochs, s);  // one launch per epoch
+    }
     const int rows = ndim == 3 ? D * H : H;
     const dim3 grid(blocks_per_pair(rows, n_pairs), n_pairs);
     for (int e = 0; e < n_epochs; ++e) {

@@ -15,6 +15,9 @@ constexpr int kMaxSlots = 1024;      // partial-sum slots per pair in the worksp
 struct AffineParams;
 bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs);
 int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int n_launch, cudaStream_t stream);
+// persistent multi-epoch kernel (affine_persist.cu); TRB_ERR_UNSUPPORTED = nothing enqueued, take the per-epoch kernel
+int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream);
+void set_no_persist(bool v);
 
 struct AffineParams {
     const float *moving, *target;
@@ -32,6 +35,7 @@ struct AffineParams {
     int mode, optimiser;
     float beta1, beta2, adam_eps;
     const double *extra;         // optional [n_pairs][13]: extra loss term and its d/dtheta (e.g. the NMI term), or NULL
+    int extra_pair;              // row of `extra` (set by the epilogue wrappers)
     PeerExchange peer;
 };
 
@@ -93,19 +97,22 @@ __device__ void rigid_chain(const float *p, const double *g, double *dp)
 // Runs in ONE thread per pair (O(100) flops).  M holds the TRB_MOMENTS sums with the
 // UN-scaled interpolant derivative; the grid_sample un-normalisation factor S_r/2 is
 // applied here.
-template <int NDIM>
-__device__ void affine_epilogue(const double *M, const AffineParams &p, int pair)
+// `st` is the pair's TRB_STATE_FLOATS block: in global memory (LOCAL = false; __ldcg loads: another CTA wrote it in the
+// previous epoch) or a private copy in shared memory (LOCAL = true; the persistent kernel keeps one per CTA and pair).
+// Returns the loss of the pre-step theta; *improved says whether this epoch became the best so far.
+template <int NDIM, bool LOCAL>
+__device__ float affine_epilogue_core(const double *M, const AffineParams &p, int epoch, float *st, bool *improved)
 {
     constexpr int NC = NDIM + 1, NT = NDIM * NC;
-    float *st = p.state + (size_t)pair * TRB_STATE_FLOATS;
+    auto ld = [&](int i) -> float { return LOCAL ? st[i] : __ldcg(st + i); };
     // read everything first (independent loads, one round trip), compute, then write
     float par[12], th_cur[12], am[12], av[12];
 #pragma unroll
-    for (int i = 0; i < 12; ++i) { par[i] = __ldcg(st + TRB_STATE_PARAMS + i); th_cur[i] = __ldcg(st + TRB_STATE_THETA + i); }
-    const float best_prev = __ldcg(st + TRB_STATE_BEST_LOSS);
+    for (int i = 0; i < 12; ++i) { par[i] = ld(TRB_STATE_PARAMS + i); th_cur[i] = ld(TRB_STATE_THETA + i); }
+    const float best_prev = ld(TRB_STATE_BEST_LOSS);
     if (p.optimiser != TRB_OPT_SGD) {
 #pragma unroll
-        for (int i = 0; i < 12; ++i) { am[i] = __ldcg(st + TRB_STATE_ADAM_M + i); av[i] = __ldcg(st + TRB_STATE_ADAM_V + i); }
+        for (int i = 0; i < 12; ++i) { am[i] = ld(TRB_STATE_ADAM_M + i); av[i] = ld(TRB_STATE_ADAM_V + i); }
     }
     const double n = (double)(NDIM == 3 ? p.D : 1) * (double)p.H * (double)p.W;
     const LossCoef lc = loss_coefficients(n, M[0], M[1], M[2], M[3], M[4], (double)p.w_mse, (double)p.w_ncc);
@@ -120,20 +127,20 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
         }
     double loss_d = lc.loss;
     if (p.extra) {                                  // externally evaluated term (already in theta units)
-        const double *ex = p.extra + (size_t)pair * 13;
+        const double *ex = p.extra + (size_t)(p.extra_pair) * 13;
         loss_d += ex[0];
 #pragma unroll
         for (int i = 0; i < NT; ++i) dth[i] += ex[1 + i];
     }
     const float loss = (float)loss_d;
     // best tracking on the pre-step theta (warpings.py:85-93,151-159: strictly lower)
-    if (p.epoch == 0 || loss < best_prev) {
+    *improved = (epoch == 0 || loss < best_prev);
+    if (*improved) {
         st[TRB_STATE_BEST_LOSS] = loss;
 #pragma unroll
         for (int i = 0; i < NT; ++i) st[TRB_STATE_BEST_THETA + i] = th_cur[i];
     }
     st[TRB_STATE_LAST_LOSS] = loss;
-    if (p.loss_log) p.loss_log[(size_t)pair * p.log_stride + p.epoch] = loss;
 
     double dp[12];
     int np;
@@ -153,7 +160,7 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
             if (p.optimiser == TRB_OPT_SGD) {
                 v = v - p.lr * g;                      // torch.optim.SGD, no momentum / decay
             } else {                                   // torch.optim.Adam semantics (extension)
-                const float t = (float)(p.epoch + 1);
+                const float t = (float)(epoch + 1);
                 float m = am[i], s = av[i];
                 m = p.beta1 * m + (1.f - p.beta1) * g;
                 s = p.beta2 * s + (1.f - p.beta2) * g * g;
@@ -175,6 +182,16 @@ __device__ void affine_epilogue(const double *M, const AffineParams &p, int pair
 #pragma unroll
         for (int i = 0; i < NT; ++i) st[TRB_STATE_THETA + i] = par[i];
     }
+    return loss;
+}
+
+template <int NDIM>
+__device__ void affine_epilogue(const double *M, AffineParams p, int pair)
+{
+    bool improved;
+    p.extra_pair = pair;
+    const float loss = affine_epilogue_core<NDIM, false>(M, p, p.epoch, p.state + (size_t)pair * TRB_STATE_FLOATS, &improved);
+    if (p.loss_log) p.loss_log[(size_t)pair * p.log_stride + p.epoch] = loss;
 }
 
 // second half of the CTA reduction: `red` holds one row of TRB_MOMENTS warp totals per warp

@@ -21,9 +21,10 @@ OPT = {"sgd": 0, "adam": 1}
 
 
 def set_kernel_path(path: str = "auto") -> None:
-    """'auto': TMA-staged 3-D kernel when shape/alignment allow, else the direct-gather kernel;
-    'direct': always the direct-gather kernel (tests / A-B timing)."""
-    check(_lib.load().trb_set_kernel_path({"auto": 0, "direct": 1}[path]), "set_kernel_path")
+    """'auto': persistent multi-epoch TMA kernel when shape/alignment allow, else the direct-gather kernel;
+    'direct': always the direct-gather kernel; 'tma': the per-epoch TMA kernel instead of the persistent one
+    (tests / A-B timing)."""
+    check(_lib.load().trb_set_kernel_path({"auto": 0, "direct": 1, "tma": 2}[path]), "set_kernel_path")
 
 
 def _stream(device) -> int:

@@ -27,8 +27,9 @@ class Register():
             user criterion in rigid/affine mode and uses MSE (warpings.py:38-40,125-127); so do we.
         grad_edges, debug : as in the reference.
         flow_param, smooth, optm : keyword-only EXTENSIONS with reference-preserving defaults. flow_param='direct'
-            optimises the dense flow itself (SGD or optm='ADAM') with a smoothness weight `smooth` instead of the
-            reference's U-Net parametrisation ('unet').
+            optimises the dense flow itself with a smoothness weight `smooth` instead of the reference's U-Net
+            parametrisation ('unet'). optm='ADAM' (default 'SGD', the reference's optimiser) selects torch.optim.Adam
+            semantics, fused into the epoch kernel: on theta for rigid/affine, on the flow for flow_param='direct'.
         '''
         self.criterion = criterion
         self.weight = weight
@@ -89,7 +90,7 @@ class Register():
             fn = affine_register if self.mode == 'affine' else rigid_register
             probs = []
             kw = dict(lr=lr, epochs=max_epochs, per=per, device=self.device, debug=self.debug,
-                      grad_edges=self.grad_edges, _want_warped=False, _problem_out=probs)
+                      grad_edges=self.grad_edges, optm=self.optm, _want_warped=False, _problem_out=probs)
             if both:
                 kw.update(criterions=self.criterion, weights=self.weight)
             elif self.weight is not None:

@@ -108,11 +108,23 @@ def _warp_batch(theta, moving):
     return torch.cat([TF.warp_affine(theta[i], moving[i:i + 1]) for i in range(moving.shape[0])], dim=0)
 
 
-def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, want_warped=True):
+def _optimiser_name(optm) -> str:
+    """'SGD' (the reference's only optimiser, warpings.py:58,131) or 'ADAM' (keyword-only extension; the reference's
+    docstring names an `optm` parameter it never implements, torchregister.py:28-29)."""
+    name = str(optm).lower()
+    if name not in TF.OPT:
+        raise ValueError("optm must be 'SGD' or 'ADAM' (got %r)" % (optm,))
+    return name
+
+
+def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, want_warped=True, optm='SGD',
+                 betas=(0.9, 0.999), eps=1e-8):
     w_mse, w_ncc, w_nmi = weights3
+    opt = _optimiser_name(optm)
     prob = TF.AffineProblem(moving, target, mode, params0, epochs)
     if w_nmi == 0:
-        prob.run(epochs, lr, w_mse, w_ncc)               # one fused launch per epoch, no host round trips
+        # all epochs in one persistent launch (3-D) / one fused launch per epoch (2-D); no host round trips
+        prob.run(epochs, lr, w_mse, w_ncc, optimiser=opt, betas=betas, eps=eps)
     else:
         # Default weights of the reference include the NMI/KDE term (utils.py:224-259).  Per epoch: the MSE/NCC
         # moments from the CUDA pass, the warped volume, the NMI term and its gradient w.r.t. the warped volume
@@ -131,7 +143,7 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
                 term, gw = terms[i].loss_grad(warped, w_nmi)
                 extra[i, 0:1] = term
                 extra[i, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta[i], moving[i:i + 1], gw).reshape(-1)
-            prob.apply(mom, lr, w_mse, w_ncc, extra=extra)
+            prob.apply(mom, lr, w_mse, w_ncc, optimiser=opt, betas=betas, eps=eps, extra=extra)
     final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
     # the reference keeps the warped volumes of the final and best epochs; we never write them during
     # the loop and re-create them here only when the caller wants them (Register.optim does not)
@@ -143,24 +155,28 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
 
 
 def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
-                    weights=[0.33, 0.33, 0.33], grad_edges=True, *, _want_warped=True, _problem_out=None):
+                    weights=[0.33, 0.33, 0.33], grad_edges=True, *, optm='SGD', betas=(0.9, 0.999), eps=1e-8,
+                    _want_warped=True, _problem_out=None):
     """Affine registration by SGD on the 12 (6) entries of theta, identity start
     (reference warpings.py:30-113).  The reference routes theta through a zero-initialised MLP
     that is provably inert under momentum-free SGD; `per` only sizes that MLP and
-    is accepted and ignored.  Returns ([final_warped, best_warped], [final_theta, best_theta])."""
+    is accepted and ignored.  Returns ([final_warped, best_warped], [final_theta, best_theta]).
+    `optm='ADAM'` (keyword-only extension, north_star item 3): torch.optim.Adam semantics on theta, fused into the
+    epoch's final reduction like the SGD step."""
     _reject_edges(grad_edges)
     TF.require_cuda(moving, "moving")
     nd = moving.dim() - 2
     wp = similarity_weights(criterions, weights, "affine_register")
     ident = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)      # every pair starts at identity
-    prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug, _want_warped)
+    prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug, _want_warped, optm, betas, eps)
     if _problem_out is not None:
         _problem_out.append(prob)
     return warped, theta
 
 
 def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
-                   weights=[0.33, 0.33, 0.33], grad_edges=True, *, reg0=None, _want_warped=True, _problem_out=None):
+                   weights=[0.33, 0.33, 0.33], grad_edges=True, *, reg0=None, optm='SGD', betas=(0.9, 0.999), eps=1e-8,
+                   _want_warped=True, _problem_out=None):
     """Rigid registration: SGD on (psi, theta, phi, a, b, c) / (theta, tx, ty)
     (reference warpings.py:117-174, utils.py:287-330).  Initial parameters are drawn with
     torch.rand on the data's device like the reference's Regressor; `reg0` (keyword-only
@@ -174,7 +190,7 @@ def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', 
         reg0 = torch.rand(npar, device=moving.device) if moving.shape[0] == 1 else torch.rand(moving.shape[0], npar, device=moving.device)
     if debug:
         print(reg0)
-    prob, warped, theta = _affine_like("rigid", moving, target, lr, epochs, wp, reg0, debug, _want_warped)
+    prob, warped, theta = _affine_like("rigid", moving, target, lr, epochs, wp, reg0, debug, _want_warped, optm, betas, eps)
     if _problem_out is not None:
         _problem_out.append(prob)
     return warped, theta
