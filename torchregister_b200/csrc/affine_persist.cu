@@ -42,6 +42,8 @@ constexpr int kAccWords = 168;                                    // per (epoch,
 constexpr int kCountBits = 12;                                    // low bits of every word: contributions received
 constexpr int kRedLdP = 44;
 constexpr int kTargetWord = 100;                                  // tickets[pair*kTicketStride + 100]: contributions per epoch
+constexpr int kTsumWord = 104;                                    // tickets[pair*kTicketStride + 104..119]: sum t, sum t^2 (2 x 4 limbs, u64)
+constexpr int kTsumBlocks = 64;
 
 enum { kFits = 1, kNewCol = 2, kEndCol = 4, kEnd = 8 };
 
@@ -63,6 +65,7 @@ struct __align__(16) PCol { int x0, y0, pair, pad; float coef[12]; };
 
 struct PersistParams {
     TmaParams t;
+    int tsum_blocks;                 // blocks per pair of target_sums_kernel (= count field of its words)
     int n_epochs;                    // epochs in this launch (<= chunk capacity of the accumulator region)
     unsigned long long *acc;         // [n_epochs][n_pairs][kAccWords], zeroed before the launch
     const unsigned *targets;         // tickets region; word [pair*kTicketStride + kTargetWord]
@@ -90,15 +93,21 @@ __device__ __forceinline__ void red_add_u64(unsigned long long *p, unsigned long
 {
     asm volatile("red.relaxed.gpu.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, unsigned parity)
+// helper warps wait for microseconds at a time: let the hardware suspend them (suspend-time hint) and back off between
+// tries, so that they do not take issue slots from the consumer warps of their sub-partition (the first version's spin
+// loops were 4 % of all executed instructions, ncu)
+__device__ __forceinline__ void mbar_wait_sleepy(uint64_t *bar, unsigned parity)
 {
     unsigned ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    return ok != 0;
+    for (;;) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+        if (ok) return;
+        __nanosleep(200);
+    }
 }
 
 // ---- fixed-point accumulators -----------------------------------------------------------------------------------
@@ -122,6 +131,51 @@ __device__ __forceinline__ double from_limbs(const unsigned long long *w /*smem,
     for (int l = 0; l < kLimbs; ++l)
         q[l] = (double)((long long)(w[l * TRB_MOMENTS] - (unsigned long long)count) >> kCountBits);
     return (q[0] * 0x1p40 + q[1]) + (q[2] * 0x1p-40 + q[3] * 0x1p-80);
+}
+
+
+// sum t and sum t^2 of every pair's slab [s_begin, s_end): independent of theta, so computed once per launch instead
+// of once per voxel and epoch.  fp64 per thread, fixed-point atomics across blocks (order independent, see to_limbs).
+__global__ void __launch_bounds__(256) target_sums_kernel(const float *__restrict__ target, long long pair_stride, long long begin,
+                                                          long long count, unsigned *tickets)
+{
+    const int pair = blockIdx.y;
+    const float4 *src = reinterpret_cast<const float4 *>(target + (size_t)pair * pair_stride + begin);
+    const long long n4 = count >> 2;
+    double s = 0.0, ss = 0.0;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float4 v = __ldg(src + i);
+        s += ((double)v.x + (double)v.y) + ((double)v.z + (double)v.w);
+        ss += ((double)v.x * v.x + (double)v.y * v.y) + ((double)v.z * v.z + (double)v.w * v.w);
+    }
+    s = warp_sum(s); ss = warp_sum(ss);
+    __shared__ double sh[2][8];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) { sh[0][warp] = s; sh[1][warp] = ss; }
+    __syncthreads();
+    if (threadIdx.x < 2) {
+        double t = 0.0;
+        for (int w = 0; w < 8; ++w) t += sh[threadIdx.x][w];
+        unsigned long long *dst = reinterpret_cast<unsigned long long *>(tickets + (size_t)pair * kTicketStride + kTsumWord) + threadIdx.x * kLimbs;
+        long long q[kLimbs];
+        const bool fin = isfinite(t) && fabs(t) < 0x1p78;
+        to_limbs(fin ? t : 0.0, q);
+#pragma unroll
+        for (int l = 0; l < kLimbs; ++l) red_add_u64(dst + l, ((unsigned long long)q[l] << kCountBits) + (fin ? 1ull : 0ull));
+    }
+}
+__device__ __forceinline__ double tsum_read(const unsigned *tickets, int pair, int which, unsigned count)
+{
+    const unsigned long long *w = reinterpret_cast<const unsigned long long *>(tickets + (size_t)pair * kTicketStride + kTsumWord) + which * kLimbs;
+    double q[kLimbs];
+    bool ok = true;
+#pragma unroll
+    for (int l = 0; l < kLimbs; ++l) {
+        const unsigned long long v = __ldcg(w + l);
+        ok = ok && ((unsigned)(v & ((1ull << kCountBits) - 1ull)) == count);      // a non-finite block sum leaves the count short
+        q[l] = (double)((long long)(v - (unsigned long long)(v & ((1ull << kCountBits) - 1ull))) >> kCountBits);
+    }
+    return ok ? (q[0] * 0x1p40 + q[1]) + (q[2] * 0x1p-40 + q[3] * 0x1p-80) : __longlong_as_double(0x7ff8000000000000ll);
 }
 
 // footprint constants of one column under the coordinate map k (compute_col of affine_tile.cuh without its smem cache)
@@ -234,6 +288,7 @@ __device__ float affine_epilogue_warp(const double *M, const AffineParams &p, in
 // e_rel-1 to be complete (every word's count field == contributions per epoch), rebuild the 41 moments and run the
 // epilogue on the private state.  All 32 lanes take part.
 __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, float *st, bool writer, unsigned target,
+                              const double *tsum /* sum t, sum t^2 of the pair, or NULL (MSE only) */,
                               unsigned long long *accw, double *mrow, int lane)
 {
     if (e_rel == 0) return;
@@ -241,6 +296,7 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
     const unsigned long long *A = pp.acc + ((size_t)(e_rel - 1) * pp.t.n_pairs + pair) * kAccWords;
     const unsigned long long cmask = (1ull << kCountBits) - 1ull;
     const unsigned long long tq0 = PT_NOW();
+    unsigned backoff = 32;
     for (;;) {
         // cheap probe first: one word (the one the contributors add last), then the full check
         unsigned long long probe = 0ull;
@@ -260,7 +316,8 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
             if (__all_sync(kFull, ok)) break;
         }
         PT_INC(16);
-        __nanosleep(100);
+        __nanosleep(backoff);                      // 32 ns .. 1 us: short while the hand-over is imminent (single pair), cheap otherwise
+        if (backoff < 1024) backoff += backoff >> 1;
     }
     PT_ADD(2, tq0);
     const unsigned long long te0 = PT_NOW();
@@ -268,6 +325,8 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
     const bool bad = (accw[kAccNan] >> kCountBits) != 0ull;
     for (int v = lane; v < TRB_MOMENTS; v += 32)
         mrow[v] = bad ? __longlong_as_double(0x7ff8000000000000ll) : from_limbs(accw + v, target);
+    __syncwarp();
+    if (tsum && lane == 0 && !bad) { mrow[0] = tsum[0]; mrow[2] = tsum[1]; }
     __syncwarp();
     const int epoch = a.epoch + e_rel - 1;
     const float loss = affine_epilogue_warp(mrow, a, epoch, st, reinterpret_cast<double *>(accw) /* words are consumed: scratch */, lane);
@@ -332,7 +391,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                             PT_INC(1);
                             cur_pair = pair;
                             const int cs = seg % kCoefSlots;
-                            mbar_wait(coef_full + cs, (unsigned)(seg / kCoefSlots) & 1u);
+                            mbar_wait_sleepy(coef_full + cs, (unsigned)(seg / kCoefSlots) & 1u);
                             const float *cq = coefq + cs * 12;
 #pragma unroll
                             for (int r = 0; r < 3; ++r) {
@@ -360,7 +419,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                     }
                     const int stage = it % kStages;
                     const unsigned long long tw0 = PT_NOW();
-                    if (it >= kStages) mbar_wait(empty_bar + stage, (unsigned)((it / kStages) - 1) & 1u);
+                    if (it >= kStages) mbar_wait_sleepy(empty_bar + stage, (unsigned)((it / kStages) - 1) & 1u);
                     PT_ADD(4, tw0);
                     TileIter nx = t;
                     const bool moved = iter_next(nx, p, b, G);
@@ -403,7 +462,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             PT_SET(7);
             {   // end of stream
                 const int stage = it % kStages;
-                if (it >= kStages) mbar_wait(empty_bar + stage, (unsigned)((it / kStages) - 1) & 1u);
+                if (it >= kStages) mbar_wait_sleepy(empty_bar + stage, (unsigned)((it / kStages) - 1) & 1u);
                 if (lane == 0) {
                     PTile m = {};
                     m.flags = kEnd;
@@ -423,7 +482,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                     if (!iter_next(t, p, b, G)) continue;                // walk to the end of the column piece
                     const int cbuf = k & 1;
                     const unsigned long long tr0 = PT_NOW();
-                    mbar_wait(red_full + cbuf, (unsigned)(k >> 1) & 1u);
+                    mbar_wait_sleepy(red_full + cbuf, (unsigned)(k >> 1) & 1u);
                     PT_ADD(14, tr0);
                     const unsigned long long tp0 = PT_NOW();
                     const float *rows = red + cbuf * (kConsumerWarps * kRedLdP);
@@ -464,6 +523,8 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             __shared__ int slot_pair[kStateSlots];
             __shared__ unsigned slot_target[kStateSlots];
             __shared__ int slot_writer[kStateSlots];
+            __shared__ double slot_tsum[kStateSlots][2];
+            const bool need_tsum = !MSE_ONLY;
             int n_slots = 0;
             {
                 TileIter t;
@@ -479,6 +540,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                                 slot_target[n_slots] = pp.targets[(size_t)pair * kTicketStride + kTargetWord];
                                 slot_writer[n_slots] = (t.cg == pair * p.cols_per_pair && t.tz_i == 0) ? 1 : 0;
                             }
+                            if (need_tsum && lane < 2) slot_tsum[n_slots][lane] = tsum_read(pp.targets, pair, lane, (unsigned)pp.tsum_blocks);
                             const float *src = p.a.state + (size_t)pair * TRB_STATE_FLOATS;
                             state_s[n_slots * TRB_STATE_FLOATS + lane] = __ldcg(src + lane);
                             state_s[n_slots * TRB_STATE_FLOATS + 32 + lane] = __ldcg(src + 32 + lane);
@@ -495,9 +557,9 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             for (int e_rel = 0; e_rel < pp.n_epochs; ++e_rel) {
                 for (int sl = 0; sl < n_slots; ++sl, ++seg) {
                     float *st = state_s + sl * TRB_STATE_FLOATS;
-                    acquire_theta(pp, e_rel, slot_pair[sl], st, slot_writer[sl] != 0, slot_target[sl], accw, mrow, lane);
+                    acquire_theta(pp, e_rel, slot_pair[sl], st, slot_writer[sl] != 0, slot_target[sl], need_tsum ? slot_tsum[sl] : nullptr, accw, mrow, lane);
                     const int cs = seg % kCoefSlots;
-                    if (seg >= kCoefSlots) mbar_wait(coef_empty + cs, (unsigned)((seg / kCoefSlots) - 1) & 1u);
+                    if (seg >= kCoefSlots) mbar_wait_sleepy(coef_empty + cs, (unsigned)((seg / kCoefSlots) - 1) & 1u);
                     if (lane < 12) {
                         // make_coef of affine_tile.cuh, one entry per lane
                         const int r = lane >> 2, cidx = lane & 3;
@@ -513,7 +575,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             for (int sl = 0; sl < n_slots; ++sl) {
                 if (!slot_writer[sl]) continue;
                 float *st = state_s + sl * TRB_STATE_FLOATS;
-                acquire_theta(pp, pp.n_epochs, slot_pair[sl], st, true, slot_target[sl], accw, mrow, lane);
+                acquire_theta(pp, pp.n_epochs, slot_pair[sl], st, true, slot_target[sl], need_tsum ? slot_tsum[sl] : nullptr, accw, mrow, lane);
                 float *dst = p.a.state + (size_t)slot_pair[sl] * TRB_STATE_FLOATS;
                 dst[lane] = st[lane];
                 dst[32 + lane] = st[32 + lane];
@@ -528,7 +590,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
     bool valid = false;
     float xv = 0.f, yv = 0.f, pxy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f};
     const float *__restrict__ mov = p.a.moving;
-    Acc A;
+    Acc2 A;
     int kcol = 0;
     for (int it = 0;; ++it) {
         const int stage = it % kStages;
@@ -556,11 +618,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             }
             mov = p.a.moving + (size_t)pc.pair * p.a.pair_stride;
 #pragma unroll
-            for (int i = 0; i < 5; ++i) A.s[i] = f2(0.f);
-#pragma unroll
-            for (int kk = 0; kk < 3; ++kk)
-#pragma unroll
-                for (int r = 0; r < 3; ++r) A.P[kk][r] = A.Q[kk][r] = f2(0.f);
+            for (int i = 0; i < 12; ++i) A.a[i] = f2(0.f);
 #ifdef TRB_TIMING
             if (lane == 0 && warp == 0) { g_pdbg[blockIdx.x * 32 + 12] += gtime() - ts0; }
 #endif
@@ -587,7 +645,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                         case 2: t = make_float2(lds_f<4 * TX * TY * 4>(tg), lds_f<5 * TX * TY * 4>(tg)); break;
                         default: t = make_float2(lds_f<6 * TX * TY * 4>(tg), lds_f<7 * TX * TY * 4>(tg)); break;
                         }
-                        pair_step<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                         zf = __fadd2_rn(zf, f2(2.f));
                     }
                 } else {
@@ -600,14 +658,14 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                         const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
                         const float2 t = make_float2(lds_f_dyn(tg + zz * (TX * TY * 4)),
                                                      lds_f_dyn(tg + (second ? zz + 1 : zz) * (TX * TY * 4)));
-                        if (second) pair_step<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
-                        else pair_step<kBX, kBY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        if (second) pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        else pair_step2<kBX, kBY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                     }
                 }
             } else {
                 for (int zz = 0; zz < nz; ++zz) {
                     const float zf = m.zf0 + (float)zz;
-                    voxel_direct<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
+                    voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
                                            lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
                 }
             }
@@ -624,19 +682,35 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
 #pragma unroll
             for (int i = 0; i < TRB_MOMENTS; ++i) acc[i] = 0.f;
             if (valid) {
-#pragma unroll
-                for (int i = 0; i < 5; ++i) acc[i] = A.s[i].x + A.s[i].y;
-#pragma unroll
-                for (int kk = 0; kk < 3; ++kk)
+                // Acc2 layout (affine_tile.cuh): family f in {1, t, w, z, tz, wz} -> a[2f] = (k G0, k G1), a[2f+1] = (k G2, k w);
+                // MSE only: families {d, d z} with (d G2, d^2) in a[1].  sum t / sum t^2 are not accumulated (target_sums_kernel).
+                if (MSE_ONLY) {
+                    acc[2] = A.a[1].y;                                  // sum d^2 rides in the sum t^2 slot
+                    const float Pr[3] = {A.a[0].x, A.a[0].y, A.a[1].x}, Qr[3] = {A.a[2].x, A.a[2].y, A.a[3].x};
 #pragma unroll
                     for (int r = 0; r < 3; ++r) {
-                        const float pq = A.P[kk][r].x + A.P[kk][r].y, qq = A.Q[kk][r].x + A.Q[kk][r].y;
-                        const int bi = 5 + kk * 12 + r * 4;
-                        acc[bi + 0] = xv * pq;
-                        acc[bi + 1] = yv * pq;
-                        acc[bi + 2] = fmaf(inv_d2, qq, zoff * pq);
-                        acc[bi + 3] = pq;
+                        const int bi = 5 + 2 * 12 + r * 4;              // the "w" family: the epilogue turns it into gm * sum d J
+                        acc[bi + 0] = xv * Pr[r];
+                        acc[bi + 1] = yv * Pr[r];
+                        acc[bi + 2] = fmaf(inv_d2, Qr[r], zoff * Pr[r]);
+                        acc[bi + 3] = Pr[r];
                     }
+                } else {
+                    acc[1] = A.a[1].y; acc[3] = A.a[5].y; acc[4] = A.a[3].y;
+#pragma unroll
+                    for (int kk = 0; kk < 3; ++kk) {
+                        const float Pr[3] = {A.a[2 * kk].x, A.a[2 * kk].y, A.a[2 * kk + 1].x};
+                        const float Qr[3] = {A.a[2 * (kk + 3)].x, A.a[2 * (kk + 3)].y, A.a[2 * (kk + 3) + 1].x};
+#pragma unroll
+                        for (int r = 0; r < 3; ++r) {
+                            const int bi = 5 + kk * 12 + r * 4;
+                            acc[bi + 0] = xv * Pr[r];
+                            acc[bi + 1] = yv * Pr[r];
+                            acc[bi + 2] = fmaf(inv_d2, Qr[r], zoff * Pr[r]);
+                            acc[bi + 3] = Pr[r];
+                        }
+                    }
+                }
             }
             const int cbuf = kcol & 1, use = kcol >> 1;
             if (use > 0) mbar_wait(red_empty + cbuf, (unsigned)(use - 1) & 1u);
@@ -748,6 +822,14 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         if (e != cudaSuccess) return check_cuda(e, "cudaMemcpy2DAsync(contributions)");
         pp.acc = reinterpret_cast<unsigned long long *>(as.partials);
         pp.targets = as.tickets;
+        pp.tsum_blocks = kTsumBlocks;
+        if (!mse_only) {
+            e = cudaMemset2DAsync(as.tickets + kTsumWord, kTicketStride * sizeof(unsigned), 0, 2 * kLimbs * sizeof(unsigned long long), (size_t)np, stream);
+            if (e != cudaSuccess) return check_cuda(e, "cudaMemset2DAsync(target sums)");
+            const long long slab = (long long)as.H * as.W;
+            target_sums_kernel<<<dim3(kTsumBlocks, np), 256, 0, stream>>>(as.target, as.pair_stride, (long long)as.s_begin * slab,
+                                                                        (long long)(as.s_end - as.s_begin) * slab, as.tickets);
+        }
         for (int done = 0; done < n_epochs;) {
             const int ne = min(chunk_cap, n_epochs - done);
             pp.n_epochs = ne;

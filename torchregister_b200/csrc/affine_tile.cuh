@@ -195,6 +195,131 @@ __device__ __forceinline__ void pair_step(uint32_t box_m, float Mrel, float2 ix,
     }
 }
 
+// ---- second formulation of the per-voxel arithmetic (round 2; used by affine_persist.cu) ------------------------------
+// tools/microbench2.cu: on sm_100a a packed fp32 instruction is bounded by REGISTER-FILE READS, not by the fp32 pipe: an
+// FFMA2 with three distinct register pairs costs 4.2 cycles per sub-partition, one whose third source is a 32-bit
+// broadcast or sits in the operand reuse cache 2.6, two broadcasts 2.15 (profiles/r02_microbench_ffma2_operands.txt).
+// pair_step packs voxel a / voxel b into the two halves of every value, so its moment updates read three pairs
+// (k, G_r, accumulator).  Here the two halves of a pair belong to the SAME voxel instead:
+//   * interpolation: the x- and y-stage run on pairs over the two z planes of the cell ((c000,c100), ...) with the
+//     fractions as 32-bit broadcast operands; the z-stage is scalar and leaves val, G0, G1, G2 in freely allocatable
+//     registers, i.e. as the pairs GA = (G0,G1), GB = (G2,val) at no cost;
+//   * moments: acc_k += k * GA, acc_k' += k * GB with k in {1, t, val, z, t z, val z} a broadcast scalar — two source
+//     pairs per instruction, one of them (GA / GB) shared by six consecutive instructions.  The second lane of GB yields
+//     sum w, sum t w, sum w^2 for free.  Both voxels of a step add into the same accumulators: 12 pairs = 24 registers
+//     instead of 23 x 2 lanes = 46;
+//   * sum t and sum t^2 do not depend on theta: they are not accumulated here at all (target_sums_kernel computes them
+//     once per launch).
+// Every interpolation operation is the same IEEE operation as in pair_step (same values bit for bit); only the order
+// in which the moments are summed differs.
+struct Acc2 {
+    float2 a[12];    // [2*f + h]: family f in {1, t, w, z, tz, wz}, h = 0: (sum k G0, sum k G1), h = 1: (sum k G2, sum k w)
+};                   // MSE_ONLY uses [0..3]: family d = w - t and d z, with h = 1: (sum d G2, sum d^2) / (sum d z G2, -)
+
+template <bool MSE_ONLY>
+__device__ __forceinline__ void moments_accumulate(float t, float z, float val, float G0, float G1, float G2, Acc2 &A)
+{
+    const float2 GA = make_float2(G0, G1);
+    if (MSE_ONLY) {
+        const float d = val - t, dz = d * z;
+        const float2 GB = make_float2(G2, d);
+        A.a[0] = __ffma2_rn(f2(d), GA, A.a[0]);
+        A.a[2] = __ffma2_rn(f2(dz), GA, A.a[2]);
+        A.a[1] = __ffma2_rn(f2(d), GB, A.a[1]);
+        A.a[3] = __ffma2_rn(f2(dz), GB, A.a[3]);
+    } else {
+        const float2 GB = make_float2(G2, val);
+        const float tz = t * z, wz = val * z;
+        A.a[0] = __fadd2_rn(A.a[0], GA);
+        A.a[2] = __ffma2_rn(f2(t), GA, A.a[2]);
+        A.a[4] = __ffma2_rn(f2(val), GA, A.a[4]);
+        A.a[6] = __ffma2_rn(f2(z), GA, A.a[6]);
+        A.a[8] = __ffma2_rn(f2(tz), GA, A.a[8]);
+        A.a[10] = __ffma2_rn(f2(wz), GA, A.a[10]);
+        A.a[1] = __fadd2_rn(A.a[1], GB);
+        A.a[3] = __ffma2_rn(f2(t), GB, A.a[3]);
+        A.a[5] = __ffma2_rn(f2(val), GB, A.a[5]);
+        A.a[7] = __ffma2_rn(f2(z), GB, A.a[7]);
+        A.a[9] = __ffma2_rn(f2(tz), GB, A.a[9]);
+        A.a[11] = __ffma2_rn(f2(wz), GB, A.a[11]);
+    }
+}
+
+// one voxel whose cell is staged in shared memory at byte address q (its corner (x0,y0,z0))
+template <int BX, int BY, bool MSE_ONLY>
+__device__ __forceinline__ void voxel_staged(uint32_t q, float tx, float ty, float tz, float t, float z, Acc2 &A)
+{
+    constexpr int SY = BX * 4, SZ = BX * BY * 4;
+    const float2 P0 = make_float2(lds_f<0>(q), lds_f<SZ>(q)), P1 = make_float2(lds_f<4>(q), lds_f<SZ + 4>(q));
+    const float2 R0 = make_float2(lds_f<SY>(q), lds_f<SZ + SY>(q)), R1 = make_float2(lds_f<SY + 4>(q), lds_f<SZ + SY + 4>(q));
+    const float2 dP = sub2(P1, P0), dR = sub2(R1, R0);                   // (d00, d10), (d01, d11)
+    const float2 vA = __ffma2_rn(f2(tx), dP, P0), vB = __ffma2_rn(f2(tx), dR, R0);   // (v00, v10), (v01, v11)
+    const float2 e = sub2(vB, vA);                                        // (e0, e1)
+    const float2 w = __ffma2_rn(f2(ty), e, vA);                           // (w0, w1)
+    const float2 dx = __ffma2_rn(f2(ty), sub2(dR, dP), dP);               // (dx0, dx1)
+    const float G2 = w.y - w.x;
+    const float val = fmaf(tz, G2, w.x);
+    const float G1 = fmaf(tz, e.y - e.x, e.x);
+    const float G0 = fmaf(tz, dx.y - dx.x, dx.x);
+    moments_accumulate<MSE_ONLY>(t, z, val, G0, G1, G2, A);
+}
+
+// two voxels (same x,y; z and z+1): coordinates, floor, fraction and index stay packed over the two voxels (their
+// operands are per-thread constants, i.e. broadcasts); SECOND = false skips voxel b.
+template <int BX, int BY, bool SECOND, bool MSE_ONLY>
+__device__ __forceinline__ void pair_step2(uint32_t box_m, float Mrel, float2 ix, float2 iy, float2 iz, float2 t, float2 zf, Acc2 &A)
+{
+#ifdef TRB_XU_FLOOR
+    // floor on the (otherwise idle) XU pipe: FRND.FLOOR, 16 lanes/clk/SM, instead of two packed adds on the fp32 pipe
+    const float2 fx = make_float2(floorf(ix.x), floorf(ix.y)), fy = make_float2(floorf(iy.x), floorf(iy.y)),
+                 fz = make_float2(floorf(iz.x), floorf(iz.y));
+#else
+    const float2 M = f2(kMagic), nM = f2(-kMagic);
+    const float2 flx = __fadd2_rd(ix, M), fly = __fadd2_rd(iy, M), flz = __fadd2_rd(iz, M);
+    const float2 fx = __fadd2_rn(flx, nM), fy = __fadd2_rn(fly, nM), fz = __fadd2_rn(flz, nM);
+#endif
+    const float2 tx = sub2(ix, fx), ty = sub2(iy, fy), tz = sub2(iz, fz);
+    const float2 tb = __ffma2_rn(f2(kIdxScale * (float)(BX * BY)), fz,
+                                 __ffma2_rn(f2(kIdxScale * (float)BX), fy, __ffma2_rn(f2(kIdxScale), fx, f2(Mrel))));
+    const uint32_t qa = box_m + ((uint32_t)__float_as_int(tb.x) << 2);
+    voxel_staged<BX, BY, MSE_ONLY>(qa, tx.x, ty.x, tz.x, t.x, zf.x, A);
+    if (SECOND) {
+        const uint32_t qb = box_m + ((uint32_t)__float_as_int(tb.y) << 2);
+        voxel_staged<BX, BY, MSE_ONLY>(qb, tx.y, ty.y, tz.y, t.y, zf.y, A);
+    }
+}
+
+// fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers (Acc2 form)
+template <bool MSE_ONLY>
+__device__ __forceinline__ void voxel_direct2(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
+                                              float t, float zf, Acc2 &A)
+{
+    ix = fminf(fmaxf(ix, -4.f), (float)W + 4.f);        // keeps the magic-number floor in range
+    iy = fminf(fmaxf(iy, -4.f), (float)H + 4.f);
+    iz = fminf(fmaxf(iz, -4.f), (float)D + 4.f);
+    const float fx = __fadd_rd(ix, kMagic) - kMagic, fy = __fadd_rd(iy, kMagic) - kMagic, fz = __fadd_rd(iz, kMagic) - kMagic;
+    const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const bool vx0 = (unsigned)x0 < (unsigned)W, vx1 = (unsigned)(x0 + 1) < (unsigned)W;
+    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+    const long long HW = (long long)H * W, o = ((long long)z0 * H + y0) * W + x0;
+    const float c000 = (vz0 & vy0 & vx0) ? __ldg(mov + o) : 0.f, c001 = (vz0 & vy0 & vx1) ? __ldg(mov + o + 1) : 0.f;
+    const float c010 = (vz0 & vy1 & vx0) ? __ldg(mov + o + W) : 0.f, c011 = (vz0 & vy1 & vx1) ? __ldg(mov + o + W + 1) : 0.f;
+    const float c100 = (vz1 & vy0 & vx0) ? __ldg(mov + o + HW) : 0.f, c101 = (vz1 & vy0 & vx1) ? __ldg(mov + o + HW + 1) : 0.f;
+    const float c110 = (vz1 & vy1 & vx0) ? __ldg(mov + o + HW + W) : 0.f, c111 = (vz1 & vy1 & vx1) ? __ldg(mov + o + HW + W + 1) : 0.f;
+    const float d00 = c001 - c000, d01 = c011 - c010, d10 = c101 - c100, d11 = c111 - c110;
+    const float v00 = fmaf(tx, d00, c000), v01 = fmaf(tx, d01, c010), v10 = fmaf(tx, d10, c100), v11 = fmaf(tx, d11, c110);
+    const float e0 = v01 - v00, e1 = v11 - v10;
+    const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
+    const float G2 = w1 - w0;
+    const float val = fmaf(tz, G2, w0);
+    const float G1 = fmaf(tz, e1 - e0, e0);
+    const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
+    const float G0 = fmaf(tz, dx1 - dx0, dx0);
+    moments_accumulate<MSE_ONLY>(t, zf, val, G0, G1, G2, A);
+}
+
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
 template <bool MSE_ONLY>
 __device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
