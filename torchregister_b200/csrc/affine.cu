@@ -286,16 +286,15 @@ __global__ void vjp_extract_kernel(const double *moments, double *dtheta, int nd
 }
 
 // ---- host side ---------------------------------------------------------------------------
-static int g_sm_count = 0;
+static int g_sm_count[64] = {};       // per device ordinal
 static bool g_force_direct = false;   // test hook: trb_set_kernel_path(1) pins the non-TMA kernel
 static int sm_count()
 {
-    if (g_sm_count == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess) return -1;
-        if (cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
-    }
-    return g_sm_count;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return -1;
+    int &n = g_sm_count[dev & 63];
+    if (n == 0 && cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return -1;
+    return n;
 }
 
 constexpr int kMaxBlocksPerPair = kMaxSlots;
@@ -432,6 +431,8 @@ extern "C" int trb_affine_optim_peer(const float *moving_dev, const float *targe
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
     if (!tma_path_eligible(3, p, 1)) { set_error("the fused sharded epoch needs the TMA kernel (3-D, W %% 4 == 0, W >= 32, H >= 16)"); return TRB_ERR_UNSUPPORTED; }
     if (n_epochs <= 0) return TRB_OK;             // validation only
+    rc = launch_affine3d_persist(p, 1, epoch0, n_epochs, (cudaStream_t)stream);   // all epochs in one launch, exchange inside
+    if (rc != TRB_ERR_UNSUPPORTED) return rc;
     return launch_affine3d_tma(p, 1, true, epoch0, n_epochs, (cudaStream_t)stream);
 }
 

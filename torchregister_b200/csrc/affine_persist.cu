@@ -328,6 +328,49 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
     __syncwarp();
     if (tsum && lane == 0 && !bad) { mrow[0] = tsum[0]; mrow[2] = tsum[1]; }
     __syncwarp();
+    if (a.peer.world > 1) {
+        // one volume sharded into z-slabs over the GPUs of the box: the designated CTA of every rank pushes this
+        // rank's 41 sums into every rank's mailbox over NVLink (peer.cuh), EVERY CTA of a rank then reads its own
+        // rank's mailbox (local memory) and adds the contributions in rank order, so all CTAs of all ranks continue
+        // with identical moments.  Two parities of slots suffice: a rank can push epoch e+2 only after every rank
+        // pushed e+1, i.e. after all their CTAs finished reading epoch e.
+        const PeerExchange &x = a.peer;
+        const unsigned long long seq = x.seq + (unsigned long long)(e_rel - 1);
+        const size_t par = (size_t)(seq & 1ull) * 8 * kMailSlot;
+        if (writer) {
+            for (int r = 0; r < x.world; ++r) {
+                volatile double *dst = x.mailbox[r] + par + (size_t)x.rank * kMailSlot;
+                for (int v = lane; v < TRB_MOMENTS; v += 32) dst[v] = mrow[v];
+            }
+            __threadfence_system();
+            __syncwarp();
+            if (lane < x.world) {
+                unsigned long long *flag = reinterpret_cast<unsigned long long *>(x.mailbox[lane] + par + (size_t)x.rank * kMailSlot + (kMailSlot - 1));
+                asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(seq) : "memory");
+            }
+        }
+        double *mine = x.mailbox[x.rank] + par;
+        volatile unsigned long long *poison = reinterpret_cast<volatile unsigned long long *>(x.mailbox[x.rank] + kMailPoison);
+        bool ok = *poison == 0ull;
+        if (ok && lane < x.world) {
+            const unsigned long long *flag = reinterpret_cast<const unsigned long long *>(mine + (size_t)lane * kMailSlot + (kMailSlot - 1));
+            unsigned long long got = 0;
+            long long spins = 0;
+            do {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(got) : "l"(flag) : "memory");
+                if (got != seq) __nanosleep(40);
+            } while (got != seq && ++spins < (1ll << 24));
+            ok = got == seq;
+        }
+        ok = __all_sync(kFull, ok);
+        if (!ok && lane == 0) *poison = 1ull;
+        for (int v = lane; v < TRB_MOMENTS; v += 32) {
+            double t = 0.0;
+            for (int r = 0; r < x.world; ++r) t += reinterpret_cast<volatile const double *>(mine)[(size_t)r * kMailSlot + v];
+            mrow[v] = ok ? t : __longlong_as_double(0x7ff8000000000000ll);
+        }
+        __syncwarp();
+    }
     const int epoch = a.epoch + e_rel - 1;
     const float loss = affine_epilogue_warp(mrow, a, epoch, st, reinterpret_cast<double *>(accw) /* words are consumed: scratch */, lane);
     if (lane == 0 && writer && a.loss_log) a.loss_log[(size_t)pair * a.log_stride + epoch] = loss;
@@ -754,7 +797,8 @@ void set_no_persist(bool v) { g_no_persist = v; }
 // enqueuing anything) when the configuration does not fit it; the caller then takes the per-epoch kernel.
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream)
 {
-    if (g_no_persist || a.peer.world > 1 || a.extra) return TRB_ERR_UNSUPPORTED;
+    if (g_no_persist || a.extra) return TRB_ERR_UNSUPPORTED;
+    if (a.peer.world > 1 && n_pairs != 1) return TRB_ERR_UNSUPPORTED;
     int dev = 0, sms = 0, coop = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return TRB_ERR_UNSUPPORTED;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -834,6 +878,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
             const int ne = min(chunk_cap, n_epochs - done);
             pp.n_epochs = ne;
             pp.t.a.epoch = epoch0 + done;
+            pp.t.a.peer.seq = a.peer.seq + (unsigned long long)done;
             e = cudaMemsetAsync(pp.acc, 0, (size_t)ne * np * kAccWords * sizeof(unsigned long long), stream);
             if (e != cudaSuccess) return check_cuda(e, "cudaMemsetAsync(accumulators)");
             cudaLaunchConfig_t cfg = {};

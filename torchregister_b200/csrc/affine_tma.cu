@@ -517,7 +517,9 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
     const bool mse_only = fused && a.w_ncc == 0.f;
     auto kf = mse_only ? affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, true> : affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, false>;
     auto ku = affine3d_tma_kernel<kBX, kBY, kBZ, kStages, false, false>;
-    static bool attr_set = false;
+    // the attribute is per device: keep one flag per device ordinal (a process may drive several GPUs)
+    static bool attr_set_dev[64] = {};
+    bool &attr_set = attr_set_dev[dev & 63];
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e == cudaSuccess) e = cudaFuncSetAttribute(affine3d_tma_kernel<kBX, kBY, kBZ, kStages, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -64,6 +64,23 @@ class PeerMailbox:
         self.seq += int(n)
         return s
 
+    def check(self):
+        """Raise if an in-kernel exchange gave up waiting for a peer (csrc/peer.cuh: bounded spin, then the moments
+        are poisoned with NaN and this word is set).  Synchronises the device; call it after the epochs of interest."""
+        poison = self.buf[2 * 8 * 48:2 * 8 * 48 + 1].view(torch.int64)
+        if int(poison.item()) != 0:
+            raise RuntimeError(
+                "peer exchange timed out on rank %d: a rank of the group did not reach the same epoch within the spin "
+                "budget (results from that epoch on are NaN). Re-create the sharded problem after fixing the skew." % self.rank)
+
+    def reset(self):
+        """Clear the poison word and the slots (collective: every rank, then a barrier)."""
+        torch.cuda.synchronize(self.buf.device)
+        self.buf.zero_()
+        torch.cuda.synchronize(self.buf.device)
+        dist.barrier()
+        self.seq = 1
+
 
 class ShardedAffine:
     """Rigid/affine registration of ONE large pair with the output volume split into slabs over the
@@ -96,15 +113,27 @@ class ShardedAffine:
                 if peer is True:
                     raise RuntimeError("fused sharded epoch unavailable: %s" % (self.peer_error or "another rank declined"))
 
-    def run(self, n_epochs, lr, w_mse, w_ncc, optimiser="sgd"):
+    def run(self, n_epochs, lr, w_mse, w_ncc, optimiser="sgd", check=False, align=True):
         if self.mailbox is not None:
+            if align:
+                # ranks may arrive here seconds apart (data loading, lazy module loads): line them up first, the
+                # in-kernel exchange only spins for a bounded time (align=False: the caller has just done so)
+                torch.cuda.current_stream(self.prob.device).synchronize()
+                dist.barrier(self.group)
             self.prob.run_peer(n_epochs, self.s_begin, self.s_end, self.mailbox.ptrs, self.rank, self.world,
                                self.mailbox.take(n_epochs), lr, w_mse, w_ncc, optimiser)
+            if check:
+                self.mailbox.check()
             return
         for _ in range(n_epochs):
             self.prob.moments(self.s_begin, self.s_end, out=self._mom)
             allreduce_moments(self._mom, self.group)
             self.prob.apply(self._mom, lr, w_mse, w_ncc, optimiser)
+
+    def check(self):
+        """Raise if the fused exchange timed out on a peer (see PeerMailbox.check)."""
+        if self.mailbox is not None:
+            self.mailbox.check()
 
     @property
     def final_theta(self):
@@ -225,6 +254,11 @@ class ShardedDirectFlow:
             m = self.prob.stats(smooth, self.halo_lo, self.halo_hi)
             allreduce_moments(m, self.group)
             self.prob.update(lr, w_mse, w_ncc, smooth, self.halo_lo, self.halo_hi, betas, eps)
+
+    def check(self):
+        """Raise if the fused exchange timed out on a peer (see PeerMailbox.check)."""
+        if self.mailbox is not None:
+            self.mailbox.check()
 
     @property
     def flow_slab(self):

@@ -138,10 +138,13 @@ class NMILoss(nn.Module):
         """CUDA kernels (csrc/nmi.cu) for one fp32 [1,1,...] pair with the default bins/patch; the target's resample
         and marginal are cached while the same target tensor comes back (every epoch of a registration)."""
         from . import functional as TF
-        key = (y.data_ptr(), y._version, tuple(y.shape), float(self.bandwidth), float(self.alpha))
-        if getattr(self, "_term_key", None) != key:
+        # The cache holds a REFERENCE to the target tensor and compares identity (+ in-place version): a different
+        # tensor that the caching allocator happens to place at the same address can therefore never hit it.
+        key = (y._version, tuple(y.shape), float(self.bandwidth), float(self.alpha))
+        if getattr(self, "_term_target", None) is not y or getattr(self, "_term_key", None) != key:
             self._term = TF.NmiTerm(y, self.bandwidth, self.alpha)
             self._term_key = key
+            self._term_target = y
         return self._term
 
     def forward(self, y, yp):
