@@ -1,10 +1,13 @@
 """TEST INFRASTRUCTURE — not product code.
 
-Imports the UNMODIFIED reference (AgamChopra/TorchRegister) from
-/root/reference so that (a) the restatements in this directory can be checked
-against it and (b) golden vectors can be generated (tests/golden/make_golden.py).
-/root/reference only exists in the build container, never on the GPU box:
-nothing under tests -m gpu, smoke() or bench.py may call `load()`.
+Imports the UNMODIFIED reference (AgamChopra/TorchRegister) so that (a) the
+restatements in this directory can be checked against it, (b) golden vectors can
+be generated (tests/golden/make_golden.py) and (c) bench.py can time the
+reference's own CPU path (`--impl reference`, `cpu_baseline.kind = "reference"`).
+Where it is found, in this order: $TRB_REFERENCE_ROOT, /root/reference (build
+container only) and baseline/_ref/ — the `pip install --target baseline/_ref`
+copy that __graft_entry__.build() makes (git-ignored, travels to the GPU box).
+The GPU parity tests and smoke() never call `load()`.
 
 Shim: the reference imports matplotlib (absent here) and uses
 absolute intra-package imports, so we stub matplotlib.pyplot and put
@@ -19,14 +22,30 @@ import os
 import sys
 import types
 
-REF_ROOT = os.environ.get("TRB_REFERENCE_ROOT", "/root/reference")
-REF_SRC = os.path.join(REF_ROOT, "src", "TorchRegister")
+_REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+_CANDIDATES = [os.path.join(os.environ["TRB_REFERENCE_ROOT"], "src", "TorchRegister")] if os.environ.get("TRB_REFERENCE_ROOT") else []
+_CANDIDATES += [os.path.join("/root/reference", "src", "TorchRegister"), os.path.join(_REPO, "baseline", "_ref", "TorchRegister")]
+
+
+def _find():
+    for c in _CANDIDATES:
+        if os.path.isfile(os.path.join(c, "torchregister.py")):
+            return c
+    return None
+
+
+REF_SRC = _find() or _CANDIDATES[0]
 
 captured_losses: list = []
 
 
 def available() -> bool:
-    return os.path.isfile(os.path.join(REF_SRC, "torchregister.py"))
+    return _find() is not None
+
+
+def source() -> str:
+    """Directory the reference is imported from (for reports)."""
+    return _find() or ""
 
 
 def _install_stubs():
@@ -50,11 +69,12 @@ def _install_stubs():
 
 def load():
     """Return (torchregister, warpings, utils) modules of the reference."""
-    if not available():
-        raise RuntimeError("reference not present at %s" % REF_SRC)
+    src = _find()
+    if src is None:
+        raise RuntimeError("reference not present (looked in %s)" % ", ".join(_CANDIDATES))
     _install_stubs()
-    if REF_SRC not in sys.path:
-        sys.path.insert(0, REF_SRC)
+    if src not in sys.path:
+        sys.path.insert(0, src)
     import torchregister as ref_api   # noqa: E402  (reference module names)
     import warpings as ref_warp       # noqa: E402
     import utils as ref_utils         # noqa: E402

@@ -10,11 +10,9 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 
-def main():
-    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    dist.init_process_group("nccl", device_id=dev)
+def run_checks(rank, world, dev):
+    """The checks proper; needs an initialised NCCL process group.  Returns the summary string (also used by
+    bench.py --gpus 2, which records it in its JSON line)."""
     import torchregister_b200.functional as TF
     from torchregister_b200.parallel import ShardedAffine, ShardedDirectFlow, shard_pairs
     from torchregister_b200.synth import make_pair, smooth_flow
@@ -66,8 +64,17 @@ def main():
     dist.all_reduce(out)
     assert torch.allclose(out, ref.final_theta, atol=2e-6)
     dist.barrier()
+    return "MGPU OK world=%d; sharded affine paths checked: %s" % (world, paths)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    msg = run_checks(rank, world, dev)
     if rank == 0:
-        print("MGPU OK world=%d; sharded affine paths checked: %s" % (world, paths))
+        print(msg)
     dist.destroy_process_group()
 
 
