@@ -112,6 +112,26 @@ int trb_affine_optim(int ndim, int mode,
                      int optimiser, float beta1, float beta2, float adam_eps,
                      void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* trb_affine_optim with option flags.  TRB_FLAG_LARGE_ROTATION selects, for 3-D shapes the persistent kernel accepts,
+ * its large-rotation variant: the moving volume is gathered through L1 by 8x4-voxel warp patches instead of being staged
+ * box by box with TMA — the right choice when theta rotates by more than a few degrees (e.g. the reference's own
+ * Regressor start, torch.rand(6) rad, utils.py:317), where the source footprint of an output tile no longer fits the
+ * staged box.  Same results either way (same arithmetic per voxel). */
+#define TRB_FLAG_LARGE_ROTATION 1
+int trb_affine_optim_ex(int ndim, int mode,
+                        const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs,
+                        int D, int H, int W,
+                        const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                        float *state_dev, float *loss_log_dev, int log_stride,
+                        int epoch0, int n_epochs,
+                        float w_mse, float w_ncc, float lr,
+                        int optimiser, float beta1, float beta2, float adam_eps, int flags,
+                        void *workspace_dev, size_t workspace_bytes, void *stream);
+
+/* Host-side helper for choosing that flag: 1 if the source footprint of a 32x16x8 output tile under `theta_host`
+ * (12 floats, HOST memory, row-major 3x4) fits the box the TMA-staged kernels fetch, else 0. */
+int trb_affine_tile_fits(int D, int H, int W, const float *theta_host);
+
 /* One volume sharded into z-slabs over up to 8 GPUs of one box, fused form (replaces the trb_affine_moments ->
  * all-reduce -> trb_affine_apply triple): n_epochs launches of the epoch kernel on slices [s_begin, s_end); the last
  * CTA of every rank pushes its 41 partial moments into every rank's mailbox with peer stores over NVLink, waits for

@@ -215,7 +215,56 @@ def case_flow_register(name, shape, n, lr, epochs, w_mse, w_ncc):
     save(name, **out)
 
 
+def case_long(name, shape, kind, stages, criterions, weights, eff_weights, p0, stub_nmi=False):
+    """Long-horizon run (round 2): the README schedule — rigid for stages[0] = (epochs, lr), then (3-D) affine for
+    stages[1] on the rigidly warped volume, README.md:59-71 — recorded per epoch in float32 and float64.  Inputs are
+    stored too (exact parity needs exact inputs); warped volumes are not (only the final loss/theta matter here)."""
+    mov, tgt = make_pair(shape, kind)
+    out = dict(moving=mov.numpy(), target=tgt.numpy(), weights=np.asarray(eff_weights, np.float64), p0=np.asarray(p0, np.float32))
+    for dtype, sfx in ((torch.float32, ""), (torch.float64, "_f64")):
+        cur = mov
+        for si, (mode, epochs, lr) in enumerate(stages):
+            crit = None if criterions is None else [nn.MSELoss()]
+            r = run_affine_like(mode, cur, tgt, lr, epochs, crit, weights, p0 if mode == "rigid" else None, dtype, stub_nmi, None)
+            out["s%d_losses%s" % (si, sfx)] = r["losses"]
+            out["s%d_final_theta%s" % (si, sfx)] = r["final_theta"]
+            out["s%d_best_theta%s" % (si, sfx)] = r["best_theta"]
+            # the README feeds `warping(moving)` = warp with Register.theta (the BEST theta) to the next stage
+            cur = torch.from_numpy(r["best_warped"]).to(torch.float32)
+            if sfx == "":
+                out["s%d_best_warped" % si] = r["best_warped"].astype(np.float32)
+            print(name, sfx or "_f32", "stage", si, mode, "loss %.6g -> %.6g (min %.6g)" % (r["losses"][0], r["losses"][-1], r["losses"].min()), flush=True)
+    out["stages"] = np.array([[0 if m == "rigid" else 1, e, lr] for m, e, lr in stages], np.float64)
+    save(name, **out)
+
+
+def main_round2(which):
+    """Round-2 goldens: 3-D cases at a shape the TMA-staged kernels accept (W >= 32, W % 4 == 0, H >= 16), with partial
+    tiles in every axis, and long-horizon runs."""
+    p3 = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02])
+    p2 = torch.tensor([0.03, 0.02, -0.01])
+    ST = (20, 32, 48)
+    if which in ("all", "tma"):
+        case_affine_like("rigid3d_tma_ncc", ST, "rigid", "rigid", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0], p3, stub_nmi=True)
+        case_affine_like("rigid3d_tma_mix", ST, "rigid", "rigid", 1e-4, 12, None, [0.5, 0.5, 0.0], [.5, .5, 0], p3, stub_nmi=True)
+        case_affine_like("rigid3d_tma_mse", ST, "rigid", "rigid", 5e-2, 12, [nn.MSELoss()], [1.0], [1, 0, 0], p3)
+        case_affine_like("affine3d_tma_ncc", ST, "affine", "affine", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0], stub_nmi=True)
+        case_affine_like("affine3d_tma_mix", ST, "affine", "affine", 1e-4, 12, None, [0.5, 0.5, 0.0], [.5, .5, 0], stub_nmi=True)
+        case_affine_like("rigid3d_tma_rand", ST, "rigid", "rigid", 1e-4, 8, None, [0.0, 1.0, 0.0], [0, 1, 0], None, stub_nmi=True, seed=0)
+    if which in ("all", "long3d"):
+        case_long("long3d_rigid_affine", (48, 64, 64), "affine", [("rigid", 500, 1e-3), ("affine", 200, 1e-3)], None, [0.0, 1.0, 0.0],
+                  [0, 1, 0], p3, stub_nmi=True)
+    if which in ("all", "long2d"):
+        case_long("long2d_rigid_mse", (256, 256), "rigid", [("rigid", 500, 5e-2)], [nn.MSELoss()], [1.0], [1, 0, 0], p2)
+    if which in ("all", "long2d_default"):
+        # BASELINE configs[0] as written: 2-D rigid 256x256, 500 epochs, the reference's DEFAULT loss incl. its real NMI term
+        case_long("long2d_rigid_default", (256, 256), "rigid", [("rigid", 500, 1e-5)], None, None, [.33, .33, .33], p2)
+
+
 def main():
+    if len(sys.argv) > 1 and sys.argv[1] == "round2":
+        main_round2(sys.argv[2] if len(sys.argv) > 2 else "all")
+        return
     if len(sys.argv) > 1 and sys.argv[1] == "flowreg":
         case_flow_register("flowreg2d", (160, 168), 32, 1e-3, 3, 0.5, 0.5)
         return

@@ -1,0 +1,60 @@
+"""Large-rotation (L1-gather) variant of the persistent kernel: parity against the TMA variant / direct kernel and timing."""
+import sys, torch
+sys.path.insert(0, ".")
+import torchregister_b200.functional as TF
+from torchregister_b200.synth import make_pair
+dev = torch.device("cuda:0")
+
+def run(shape, p0, epochs, w, large, path="auto", n_pairs=1, lr=1e-3):
+    TF.set_kernel_path(path)
+    movs, tgts = [], []
+    for i in range(n_pairs):
+        m, t = make_pair(shape, "rigid", seed=77 + i, device=dev)
+        movs.append(m); tgts.append(t)
+    mov, tgt = torch.cat(movs).contiguous(), torch.cat(tgts).contiguous()
+    prob = TF.AffineProblem(mov, tgt, "rigid", p0.to(dev).repeat(n_pairs, 1), epochs, large_rotation=large)
+    prob.run(epochs, lr, w[0], w[1])
+    torch.cuda.synchronize()
+    TF.set_kernel_path("auto")
+    return prob.losses.cpu().double(), prob.final_theta.cpu().double(), prob.flags
+
+torch.manual_seed(0)
+rand0 = torch.rand(6)
+small = torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02])
+ok = True
+for shape, p0, n in (((40, 48, 64), rand0, 1), ((37, 50, 36), rand0, 3), ((64, 64, 96), small, 2), ((33, 47, 64), torch.tensor([0.3, -0.2, 0.25, 0.1, 0.0, -0.1]), 1)):
+    for w in ((0.5, 0.5), (1.0, 0.0)):
+        g = run(shape, p0, 6, w, True, n_pairs=n)
+        a = run(shape, p0, 6, w, None, n_pairs=n)
+        d = run(shape, p0, 6, w, False, "direct", n_pairs=n)
+        rl = ((g[0] - d[0]).abs() / d[0].abs().clamp_min(1e-30)).max().item()
+        rt = (g[1] - d[1]).abs().max().item()
+        ra = ((g[0] - a[0]).abs() / a[0].abs().clamp_min(1e-30)).max().item()
+        good = rl < 1e-4 and rt < 5e-6
+        ok &= good
+        print(shape, n, w, "auto flags", a[2], "| gather vs direct: loss %.2e theta %.2e | gather vs auto: %.2e %s" % (rl, rt, ra, "OK" if good else "FAIL"), flush=True)
+print("ROT PARITY", "OK" if ok else "FAIL")
+
+def timeit(shape, p0, large, epochs=100, n_pairs=1, w=(0.0, 1.0)):
+    movs, tgts = [], []
+    for i in range(n_pairs):
+        m, t = make_pair(shape, "affine", seed=1234 + i, device=dev)
+        movs.append(m); tgts.append(t)
+    mov, tgt = torch.cat(movs).contiguous(), torch.cat(tgts).contiguous()
+    prob = TF.AffineProblem(mov, tgt, "rigid", p0.to(dev).repeat(n_pairs, 1), 10 + epochs, large_rotation=large)
+    prob.run(10, 1e-5, *w)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); prob.run(epochs, 1e-5, *w); e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) * 1e3 / epochs
+
+deg = 3.14159265 / 180
+for name, p0 in (("small", small), ("rand(6) seed 0", rand0), ("10 deg z", torch.tensor([0., 10 * deg, 0., 0., 0., 0.])), ("45 deg z", torch.tensor([0., 45 * deg, 0., 0., 0., 0.])),
+                 ("30/30/30 deg", torch.tensor([30 * deg, 30 * deg, 30 * deg, 0.1, 0.1, 0.1]))):
+    for large in (False, True):
+        us = timeit((256, 256, 256), p0, large)
+        print("256^3 %-16s %s %.1f us/epoch" % (name, "gather" if large else "tma   ", us), flush=True)
+for large in (False, True):
+    us = timeit((192, 192, 160), rand0, large, n_pairs=8)
+    print("batch8 rand(6) %s %.1f us/epoch" % ("gather" if large else "tma   ", us), flush=True)

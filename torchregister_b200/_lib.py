@@ -24,6 +24,9 @@ _SIGNATURES = {
     "trb_affine_init_state": (_i, [_i, _i, c_fp, _i, c_fp]),
     "trb_affine_optim": (_i, [_i, _i, c_fp, c_fp, _ll, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i,
                               _i, _i, _f, _f, _f, _i, _f, _f, _f, c_fp, _sz, c_fp]),
+    "trb_affine_optim_ex": (_i, [_i, _i, c_fp, c_fp, _ll, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i,
+                                 _i, _i, _f, _f, _f, _i, _f, _f, _f, _i, c_fp, _sz, c_fp]),
+    "trb_affine_tile_fits": (_i, [_i, _i, _i, C.POINTER(C.c_float)]),
     "trb_affine_moments": (_i, [_i, c_fp, c_fp, _ll, _i, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp,
                                 c_fp, _sz, c_fp]),
     "trb_affine_apply": (_i, [_i, _i, c_fp, _i, _i, _i, _i, c_fp, c_fp, _i, _i, _f, _f, _f, _i, _f, _f, _f, c_fp, c_fp]),

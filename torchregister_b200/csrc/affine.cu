@@ -16,6 +16,7 @@
 // target 4), everything else is O(1) per pair.
 #include "common.cuh"
 #include "affine_shared.cuh"
+#include "affine_tile.cuh"
 #include <math.h>
 
 namespace trb {
@@ -368,12 +369,41 @@ static int fill_params(AffineParams &p, int ndim, const float *moving, const flo
     return TRB_OK;
 }
 
+extern "C" int trb_affine_tile_fits(int D, int H, int W, const float *theta_host)
+{
+    // the footprint test of the producer (csrc/affine_persist.cu) for the tile at the centre of the volume, on the host
+    if (!theta_host || D < 1 || H < 1 || W < 1) return 0;
+    const double h[3] = {0.5 * W, 0.5 * H, 0.5 * D};
+    const double T[3] = {(double)(TX < W ? TX : W), (double)(TY < H ? TY : H), (double)(TZ < D ? TZ : D)};
+    const double step[3] = {2.0 / W, 2.0 / H, 2.0 / D};          // base coordinate per voxel
+    const int B[3] = {kBX, kBY, kBZ};
+    for (int r = 0; r < 3; ++r) {
+        double ext = 0.0;
+        for (int c = 0; c < 3; ++c) ext += fabs((double)theta_host[r * 4 + c]) * h[r] * step[c] * (T[c] - 1.0);
+        const double need = ext + 2.06 + (r == 0 ? 3.0 : 0.0);   // + the cell's far corner, + 16-byte alignment of the box start in x
+        if (need > (double)B[r] - 1.0) return 0;
+    }
+    return 1;
+}
+
 extern "C" int trb_affine_optim(int ndim, int mode, const float *moving_dev, const float *target_dev,
                                 long long pair_stride, int n_pairs, int D, int H, int W,
                                 const float *xb_dev, const float *yb_dev, const float *zb_dev,
                                 float *state_dev, float *loss_log_dev, int log_stride, int epoch0, int n_epochs,
                                 float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2,
                                 float adam_eps, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    return trb_affine_optim_ex(ndim, mode, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev, state_dev,
+                               loss_log_dev, log_stride, epoch0, n_epochs, w_mse, w_ncc, lr, optimiser, beta1, beta2, adam_eps,
+                               0, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int trb_affine_optim_ex(int ndim, int mode, const float *moving_dev, const float *target_dev,
+                                   long long pair_stride, int n_pairs, int D, int H, int W,
+                                   const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                   float *state_dev, float *loss_log_dev, int log_stride, int epoch0, int n_epochs,
+                                   float w_mse, float w_ncc, float lr, int optimiser, float beta1, float beta2,
+                                   float adam_eps, int flags, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     AffineParams p{};
     int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
@@ -387,6 +417,7 @@ extern "C" int trb_affine_optim(int ndim, int mode, const float *moving_dev, con
     p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride;
     p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
+    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
         if (n_epochs <= 0) return TRB_OK;

@@ -72,7 +72,8 @@ struct PersistParams {
 };
 
 using PL = SmemLayout<kBX, kBY, kBZ>;
-constexpr size_t kOffBars = (size_t)kStages * PL::kStageBytes;
+// the small arrays come first, the TMA ring last: its stage size depends on the kernel variant
+constexpr size_t kOffBars = 0;
 constexpr size_t kOffTiles = kOffBars + 24 * sizeof(uint64_t);
 constexpr size_t kOffCols = kOffTiles + kStages * sizeof(PTile);
 constexpr size_t kOffRed = kOffCols + kColSlots * sizeof(PCol);
@@ -80,8 +81,15 @@ constexpr size_t kOffState = kOffRed + 2 * kConsumerWarps * kRedLdP * sizeof(flo
 constexpr size_t kOffAccw = kOffState + kStateSlots * TRB_STATE_FLOATS * sizeof(float);
 constexpr size_t kOffMrow = kOffAccw + kAccWords * sizeof(unsigned long long);
 constexpr size_t kOffCoefq = kOffMrow + 48 * sizeof(double);
-constexpr size_t kPersistSmem = kOffCoefq + kCoefSlots * 12 * sizeof(float);
-static_assert(kPersistSmem <= 232448, "persistent kernel: shared memory budget");
+constexpr size_t kOffStages = (kOffCoefq + kCoefSlots * 12 * sizeof(float) + 1023) / 1024 * 1024;
+// ROT = false: a stage is the staged box of the moving volume + the target tile (TMA-staged variant);
+// ROT = true : the target tile only — the moving volume is gathered through L1 (large-rotation variant, below)
+template <bool ROT> struct Ring {
+    static constexpr size_t kTgtOff = ROT ? 0 : (size_t)PL::kBoxFloats * 4;
+    static constexpr size_t kStageBytes = ROT ? (size_t)PL::kTgtFloats * 4 : (size_t)PL::kStageBytes;
+    static constexpr size_t kSmem = kOffStages + kStages * kStageBytes;
+};
+static_assert(Ring<false>::kSmem <= 232448, "persistent kernel: shared memory budget");
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {
@@ -378,7 +386,12 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
     PT_ADD(3, te0);
 }
 
-template <bool MSE_ONLY>
+// ROT (large rotations, e.g. the reference's own torch.rand(6) start, utils.py:317): the source footprint of a 32x16x8
+// tile is a rotated box whose axis-aligned hull is 4-9x the tile, so staging it by TMA does not pay (the TMA variant
+// then falls back to uncached global gathers, 5.5x slower).  This variant stages only the target tile (64 KB of shared
+// memory instead of 219 KB, which leaves ~128 KB of L1), maps a warp onto an 8x4 (x,y) patch instead of a 32-voxel row —
+// the 8 corner loads of a patch touch a compact source region — and gathers the moving volume through L1.
+template <bool MSE_ONLY, bool ROT>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensorMap map_mov,
                         const __grid_constant__ CUtensorMap map_tgt)
@@ -469,7 +482,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                     if (lane == 0) {
                         // footprint of this tile -> box origin / fits (issue_tile of affine_tile.cuh with the extra stream fields)
                         int o[3];
-                        bool fits = true;
+                        bool fits = !ROT;
                         const int B[3] = {kBX, kBY, kBZ};
                         const float kfz = (float)t.tz_i;
 #pragma unroll
@@ -489,11 +502,11 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                         m.nz = min(TZ, p.a.s_end - z0);
                         m.colslot = k % kColSlots;
                         tiles[stage] = m;
-                        unsigned char *stg = smem_raw + (size_t)stage * PL::kStageBytes;
+                        unsigned char *stg = smem_raw + kOffStages + (size_t)stage * Ring<ROT>::kStageBytes;
                         const unsigned tgt_bytes = PL::kTgtFloats * 4, box_bytes = PL::kBoxFloats * 4;
                         mbar_arrive_expect_tx(full_bar + stage, fits ? (tgt_bytes + box_bytes) : tgt_bytes);
                         if (fits) tma_load_4d(stg, &map_mov, full_bar + stage, o[0], o[1], o[2], c.pair);
-                        tma_load_4d(stg + PL::kBoxFloats * 4, &map_tgt, full_bar + stage, c.x0, c.y0, z0, c.pair);
+                        tma_load_4d(stg + Ring<ROT>::kTgtOff, &map_tgt, full_bar + stage, c.x0, c.y0, z0, c.pair);
                     }
                     __syncwarp();
                     if (moved) ++k;
@@ -651,7 +664,8 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
         if (m.flags & kEnd) break;
         if (m.flags & kNewCol) {
             const PCol &pc = cols[m.colslot];
-            x = pc.x0 + lane; y = pc.y0 + warp;
+            x = pc.x0 + (ROT ? 8 * (warp & 3) + (lane & 7) : lane);
+            y = pc.y0 + (ROT ? 4 * (warp >> 2) + (lane >> 3) : warp);
             valid = (x < W) && (y < H);
             xv = __ldg(p.a.xb + min(x, W - 1)); yv = __ldg(p.a.yb + min(y, H - 1));
 #pragma unroll
@@ -666,12 +680,13 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             if (lane == 0 && warp == 0) { g_pdbg[blockIdx.x * 32 + 12] += gtime() - ts0; }
 #endif
         }
-        unsigned char *stg = smem_raw + (size_t)stage * PL::kStageBytes;
+        unsigned char *stg = smem_raw + kOffStages + (size_t)stage * Ring<ROT>::kStageBytes;
         const uint32_t box_addr = smem_u32(stg);
-        const uint32_t tg = box_addr + PL::kBoxFloats * 4 + (uint32_t)(warp * TX + lane) * 4u;
+        const uint32_t tg = box_addr + (uint32_t)Ring<ROT>::kTgtOff +
+                            (uint32_t)(ROT ? (4 * (warp >> 2) + (lane >> 3)) * TX + 8 * (warp & 3) + (lane & 7) : warp * TX + lane) * 4u;
         const int nz = m.nz;
         if (valid) {
-            if (m.flags & kFits) {
+            if (!ROT && (m.flags & kFits)) {
                 const float Mrel = m.Mrel;
                 const float zf0 = m.zf0;
                 if (nz == TZ) {
@@ -704,6 +719,14 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                         if (second) pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                         else pair_step2<kBX, kBY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                     }
+                }
+            } else if (ROT) {
+                // gathers through L1; several z steps in flight per thread
+#pragma unroll 4
+                for (int zz = 0; zz < nz; ++zz) {
+                    const float zf = m.zf0 + (float)zz;
+                    voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
+                                           lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
                 }
             } else {
                 for (int zz = 0; zz < nz; ++zz) {
@@ -805,7 +828,10 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop || sms < 1) return TRB_ERR_UNSUPPORTED;
     const bool mse_only = a.w_ncc == 0.f;
-    auto kern = mse_only ? affine3d_persist_kernel<true> : affine3d_persist_kernel<false>;
+    const bool rot = a.gather != 0;
+    auto kern = rot ? (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>)
+                    : (mse_only ? affine3d_persist_kernel<true, false> : affine3d_persist_kernel<false, false>);
+    const size_t kPersistSmem = rot ? Ring<true>::kSmem : Ring<false>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersistSmem);
     if (e != cudaSuccess) { cudaGetLastError(); return TRB_ERR_UNSUPPORTED; }
     int occ = 0;

@@ -36,6 +36,7 @@ struct AffineParams {
     float beta1, beta2, adam_eps;
     const double *extra;         // optional [n_pairs][13]: extra loss term and its d/dtheta (e.g. the NMI term), or NULL
     int extra_pair;              // row of `extra` (set by the epilogue wrappers)
+    int gather;                  // 1: large-rotation variant of the persistent kernel (L1 gathers instead of TMA-staged boxes)
     PeerExchange peer;
 };
 

@@ -86,7 +86,7 @@ class AffineProblem:
     of equally shaped volume pairs (one fused launch per epoch covers the batch)."""
 
     def __init__(self, moving: torch.Tensor, target: torch.Tensor, mode: str, params0: torch.Tensor,
-                 max_epochs: int):
+                 max_epochs: int, large_rotation: Optional[bool] = None):
         require_cuda(moving, "moving")
         require_cuda(target, "target")
         if moving.shape != target.shape:
@@ -123,6 +123,34 @@ class AffineProblem:
         with torch.cuda.device(self.device):
             check(self.lib.trb_affine_init_state(self.ndim, MODE[mode], self.state.data_ptr(), self.n_pairs,
                                                  _stream(self.device)), "affine_init_state")
+        # Kernel variant for the fused 3-D loop: TMA-staged boxes when the start theta keeps an output tile's source
+        # footprint inside the staged box (rotations up to ~5 degrees), the L1-gather variant otherwise (e.g. the
+        # reference's own torch.rand(6) start).  Decided ONCE from the initial parameters (one small D2H read if they
+        # live on the device); both variants compute the same values.
+        self.flags = 0
+        if self.ndim == 3:
+            if large_rotation is None:
+                large_rotation = self._start_needs_gather(p0)
+            self.flags = 1 if large_rotation else 0
+
+    def _start_needs_gather(self, p0: torch.Tensor) -> bool:
+        import ctypes as C
+        ph = p0.detach().to("cpu", torch.float64)
+        if self.mode == "rigid":
+            c, s_, t = torch.cos(ph[:, :3]), torch.sin(ph[:, :3]), 0.25 * torch.tanh(ph[:, 3:6])
+            cps, cth, cph = c[:, 0], c[:, 1], c[:, 2]
+            sps, sth, sph = s_[:, 0], s_[:, 1], s_[:, 2]
+            th = torch.stack([cps * cth, sph * sps * cth - cph * sth, cph * sps * cth + sph * sth, t[:, 0],
+                              cps * sth, sph * sps * sth + cph * cth, cph * sps * sth - sph * cth, t[:, 1],
+                              -sps, sph * cps, cph * cps, t[:, 2]], dim=1)          # utils.py:290-305
+        else:
+            th = ph
+        th = th.to(torch.float32).contiguous()
+        misfit = 0
+        for i in range(th.shape[0]):
+            row = (C.c_float * 12)(*th[i].tolist())
+            misfit += 0 if self.lib.trb_affine_tile_fits(self.D, self.H, self.W, row) else 1
+        return 2 * misfit > th.shape[0]
 
     def run(self, n_epochs: int, lr: float, w_mse: float, w_ncc: float, optimiser: str = "sgd",
             betas=(0.9, 0.999), eps: float = 1e-8) -> None:
@@ -132,12 +160,12 @@ class AffineProblem:
         if self.epoch + n_epochs > self.max_epochs:
             raise ValueError("max_epochs exceeded")
         with torch.cuda.device(self.device):
-            check(self.lib.trb_affine_optim(
+            check(self.lib.trb_affine_optim_ex(
                 self.ndim, MODE[self.mode], self.moving.data_ptr(), self.target.data_ptr(), self.pair_stride,
                 self.n_pairs, self.D, self.H, self.W, self.xb.data_ptr(), self.yb.data_ptr(), _ptr(self.zb),
                 self.state.data_ptr(), self.loss_log.data_ptr(), self.loss_log.shape[1], self.epoch, n_epochs,
                 float(w_mse), float(w_ncc), float(lr), OPT[optimiser], float(betas[0]), float(betas[1]), float(eps),
-                self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "affine_optim")
+                int(self.flags), self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "affine_optim")
         self.epoch += n_epochs
 
     # -- sharded (z-slab) form, fused: the epoch kernel all-reduces the moments itself through peer memory
