@@ -252,7 +252,7 @@ def main_round2(which):
         case_affine_like("affine3d_tma_mix", ST, "affine", "affine", 1e-4, 12, None, [0.5, 0.5, 0.0], [.5, .5, 0], stub_nmi=True)
         case_affine_like("rigid3d_tma_rand", ST, "rigid", "rigid", 1e-4, 8, None, [0.0, 1.0, 0.0], [0, 1, 0], None, stub_nmi=True, seed=0)
     if which in ("all", "long3d"):
-        case_long("long3d_rigid_affine", (48, 64, 64), "affine", [("rigid", 500, 1e-3), ("affine", 200, 1e-3)], None, [0.0, 1.0, 0.0],
+        case_long("long3d_rigid_affine", (40, 64, 64), "affine", [("rigid", 500, 1e-3), ("affine", 200, 1e-3)], None, [0.0, 1.0, 0.0],
                   [0, 1, 0], p3, stub_nmi=True)
     if which in ("all", "long2d"):
         case_long("long2d_rigid_mse", (256, 256), "rigid", [("rigid", 500, 5e-2)], [nn.MSELoss()], [1.0], [1, 0, 0], p2)

@@ -10,6 +10,11 @@ from oracle import torch_port as tp
 
 AFFINE_LIKE = ["rigid3d_mse", "rigid2d_mse", "rigid3d_ncc", "rigid2d_ncc", "rigid3d_mix", "rigid3d_rand",
                "rigid2d_rand", "affine3d_ncc", "affine3d_mix", "affine2d_mse", "affine2d_ncc"]
+# round 2: 3-D cases at 20x32x48 — a shape the TMA-staged kernels accept (W >= 32, W % 4 == 0, H >= 16), partial tiles
+# in every axis — so that the production kernels are compared with reference-recorded vectors directly
+AFFINE_LIKE_TMA = ["rigid3d_tma_ncc", "rigid3d_tma_mix", "rigid3d_tma_mse", "affine3d_tma_ncc", "affine3d_tma_mix",
+                   "rigid3d_tma_rand"]
+AFFINE_LIKE = AFFINE_LIKE + AFFINE_LIKE_TMA
 
 
 LATTICE_RTOL = 3e-3
@@ -179,3 +184,34 @@ def test_flow_register_port_matches_reference():
                                        lambda t, y: tp.weighted_loss(t, y, (w[0], w[1], 0.0)))
     assert _rel(losses, g["losses"]) < 1e-5
     assert np.abs(flow.numpy() - g["flow"]).max() <= 1e-5 * np.abs(g["flow"]).max()
+
+
+# --------------------------------------------------------------------------------------------
+# long horizons (round 2): the README schedule recorded from the unmodified reference
+# --------------------------------------------------------------------------------------------
+def _stage_ok(new_losses, g, si, rtol=1e-4):
+    return _loss_ok(new_losses, g["s%d_losses" % si], g["s%d_losses_f64" % si], rtol)
+
+
+def test_long2d_c_oracle_matches_reference():
+    """2-D rigid 256x256, 500 epochs (BASELINE configs[0] with the reference's MSE branch): per-epoch loss and theta."""
+    g = load_golden("long2d_rigid_mse")
+    r = co.affine_loop(g["moving"].astype(np.float64), g["target"].astype(np.float64), "rigid", g["p0"].astype(np.float64),
+                       float(g["stages"][0, 2]), int(g["stages"][0, 1]), 1.0, 0.0)
+    ok, worst = _stage_ok(r["losses"], g, 0)
+    assert ok, worst
+    ref = g["s0_final_theta_f64"].reshape(2, 3)
+    assert np.abs(r["final_theta"] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_long3d_c_oracle_matches_reference():
+    """3-D README schedule at 40x64x64: 500 rigid epochs (NCC), then 200 affine epochs on the rigidly warped volume."""
+    g = load_golden("long3d_rigid_affine")
+    mov, tgt = g["moving"].astype(np.float64), g["target"].astype(np.float64)
+    r = co.affine_loop(mov, tgt, "rigid", g["p0"].astype(np.float64), float(g["stages"][0, 2]), int(g["stages"][0, 1]), 0.0, 1.0)
+    ok, worst = _stage_ok(r["losses"], g, 0)
+    assert ok, worst
+    ref = g["s0_final_theta_f64"].reshape(3, 4)
+    assert np.abs(r["final_theta"] - ref).max() <= 1e-4 * np.abs(ref).max()
+    warped = co.warp_affine(g["moving"], g["s0_best_theta"].astype(np.float32))
+    assert np.abs(warped - g["s0_best_warped"].reshape(warped.shape)).max() < 1e-5

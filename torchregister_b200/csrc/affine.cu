@@ -40,6 +40,7 @@ __global__ void __launch_bounds__(kThreads, 2) affine_moments_kernel(const Affin
         for (int i = 0; i < NT; ++i) th[i] = __ldcg(st + i);
     }
     const float hw = 0.5f * W, hh = 0.5f * H, hd = 0.5f * D;
+    const bool mse_only = FUSED && p.w_ncc == 0.f;
     // i_r(x) = a_r * xb[x] + b_r(row): affine_grid, then ((g+1)*S-1)/2 folded in
     const float ax = th[0] * hw, ay = th[NC] * hh, az = NDIM == 3 ? th[2 * NC] * hd : 0.f;
 
@@ -146,6 +147,13 @@ __global__ void __launch_bounds__(kThreads, 2) affine_moments_kernel(const Affin
                 G[0] = fmaf(ty, d1 - d0, d0);
             }
             if (act) {
+                // w_ncc == 0 (the reference's "criterion given -> MSE" branch): accumulate d = w - t instead of t and w.
+                // MSE = sum d^2 / n then needs no (sum t^2 - 2 sum t w + sum w^2) cancellation, which costs 3 digits once
+                // the images agree to 1e-3 (500-epoch golden); the epilogue sees (t, w) = (0, d): loss and gradient are
+                // the same expressions.
+                const float tt = mse_only ? 0.f : t;
+                if (mse_only) val -= t;
+                const float t = tt;
                 s0 += t; s1 += val;
                 s2 = fmaf(t, t, s2); s3 = fmaf(val, val, s3); s4 = fmaf(t, val, s4);
 #pragma unroll
