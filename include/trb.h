@@ -42,6 +42,7 @@ extern "C" {
 #define TRB_MODE_AFFINE 1  /* params = theta itself (12 | 6 floats), warpings.py:42-55 */
 #define TRB_OPT_SGD 0      /* torch.optim.SGD(lr), warpings.py:58,131,192 */
 #define TRB_OPT_ADAM 1     /* extension (north_star item 3); no reference counterpart */
+#define TRB_FLAG_LARGE_ROTATION 1   /* trb_affine_optim_ex / trb_warp_affine_batch: see there */
 
 /* Per-pair optimiser state: TRB_STATE_FLOATS fp32 values, device resident.
  *   [ 0..11] params        (rigid: 6|3 used, affine: 12|6 used)
@@ -117,7 +118,6 @@ int trb_affine_optim(int ndim, int mode,
  * box by box with TMA — the right choice when theta rotates by more than a few degrees (e.g. the reference's own
  * Regressor start, torch.rand(6) rad, utils.py:317), where the source footprint of an output tile no longer fits the
  * staged box.  Same results either way (same arithmetic per voxel). */
-#define TRB_FLAG_LARGE_ROTATION 1
 int trb_affine_optim_ex(int ndim, int mode,
                         const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs,
                         int D, int H, int W,
@@ -174,6 +174,13 @@ int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs,
 int trb_warp_affine(int ndim, const float *moving_dev, float *out_dev, int n_channels,
                     int D, int H, int W, const float *theta_dev,
                     const float *xb_dev, const float *yb_dev, const float *zb_dev, void *stream);
+
+/* The same for a batch: n_pairs pairs of n_channels volumes each ([n_pairs][n_channels][D][H][W] contiguous), theta_dev
+ * [n_pairs][12|6], ONE launch.  3-D shapes with W % 4 == 0, W >= 32, H >= 16 take the TMA-staged kernel (csrc/warp_tma.cu);
+ * flags: TRB_FLAG_LARGE_ROTATION = theta is known to rotate by more than a few degrees (gather kernel instead). */
+int trb_warp_affine_batch(int ndim, const float *moving_dev, float *out_dev, int n_pairs, int n_channels,
+                          int D, int H, int W, const float *theta_dev,
+                          const float *xb_dev, const float *yb_dev, const float *zb_dev, int flags, void *stream);
 
 /* Vector-Jacobian product of the affine warp with respect to theta:
  * dtheta[12|6] (fp64, dev) = sum_v gout_v * d warped_v / d theta.

@@ -31,6 +31,7 @@ _SIGNATURES = {
                                 c_fp, _sz, c_fp]),
     "trb_affine_apply": (_i, [_i, _i, c_fp, _i, _i, _i, _i, c_fp, c_fp, _i, _i, _f, _f, _f, _i, _f, _f, _f, c_fp, c_fp]),
     "trb_warp_affine": (_i, [_i, c_fp, c_fp, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),
+    "trb_warp_affine_batch": (_i, [_i, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, _i, c_fp]),
     "trb_warp_affine_vjp": (_i, [_i, c_fp, c_fp, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
     "trb_flow_workspace_bytes": (_sz, []),
     "trb_warp_flow": (_i, [_i, c_fp, c_fp, c_fp, _i, _i, _i, _i, c_fp]),

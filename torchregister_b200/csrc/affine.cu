@@ -228,10 +228,14 @@ __global__ void __launch_bounds__(256) warp_affine_kernel(const float *__restric
                                                            const float *__restrict__ zb)
 {
     constexpr int NC = NDIM + 1, NT = NDIM * NC;
+    const size_t HW = (size_t)H * W, vol = HW * (NDIM == 3 ? D : 1);
+    // blockIdx.y: pair of a batch (its own theta, its own n_channels volumes)
+    theta += (size_t)blockIdx.y * NT;
+    moving += (size_t)blockIdx.y * n_channels * vol;
+    out += (size_t)blockIdx.y * n_channels * vol;
     float th[NT];
 #pragma unroll
     for (int i = 0; i < NT; ++i) th[i] = __ldg(theta + i);
-    const size_t HW = (size_t)H * W, vol = HW * (NDIM == 3 ? D : 1);
     const float hw = 0.5f * W, hh = 0.5f * H, hd = 0.5f * D;
     for_each_voxel<2>(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
         const float xv = __ldg(xb + x), yv = __ldg(yb + y);
@@ -528,18 +532,32 @@ extern "C" int trb_warp_affine(int ndim, const float *moving_dev, float *out_dev
                                const float *theta_dev, const float *xb_dev, const float *yb_dev, const float *zb_dev,
                                void *stream)
 {
-    int rc = validate_common(ndim, 1, D, H, W);
+    return trb_warp_affine_batch(ndim, moving_dev, out_dev, 1, n_channels, D, H, W, theta_dev, xb_dev, yb_dev, zb_dev, 0, stream);
+}
+
+extern "C" int trb_warp_affine_batch(int ndim, const float *moving_dev, float *out_dev, int n_pairs, int n_channels, int D, int H, int W,
+                                     const float *theta_dev, const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                     int flags, void *stream)
+{
+    int rc = validate_common(ndim, n_pairs, D, H, W);
     if (rc) return rc;
     if (!moving_dev || !out_dev || !theta_dev || !xb_dev || !yb_dev || (ndim == 3 && !zb_dev) || n_channels < 1) {
         set_error("null pointer / n_channels"); return TRB_ERR_ARG;
     }
+    if (n_pairs > 65535) { set_error("at most 65535 pairs per call"); return TRB_ERR_ARG; }
     const size_t vol = (size_t)(ndim == 3 ? D : 1) * H * W;
+    cudaStream_t s = (cudaStream_t)stream;
+    // 3-D: TMA-staged tiles unless the caller knows theta is a large rotation (then the gathers of the one-thread-per-
+    // voxel kernel, which keeps the whole L1, are the better path)
+    if (ndim == 3 && !g_force_direct && !(flags & TRB_FLAG_LARGE_ROTATION) &&
+        warp_tma_eligible(moving_dev, out_dev, n_pairs * n_channels, (long long)vol, D, H, W))
+        return launch_warp_affine_tma(moving_dev, out_dev, n_pairs, n_channels, D, H, W, theta_dev, xb_dev, yb_dev, s);
     const int sms = sm_count();
     size_t nb = (vol + 255) / 256;
     if (nb > (size_t)sms * 16) nb = (size_t)sms * 16;
-    cudaStream_t s = (cudaStream_t)stream;
-    if (ndim == 3) warp_affine_kernel<3><<<(unsigned)nb, 256, 0, s>>>(moving_dev, out_dev, n_channels, D, H, W, theta_dev, xb_dev, yb_dev, zb_dev);
-    else warp_affine_kernel<2><<<(unsigned)nb, 256, 0, s>>>(moving_dev, out_dev, n_channels, 1, H, W, theta_dev, xb_dev, yb_dev, zb_dev);
+    const dim3 grid((unsigned)nb, (unsigned)n_pairs);
+    if (ndim == 3) warp_affine_kernel<3><<<grid, 256, 0, s>>>(moving_dev, out_dev, n_channels, D, H, W, theta_dev, xb_dev, yb_dev, zb_dev);
+    else warp_affine_kernel<2><<<grid, 256, 0, s>>>(moving_dev, out_dev, n_channels, 1, H, W, theta_dev, xb_dev, yb_dev, zb_dev);
     return check_cuda(cudaGetLastError(), "warp_affine");
 }
 

@@ -243,19 +243,24 @@ class AffineProblem:
         return self.loss_log[:, : self.epoch]
 
 
-def warp_affine(theta: torch.Tensor, moving: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out[0, c] = grid_sample(moving[0, c], affine_grid(theta)), align_corners=False,
-    zeros padding (reference get_affine_warp, warpings.py:18-26).  theta: 12|6 values.
-    `out`: optional contiguous fp32 destination of moving's shape (e.g. one pair's slice of a batch result)."""
+def warp_affine(theta: torch.Tensor, moving: torch.Tensor, out: Optional[torch.Tensor] = None,
+                large_rotation: bool = False) -> torch.Tensor:
+    """out[n, c] = grid_sample(moving[n, c], affine_grid(theta[n])), align_corners=False, zeros padding (reference
+    get_affine_warp, warpings.py:18-26).  theta: 12|6 values per pair; moving [N,C,...] with N pairs (N == 1 is the
+    reference's case, N > 1 the batch extension: every pair its own theta, ONE launch for all pairs and channels).
+    `out`: optional contiguous fp32 destination of moving's shape.  `large_rotation`: theta is known to rotate by more
+    than a few degrees (3-D: take the gather kernel instead of the TMA-staged one; same values either way)."""
     require_cuda(moving, "moving")
     ndim, D, H, W = _vol_dims(moving)
-    if moving.shape[0] != 1:
-        raise ValueError("get_affine_warp expects N == 1 (the reference's theta is [1,%d,%d])" % (ndim, ndim + 1))
     lib = _lib.load()
     dev = moving.device
+    n = int(moving.shape[0])
+    nt = ndim * (ndim + 1)
     th = torch.as_tensor(theta, dtype=torch.float32, device=dev).detach().reshape(-1).contiguous()
-    if th.numel() != ndim * (ndim + 1):
-        raise ValueError("theta has %d values, expected %d" % (th.numel(), ndim * (ndim + 1)))
+    if th.numel() == nt and n > 1:
+        th = th.repeat(n)
+    if th.numel() != n * nt:
+        raise ValueError("theta has %d values, expected %d per pair (%d pair(s))" % (th.numel(), nt, n))
     src = moving.detach().contiguous()
     if out is None:
         out = torch.empty_like(src)
@@ -264,8 +269,9 @@ def warp_affine(theta: torch.Tensor, moving: torch.Tensor, out: Optional[torch.T
     xb, yb = base_coords(W, dev), base_coords(H, dev)
     zb = base_coords(D, dev) if ndim == 3 else None
     with torch.cuda.device(dev):
-        check(lib.trb_warp_affine(ndim, src.data_ptr(), out.data_ptr(), int(src.shape[1]), D, H, W, th.data_ptr(),
-                                  xb.data_ptr(), yb.data_ptr(), _ptr(zb), _stream(dev)), "warp_affine")
+        check(lib.trb_warp_affine_batch(ndim, src.data_ptr(), out.data_ptr(), n, int(src.shape[1]), D, H, W, th.data_ptr(),
+                                        xb.data_ptr(), yb.data_ptr(), _ptr(zb), 1 if large_rotation else 0, _stream(dev)),
+              "warp_affine")
     return out
 
 

@@ -49,11 +49,13 @@ class Register():
                 "torchregister_b200.Register runs on CUDA only (got device=%r); there is no CPU fallback. "
                 "Use Register(device='cuda')." % (self.device,))
 
-    def optim(self, moving, target, lr=1E-5, max_epochs=1000, n=32, per=0.1, *, reg0=None):
+    def optim(self, moving, target, lr=1E-5, max_epochs=1000, n=32, per=0.1, *, reg0=None, theta0=None):
         '''
         Optimisation loop (reference torchregister.py:46-106). Sets `self.theta` to the best
         (lowest-loss, pre-step) theta for rigid/affine, or to the last flow field for flow.
         `reg0` (keyword-only extension): initial rigid parameters instead of the torch.rand draw.
+        `theta0` (keyword-only extension, affine mode): start theta instead of identity — e.g. the theta of a preceding
+        rigid stage together with the ORIGINAL moving volume, so that the pipeline needs no intermediate resampling.
         '''
         self._check_device()
         # the reference works in float32 throughout (dtype=torch.float, warpings.py:48,55; utils.py:347)
@@ -97,6 +99,8 @@ class Register():
                 kw.update(weights=self.weight)
             if reg0 is not None and self.mode == 'rigid':
                 kw.update(reg0=reg0)
+            if theta0 is not None and self.mode == 'affine':
+                kw.update(theta0=theta0)
             _, theta = fn(moving, target, **kw)
             self.theta = theta[-1]                    # best theta, [1,nd,nd+1] ([N,nd,nd+1] for a batch: extension)
             self.losses = probs[0].losses[0] if moving.shape[0] == 1 else probs[0].losses   # device tensor(s): loss log

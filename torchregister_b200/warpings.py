@@ -49,12 +49,8 @@ def get_affine_warp(theta, moving):
         nd = moving.dim() - 2
         th = theta.reshape(moving.shape[0], nd, nd + 1)
         if not (torch.is_grad_enabled() and th.requires_grad):
-            # plain forward (Register.__call__ on a batch): every pair's kernel writes straight into its slice
-            src = moving.detach().contiguous().float()
-            out = torch.empty_like(src)
-            for i in range(src.shape[0]):
-                TF.warp_affine(th[i], src[i:i + 1], out=out[i:i + 1])
-            return out
+            # plain forward (Register.__call__ on a batch): one launch for all pairs and channels
+            return TF.warp_affine(th, moving.detach().contiguous().float())
         return torch.cat([_AffineWarpFn.apply(th[i:i + 1], moving[i:i + 1]) for i in range(moving.shape[0])], dim=0)
     return _AffineWarpFn.apply(theta, moving)
 
@@ -103,9 +99,7 @@ def _reject_edges(grad_edges):
 
 def _warp_batch(theta, moving):
     """theta [N, nd, nd+1] applied pair-wise to moving [N, C, ...] (N == 1: the reference's case)."""
-    if moving.shape[0] == 1:
-        return TF.warp_affine(theta, moving)
-    return torch.cat([TF.warp_affine(theta[i], moving[i:i + 1]) for i in range(moving.shape[0])], dim=0)
+    return TF.warp_affine(theta, moving)
 
 
 def _optimiser_name(optm) -> str:
@@ -155,20 +149,27 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
 
 
 def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', debug=True, criterions=None,
-                    weights=[0.33, 0.33, 0.33], grad_edges=True, *, optm='SGD', betas=(0.9, 0.999), eps=1e-8,
+                    weights=[0.33, 0.33, 0.33], grad_edges=True, *, theta0=None, optm='SGD', betas=(0.9, 0.999), eps=1e-8,
                     _want_warped=True, _problem_out=None):
     """Affine registration by SGD on the 12 (6) entries of theta, identity start
     (reference warpings.py:30-113).  The reference routes theta through a zero-initialised MLP
     that is provably inert under momentum-free SGD; `per` only sizes that MLP and
     is accepted and ignored.  Returns ([final_warped, best_warped], [final_theta, best_theta]).
     `optm='ADAM'` (keyword-only extension, north_star item 3): torch.optim.Adam semantics on theta, fused into the
-    epoch's final reduction like the SGD step."""
+    epoch's final reduction like the SGD step.
+    `theta0` (keyword-only extension, SURVEY.md §8 f-2 pipeline chaining): start from this theta ([N,nd,nd+1] or anything
+    reshapeable to it) instead of identity.  With the theta of a preceding rigid stage and the ORIGINAL moving volume the
+    rigid -> affine pipeline needs no intermediate resampled volume and the result is the composed transform; the
+    reference resamples between the stages (README.md:69), so the two pipelines differ by that one interpolation."""
     _reject_edges(grad_edges)
     TF.require_cuda(moving, "moving")
     nd = moving.dim() - 2
     wp = similarity_weights(criterions, weights, "affine_register")
-    ident = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)      # every pair starts at identity
-    prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, ident, debug, _want_warped, optm, betas, eps)
+    if theta0 is None:
+        start = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)  # every pair starts at identity
+    else:
+        start = torch.as_tensor(theta0, dtype=torch.float32, device=moving.device).reshape(-1, nd * (nd + 1))
+    prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, start, debug, _want_warped, optm, betas, eps)
     if _problem_out is not None:
         _problem_out.append(prob)
     return warped, theta
