@@ -282,6 +282,15 @@ int trb_flow_direct_finish(const double *moments6_dev, int D, int H, int W, floa
                            float smooth_lambda, float *loss_log_dev, int epochs_done,
                            void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ---- Edge3D pre-filter --------------------------------------------------------------
+ * Replaces utils.py:130-183 (Edge3D.__call__ with a pad that works): reflect padding, the nine 3x3x3 Sobel-type
+ * cross-correlations of get_sobel_kernel3D (utils.py:82-127; passed as weights_host[9][27], HOST memory, (x,y,z) order),
+ * gradient magnitude (1/C) sqrt(sum_s (sum_c (corr_s + eps))^2 + eps), min-max normalisation over the whole batch
+ * (utils.py:262-267) and the band threshold lo < e < hi -> {0,1}.  out_dev [B][X][Y][Z] fp32; minmax_dev: 2 x u32 scratch;
+ * norm_out_dev (optional): the normalised magnitude before thresholding. */
+int trb_edge3d(const float *img_dev, float *out_dev, int B, int C, int X, int Y, int Z, const float *weights_host,
+               float thresh_lo, float thresh_hi, unsigned *minmax_dev, float *norm_out_dev, void *stream);
+
 /* ---- NMI/KDE term of the reference's default loss -----------------------------------
  * Replaces utils.py:18-79 (K_gauss, PDF_xis, get_pdf, NMI) + utils.py:224-259 (NMILoss.forward with its default
  * bins=256, patch_size=100) and autograd's backward down to the warped volume, for ONE pair [1,1,(D,)H,W]:

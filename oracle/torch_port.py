@@ -263,3 +263,44 @@ def direct_flow_loop(moving, target, lr, epochs, weights=(0.5, 0.5, 0.0), smooth
         opt.step()
         losses.append(err.item())
     return {"losses": losses, "flow": flow.detach().clone()}
+
+
+# --------------------------------------------------------------------------- #
+# Edge3D pre-filter
+# --------------------------------------------------------------------------- #
+def sobel_kernels3d(n1=1, n2=2, n3=2):
+    """utils.py:82-127 (get_sobel_kernel3D), restated with numpy exactly as the reference writes it."""
+    import numpy as np
+    Sx = np.asarray([[[-n1, 0, n1], [-n2, 0, n2], [-n1, 0, n1]], [[-n2, 0, n2], [-n3 * n2, 0, n3 * n2], [-n2, 0, n2]],
+                     [[-n1, 0, n1], [-n2, 0, n2], [-n1, 0, n1]]])
+    Sy = np.asarray([[[-n1, -n2, -n1], [0, 0, 0], [n1, n2, n1]], [[-n2, -n3 * n2, -n2], [0, 0, 0], [n2, n3 * n2, n2]],
+                     [[-n1, -n2, -n1], [0, 0, 0], [n1, n2, n1]]])
+    Sz = np.asarray([[[-n1, -n2, -n1], [-n2, -n3 * n2, -n2], [-n1, -n2, -n1]], [[0, 0, 0], [0, 0, 0], [0, 0, 0]],
+                     [[n1, n2, n1], [n2, n3 * n2, n2], [n1, n2, n1]]])
+    Sd11 = np.asarray([[[0, n1, n2], [-n1, 0, n1], [-n2, -n1, 0]], [[0, n2, n2 * n3], [-n2, 0, n2], [-n2 * n3, -n2, 0]],
+                       [[0, n1, n2], [-n1, 0, n1], [-n2, -n1, 0]]])
+    Sd12 = np.asarray([[[-n2, -n1, 0], [-n1, 0, n1], [0, n1, n2]], [[-n2 * n3, -n2, 0], [-n2, 0, n2], [0, n2, n2 * n3]],
+                       [[-n2, -n1, 0], [-n1, 0, n1], [0, n1, n2]]])
+    Sd21, Sd22 = Sd11.T, Sd12.T
+    Sd31 = np.asarray([-S.T for S in Sd11.T])
+    Sd32 = np.asarray([S.T for S in Sd12.T])
+    return [Sx, Sy, Sz, Sd11, Sd12, Sd21, Sd22, Sd31, Sd32]
+
+
+def edge3d(img, a=1, thresh=(0.2, 0.9), return_norm=False):
+    """utils.py:153-183 (Edge3D.__call__): reflect pad by a, nine 3x3x3 cross-correlations (conv3d, padding 1), magnitude
+    (1/C) sqrt(sum_s (sum_c (corr + eps))^2 + eps), crop, min-max norm (:262-267), band threshold."""
+    import numpy as np
+    eps = 1e-10
+    B, C = img.shape[:2]
+    x = F.pad(img, (a,) * 6, mode="reflect")
+    mags = []
+    for k in sobel_kernels3d():
+        wgt = torch.from_numpy(k.astype(np.float32)).reshape(1, 1, 3, 3, 3).to(img)
+        per_c = torch.cat([F.conv3d(x[:, c:c + 1], wgt, padding=1) for c in range(C)], dim=1)
+        mags.append(torch.sum(per_c + eps, dim=1) ** 2)
+    g = (1 / C) * torch.sum(torch.stack(mags, dim=1) + eps, dim=1) ** 0.5
+    g = g[:, a:-a, a:-a, a:-a].reshape(B, 1, *img.shape[2:])
+    e = (g - torch.min(g)) / ((torch.max(g) - torch.min(g)) + 1e-9)
+    out = ((e > thresh[0]) & (e < thresh[1])).to(torch.float32)
+    return (out, e) if return_norm else out

@@ -238,6 +238,16 @@ def case_long(name, shape, kind, stages, criterions, weights, eff_weights, p0, s
     save(name, **out)
 
 
+def case_edge3d(name, shape):
+    """The unmodified reference's Edge3D with a pad that works (a=1; its default a=5000 raises) on a 2-channel volume."""
+    mov, tgt = make_pair(shape, "rigid")
+    img = torch.cat([mov, 0.7 * tgt + 0.05], dim=1)
+    f = ru.Edge3D(device="cpu")
+    edges = f(img, a=1)
+    edges2 = f(img, a=3, thresh=[0.1, 0.6])
+    save(name, img=img.numpy(), edges=edges.numpy(), edges_a3=edges2.numpy())
+
+
 def main_round2(which):
     """Round-2 goldens: 3-D cases at a shape the TMA-staged kernels accept (W >= 32, W % 4 == 0, H >= 16), with partial
     tiles in every axis, and long-horizon runs."""
@@ -251,6 +261,8 @@ def main_round2(which):
         case_affine_like("affine3d_tma_ncc", ST, "affine", "affine", 1e-4, 12, None, [0.0, 1.0, 0.0], [0, 1, 0], stub_nmi=True)
         case_affine_like("affine3d_tma_mix", ST, "affine", "affine", 1e-4, 12, None, [0.5, 0.5, 0.0], [.5, .5, 0], stub_nmi=True)
         case_affine_like("rigid3d_tma_rand", ST, "rigid", "rigid", 1e-4, 8, None, [0.0, 1.0, 0.0], [0, 1, 0], None, stub_nmi=True, seed=0)
+    if which in ("all", "edge"):
+        case_edge3d("edge3d", (18, 22, 26))
     if which in ("all", "long3d"):
         case_long("long3d_rigid_affine", (40, 64, 64), "affine", [("rigid", 500, 1e-3), ("affine", 200, 1e-3)], None, [0.0, 1.0, 0.0],
                   [0, 1, 0], p3, stub_nmi=True)

@@ -836,3 +836,33 @@ def test_register_flow_mode_3d_160():
     assert abs(reg.losses[0] - ref_losses[0]) <= 1e-4 * abs(ref_losses[0])
     out = reg(torch.cat([mov, 0.5 * tgt], dim=1))
     assert tuple(out.shape) == (1, 2) + shape and torch.isfinite(out).all()
+
+
+def test_edge3d_kernel_vs_reference_golden():
+    """the Edge3D stencil kernel against the unmodified reference's output (recorded with a working pad) and
+    against the oracle's normalised magnitude; then grad_edges=True through the public loop."""
+    import torchregister_b200 as tr
+    from oracle import torch_port as tp
+    g = load_golden("edge3d")
+    img = torch.from_numpy(g["img"])
+    f = tr.Edge3D(device=DEV)
+    out, nrm = f(img.to(DEV), a=1, return_norm=True)
+    _, ref_nrm = tp.edge3d(img, a=1, return_norm=True)
+    assert np.abs(nrm.cpu().numpy() - ref_nrm.numpy()).max() < 1e-5
+    # the mask may only differ where the normalised magnitude sits on a threshold to rounding
+    diff = out.cpu().numpy() != g["edges"]
+    near = (np.abs(ref_nrm.numpy() - 0.2) < 1e-5) | (np.abs(ref_nrm.numpy() - 0.9) < 1e-5)
+    assert not (diff & ~near).any(), int(diff.sum())
+    out3 = f(img.to(DEV), a=3, thresh=[0.1, 0.6])
+    diff3 = out3.cpu().numpy() != g["edges_a3"]
+    near3 = (np.abs(ref_nrm.numpy() - 0.1) < 1e-5) | (np.abs(ref_nrm.numpy() - 0.6) < 1e-5)
+    assert not (diff3 & ~near3).any()
+    with pytest.raises(RuntimeError):
+        f(img.to(DEV), a=5000)                    # the reference's default pad: raises there too
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((40, 48, 64), "rigid")
+    reg = tr.Register(mode="rigid", device=DEV, weight=[1.0, 0.0, 0.0], grad_edges=True)
+    reg.optim(mov, tgt, lr=1e-3, max_epochs=3, reg0=torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02]))
+    em, et = f(mov.to(DEV)), f(tgt.to(DEV))
+    ref = tp.affine_like_loop(em.cpu(), et.cpu(), "rigid", torch.tensor([0.02, -0.01, 0.03, 0.05, -0.05, 0.02]), 1e-3, 3, (1.0, 0.0, 0.0))
+    assert np.abs(reg.losses.cpu().numpy() - np.asarray(ref["losses"])).max() <= 1e-4 * max(ref["losses"])

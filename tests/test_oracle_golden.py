@@ -215,3 +215,14 @@ def test_long3d_c_oracle_matches_reference():
     assert np.abs(r["final_theta"] - ref).max() <= 1e-4 * np.abs(ref).max()
     warped = co.warp_affine(g["moving"], g["s0_best_theta"].astype(np.float32))
     assert np.abs(warped - g["s0_best_warped"].reshape(warped.shape)).max() < 1e-5
+
+
+def test_edge3d_port_matches_reference():
+    """oracle edge3d (restated conv3d pipeline) against the unmodified reference's Edge3D output (a=1 and a=3)."""
+    g = load_golden("edge3d")
+    img = torch.from_numpy(g["img"])
+    assert np.array_equal(tp.edge3d(img, a=1).numpy(), g["edges"])
+    assert np.array_equal(tp.edge3d(img, a=3, thresh=(0.1, 0.6)).numpy(), g["edges_a3"])
+    from torchregister_b200.utils import get_sobel_kernel3D
+    for ref, got in zip(tp.sobel_kernels3d(1, 3, 2), get_sobel_kernel3D(1, 3, 2)):
+        assert np.array_equal(np.asarray(ref, np.float64), got.numpy())

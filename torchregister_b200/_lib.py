@@ -50,6 +50,7 @@ _SIGNATURES = {
     "trb_flow_direct_finish": (_i, [c_fp, _i, _i, _i, _f, _f, _f, c_fp, _i, c_fp, _sz, c_fp]),
     "trb_affine_optim_peer": (_i, [c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, _i, c_fp, c_fp, _i, _i, _i,
                                    _f, _f, _f, _i, _f, _f, _f, C.POINTER(C.c_void_p), _i, _i, C.c_ulonglong, c_fp, _sz, c_fp]),
+    "trb_edge3d": (_i, [c_fp, c_fp, _i, _i, _i, _i, _i, C.POINTER(C.c_float), _f, _f, c_fp, c_fp, c_fp]),
     "trb_nmi_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "trb_nmi_prepare": (_i, [_i, c_fp, _i, _i, _i, _f, c_fp, _sz, c_fp]),
     "trb_nmi_loss_grad": (_i, [_i, c_fp, _i, _i, _i, _f, _f, _f, c_fp, c_fp, c_fp, _sz, c_fp]),

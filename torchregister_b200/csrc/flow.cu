@@ -160,6 +160,60 @@ __global__ void __launch_bounds__(256) flow_grad_kernel(const float *__restrict_
     });
 }
 
+// MSE only (w_ncc == 0): dL/dw_v = 2 w_mse (w_v - t_v) / n needs no global moments, so the statistics pass is not needed —
+// ONE pass samples, writes d loss / d flow (and optionally the warped volume) and reduces sum (w - t)^2 for the loss.
+template <int NDIM>
+__global__ void __launch_bounds__(256) flow_mse_fused_kernel(const float *__restrict__ moving, const float *__restrict__ target,
+                                                              const float *__restrict__ flow, float *__restrict__ dflow,
+                                                              float *__restrict__ warped, int D, int H, int W, double w_mse,
+                                                              double *__restrict__ ws, float *__restrict__ loss_out)
+{
+    const size_t vol = (size_t)(NDIM == 3 ? D : 1) * H * W;
+    const FlowAxes ax = flow_axes(D, H, W);
+    const float gm = (float)(2.0 * w_mse / (double)vol);
+    float sd = 0.f;
+    for_each_voxel(NDIM == 3 ? D : 1, H, W, [&](size_t idx, int x, int y, int z) {
+        float px, py, pz;
+        flow_position<NDIM>(flow, vol, idx, x, y, z, ax, px, py, pz);
+        const Sample<NDIM> s = sample_zero_pad<NDIM, true, false>(moving, D, H, W, px, py, pz);
+        const float t = ld_stream_f(target + idx);
+        const float d = s.val - t;
+        if (warped) warped[idx] = s.val;
+        sd = fmaf(d, d, sd);
+        store_dflow<NDIM>(dflow, vol, idx, gm * d, s.g);
+    });
+    __shared__ double red[8];
+    __shared__ bool is_last;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const double v = warp_sum((double)sd);
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    double *partials = ws + 8;
+    unsigned *ticket = (unsigned *)(ws + 4);
+    if (threadIdx.x == 0) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w];
+        __stcg(partials + blockIdx.x, t);
+        __threadfence();
+        is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    if (warp == 0) {                               // fixed-order reduction over blocks
+        double t = 0.0;
+        for (int b = lane; b < (int)gridDim.x; b += 32) t += __ldcg(partials + b);
+        t = warp_sum(t);
+        if (lane == 0) {
+            const double loss = w_mse * t / (double)vol;
+            ws[3] = loss;
+            if (loss_out) *loss_out = (float)loss;
+            *ticket = 0u;
+        }
+    }
+}
+
 static unsigned flow_grid(size_t vol)
 {
     int dev = 0, sms = 148;
@@ -227,6 +281,11 @@ extern "C" int trb_flow_loss_grad(int ndim, const float *moving_dev, const float
     cudaStream_t s = (cudaStream_t)stream;
     double *ws = (double *)workspace_dev;
     const unsigned g = flow_grid(vol);
+    if (w_ncc == 0.f) {                 // no global moments needed: one fused pass (32 B/voxel instead of 52)
+        if (ndim == 3) flow_mse_fused_kernel<3><<<g, 256, 0, s>>>(moving_dev, target_dev, flow_dev, dflow_dev, warped_dev_or_null, D, H, W, w_mse, ws, loss_dev);
+        else flow_mse_fused_kernel<2><<<g, 256, 0, s>>>(moving_dev, target_dev, flow_dev, dflow_dev, warped_dev_or_null, 1, H, W, w_mse, ws, loss_dev);
+        return check_cuda(cudaGetLastError(), "flow_loss_grad");
+    }
     if (ndim == 3) {
         flow_stats_kernel<3><<<g, 256, 0, s>>>(moving_dev, target_dev, flow_dev, warped_dev_or_null, D, H, W, w_mse, w_ncc, ws, loss_dev);
         flow_grad_kernel<3><<<g, 256, 0, s>>>(moving_dev, target_dev, flow_dev, dflow_dev, D, H, W, ws);

@@ -20,7 +20,7 @@ from . import functional as TF
 EPSILON = 1E-10
 
 __all__ = ["EPSILON", "NCCLoss", "SSDLoss", "NMILoss", "norm", "padNd", "Theta", "Regressor", "SpatialTransformer",
-           "attention_grid", "Attention_UNet"]
+           "attention_grid", "Attention_UNet", "Edge3D", "get_sobel_kernel3D"]
 
 
 # --------------------------------------------------------------------------- #
@@ -168,6 +168,73 @@ class _NmiCudaFn(torch.autograd.Function):
     def backward(ctx, grad_out):
         (gout,) = ctx.saved_tensors
         return gout * grad_out, None
+
+
+def get_sobel_kernel3D(n1=1, n2=2, n3=2):
+    """The nine 3x3x3 Sobel-type kernels of the reference (utils.py:82-127): axis kernels Sx, Sy, Sz, then six diagonal
+    ones derived from two base diagonals by transposition.  Returned as a list of [3,3,3] float64 tensors in the
+    reference's order [Sx, Sy, Sz, Sd11, Sd12, Sd21, Sd22, Sd31, Sd32]."""
+    a, b, c = float(n1), float(n2), float(n2 * n3)
+    plane = torch.tensor([[a, b, a], [b, c, b], [a, b, a]], dtype=torch.float64)        # smoothing across the two other axes
+    d = torch.tensor([-1.0, 0.0, 1.0], dtype=torch.float64)
+    # the reference indexes its literals [i][j][k]: Sx differentiates along k, Sy along j, Sz along i
+    Sx = plane[:, :, None] * d[None, None, :]
+    Sy = plane[:, None, :] * d[None, :, None]
+    Sz = d[:, None, None] * plane[None, :, :]
+    row = torch.tensor([a, b, a], dtype=torch.float64)                                  # weights of the three [i] slabs
+    diag1 = torch.tensor([[0, 1, 2], [-1, 0, 1], [-2, -1, 0]], dtype=torch.float64)     # pattern of Sd11 for n1=1, n2=2
+    diag2 = torch.tensor([[-2, -1, 0], [-1, 0, 1], [0, 1, 2]], dtype=torch.float64)     # pattern of Sd12
+
+    def slab(pattern, lo, hi):
+        # |1| entries -> lo, |2| entries -> hi, signs kept
+        return torch.sign(pattern) * torch.where(pattern.abs() == 2, torch.tensor(hi, dtype=torch.float64),
+                                                 torch.where(pattern.abs() == 1, torch.tensor(lo, dtype=torch.float64),
+                                                             torch.tensor(0.0, dtype=torch.float64)))
+    Sd11 = torch.stack([slab(diag1, a, b), slab(diag1, b, c), slab(diag1, a, b)])
+    Sd12 = torch.stack([slab(diag2, a, b), slab(diag2, b, c), slab(diag2, a, b)])
+    Sd21 = Sd11.permute(2, 1, 0)                 # numpy .T of a 3-D array reverses the axes
+    Sd22 = Sd12.permute(2, 1, 0)
+    Sd31 = torch.stack([-m.t() for m in Sd21])   # [-S.T for S in Sd11.T]
+    Sd32 = torch.stack([m.t() for m in Sd22])    # [S.T for S in Sd12.T]
+    del row
+    return [Sx, Sy, Sz, Sd11, Sd12, Sd21, Sd22, Sd31, Sd32]
+
+
+class Edge3D():
+    """Sobel edge pre-filter of the reference (utils.py:130-183), as one CUDA stencil pass + one threshold pass
+    (csrc/edge.cu) instead of 9*C conv3d calls on a padded copy.  Same constructor and call signature.
+
+    Deviation, deliberate: the reference's default pad `a=5000` makes its reflect padding raise for every volume smaller
+    than 5001 voxels per axis, i.e. the filter cannot be used at its defaults.  Any pad `a >= 1`
+    smaller than the volume gives the same output (the pad is cropped again and the stencil reaches one voxel), so the
+    default here is `a=1`; `a >= min(shape)` raises like torch's reflect padding does."""
+
+    def __init__(self, n1=1, n2=2, n3=2, device='cpu'):
+        self.device = device
+        ks = get_sobel_kernel3D(n1, n2, n3)
+        self.weights = torch.stack(ks).to(torch.float32).reshape(9, 27).contiguous()      # host copy, (x,y,z) order
+
+    def __call__(self, img, a=1, thresh=[0.2, 0.9], return_norm=False):
+        import ctypes as C
+        from . import _lib
+        TF.require_cuda(img, "img")
+        if img.dim() != 5:
+            raise ValueError("Edge3D expects a 5-D tensor (b, c, x, y, z)")
+        B, Cc, X, Y, Z = (int(v) for v in img.shape)
+        if a < 1 or a >= min(X, Y, Z):
+            raise RuntimeError("Padding size should be less than the corresponding input dimension (reflect pad %d, "
+                               "volume %dx%dx%d); pass 1 <= a < min(shape)" % (a, X, Y, Z))
+        src = img.detach().contiguous()
+        out = torch.empty(B, 1, X, Y, Z, dtype=torch.float32, device=src.device)
+        nrm = torch.empty_like(out) if return_norm else None
+        minmax = torch.empty(2, dtype=torch.int32, device=src.device)
+        w = (C.c_float * (9 * 27))(*self.weights.reshape(-1).tolist())
+        self._keep = w                                  # the async upload reads it until the stream gets there
+        with torch.cuda.device(src.device):
+            _lib.check(_lib.load().trb_edge3d(src.data_ptr(), out.data_ptr(), B, Cc, X, Y, Z, w, float(thresh[0]), float(thresh[1]),
+                                              minmax.data_ptr(), None if nrm is None else nrm.data_ptr(),
+                                              torch.cuda.current_stream(src.device).cuda_stream), "edge3d")
+        return (out, nrm) if return_norm else out
 
 
 def norm(x):

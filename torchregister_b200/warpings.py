@@ -90,11 +90,16 @@ def similarity_weights(criterions, weights, where: str) -> Tuple[float, float, f
     return float(w[0]), float(w[1]), float(w[2])
 
 
-def _reject_edges(grad_edges):
-    if grad_edges:
-        raise NotImplementedError(
-            "grad_edges=True (Edge3D Sobel pre-filter, reference utils.py:130-183) is outside the fused path; "
-            "the reference itself raises at its default padding. Pass grad_edges=False.")
+def _apply_edges(grad_edges, moving, target):
+    """grad_edges=True: register the Sobel edge maps instead of the intensities (reference warpings.py:31-34,118-121,
+    199-202).  The reference's filter raises at its default pad (a=5000); ours uses the working pad a=1 (utils.Edge3D)."""
+    if not grad_edges:
+        return moving, target
+    if moving.dim() != 5:
+        raise ValueError("grad_edges=True needs 3-D volumes [N,C,D,H,W] (Edge3D is a 3-D filter, reference utils.py:153)")
+    from .utils import Edge3D
+    f = Edge3D(device=moving.device)
+    return f(moving), f(target)
 
 
 def _warp_batch(theta, moving):
@@ -161,8 +166,8 @@ def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu',
     reshapeable to it) instead of identity.  With the theta of a preceding rigid stage and the ORIGINAL moving volume the
     rigid -> affine pipeline needs no intermediate resampled volume and the result is the composed transform; the
     reference resamples between the stages (README.md:69), so the two pipelines differ by that one interpolation."""
-    _reject_edges(grad_edges)
     TF.require_cuda(moving, "moving")
+    moving, target = _apply_edges(grad_edges, moving, target)
     nd = moving.dim() - 2
     wp = similarity_weights(criterions, weights, "affine_register")
     if theta0 is None:
@@ -182,8 +187,8 @@ def rigid_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu', 
     (reference warpings.py:117-174, utils.py:287-330).  Initial parameters are drawn with
     torch.rand on the data's device like the reference's Regressor; `reg0` (keyword-only
     extension) injects them instead."""
-    _reject_edges(grad_edges)
     TF.require_cuda(moving, "moving")
+    moving, target = _apply_edges(grad_edges, moving, target)
     wp = similarity_weights(criterions, weights, "rigid_register")
     npar = 6 if moving.dim() == 5 else 3
     if reg0 is None:
@@ -262,8 +267,8 @@ class flow_register(nn.Module):
         return y
 
     def optimize(self, moving, target, device, debug=True, grad_edges=False):
-        _reject_edges(grad_edges)
         TF.require_cuda(moving, "moving")
+        moving, target = _apply_edges(grad_edges, moving, target)
         w_mse, w_ncc, other = _split_criteria(self.criterions, self.weights)
         self.losses = []
         message = 'Reached max epochs'
@@ -317,22 +322,32 @@ class direct_flow_register:
         self.flow, self.losses, self._prob = None, [], None
 
     def optimize(self, moving, target, device=None, debug=True, grad_edges=False, check_every=50):
-        _reject_edges(grad_edges)
+        moving, target = _apply_edges(grad_edges, moving, target)
         prob = TF.DirectFlowProblem(moving, target, self.max_epochs, optimiser=self.optimiser)
         done = 0
         message = 'Reached max epochs'
-        while done < self.max_epochs:                       # the stop criterion is polled every `check_every` epochs
-            n = min(check_every, self.max_epochs - done)
+        # The reference's flow loop stops at the first epoch whose loss is <= stop_crit (warpings.py:231-233).  Here the
+        # epochs are enqueued in chunks without host round trips and the criterion is polled per chunk; the chunk
+        # shrinks to ONE epoch as soon as the loss is within 10x of the criterion, so the loop stops at the epoch the
+        # reference would stop at (and the loss log is cut there) unless the loss falls by more than 10x within one
+        # chunk of `check_every` epochs.
+        stop_at = None
+        chunk = check_every
+        while done < self.max_epochs:
+            n = min(chunk, self.max_epochs - done)
             prob.run(n, self.lr, self.w_mse, self.w_ncc, self.smooth, self.betas, self.eps)
             done += n
             lo = prob.losses[done - n:done]
             hit = (lo <= self.stop_crit).nonzero()
             if hit.numel():
+                stop_at = done - n + int(hit[0].item()) + 1
                 message = 'Converged to %f' % self.stop_crit
                 break
+            if float(lo[-1].item()) <= 10.0 * self.stop_crit:
+                chunk = 1
         self._prob = prob
         self.flow = prob.flow
-        self.losses = prob.losses.tolist()
+        self.losses = prob.losses.tolist() if stop_at is None else prob.losses[:stop_at].tolist()
         if debug:
             print('Optimization ended with status: %s' % message)
 
