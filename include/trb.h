@@ -77,6 +77,8 @@ int trb_sm_count(void);
  * the shape/alignment allows, direct-gather kernel otherwise), 1 = always the direct-gather kernel, 2 = the
  * one-launch-per-epoch TMA kernel instead of the persistent one.  Process-wide; meant for tests and A/B timing. */
 int trb_set_kernel_path(int path);
+/* What the last trb_affine_optim* call of this thread did about the persistent kernel (launched, or why not): diagnostics. */
+const char *trb_affine_kernel_status(void);
 
 /* ---- rigid / affine registration ---------------------------------------- */
 

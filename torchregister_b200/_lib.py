@@ -20,6 +20,7 @@ _SIGNATURES = {
     "trb_last_error": (C.c_char_p, []),
     "trb_sm_count": (C.c_int, []),
     "trb_set_kernel_path": (_i, [_i]),
+    "trb_affine_kernel_status": (C.c_char_p, []),
     "trb_affine_workspace_bytes": (_sz, [_i]),
     "trb_affine_init_state": (_i, [_i, _i, c_fp, _i, c_fp]),
     "trb_affine_optim": (_i, [_i, _i, c_fp, c_fp, _ll, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i,

@@ -343,6 +343,8 @@ extern "C" int trb_set_kernel_path(int path)
     return TRB_OK;
 }
 
+extern "C" const char *trb_affine_kernel_status(void) { return persist_status(); }
+
 extern "C" size_t trb_affine_workspace_bytes(int n_pairs) { return affine_ws_bytes(n_pairs); }
 
 static int validate_common(int ndim, int n_pairs, int D, int H, int W)

@@ -27,6 +27,7 @@
 #include "affine_tile.cuh"
 #include <cooperative_groups.h>
 #include <vector>
+#include <stdio.h>
 
 namespace trb {
 
@@ -81,7 +82,7 @@ constexpr size_t kOffState = kOffRed + 2 * kConsumerWarps * kRedLdP * sizeof(flo
 constexpr size_t kOffAccw = kOffState + kStateSlots * TRB_STATE_FLOATS * sizeof(float);
 constexpr size_t kOffMrow = kOffAccw + kAccWords * sizeof(unsigned long long);
 constexpr size_t kOffCoefq = kOffMrow + 48 * sizeof(double);
-constexpr size_t kOffStages = (kOffCoefq + kCoefSlots * 12 * sizeof(float) + 1023) / 1024 * 1024;
+constexpr size_t kOffStages = (kOffCoefq + kCoefSlots * 12 * sizeof(float) + 127) / 128 * 128;    // TMA destinations: 128-byte aligned
 // ROT = false: a stage is the staged box of the moving volume + the target tile (TMA-staged variant);
 // ROT = true : the target tile only — the moving volume is gathered through L1 (large-rotation variant, below)
 template <bool ROT> struct Ring {
@@ -89,7 +90,7 @@ template <bool ROT> struct Ring {
     static constexpr size_t kStageBytes = ROT ? (size_t)PL::kTgtFloats * 4 : (size_t)PL::kStageBytes;
     static constexpr size_t kSmem = kOffStages + kStages * kStageBytes;
 };
-static_assert(Ring<false>::kSmem <= 232448, "persistent kernel: shared memory budget");
+static_assert(Ring<false>::kSmem + 640 <= 232448, "persistent kernel: dynamic + static shared memory must stay within 227 KB");
 
 __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long *p)
 {
@@ -815,29 +816,32 @@ static void count_contributions(const TmaParams &p, int G, std::vector<unsigned>
 
 static bool g_no_persist = false;
 void set_no_persist(bool v) { g_no_persist = v; }
+static thread_local char g_persist_status[256] = "never called";
+#define PERSIST_REFUSE(...) do { snprintf(g_persist_status, sizeof(g_persist_status), __VA_ARGS__); return TRB_ERR_UNSUPPORTED; } while (0)
 
 // Enqueue n_epochs fused epochs for n_pairs pairs with the persistent kernel.  Returns TRB_ERR_UNSUPPORTED (without
 // enqueuing anything) when the configuration does not fit it; the caller then takes the per-epoch kernel.
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream)
 {
-    if (g_no_persist || a.extra) return TRB_ERR_UNSUPPORTED;
-    if (a.peer.world > 1 && n_pairs != 1) return TRB_ERR_UNSUPPORTED;
+    if (g_no_persist || a.extra) PERSIST_REFUSE("disabled (kernel path / extra term)");
+    if (a.peer.world > 1 && n_pairs != 1) PERSIST_REFUSE("peer exchange needs one pair");
     int dev = 0, sms = 0, coop = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess) return TRB_ERR_UNSUPPORTED;
+    if (cudaGetDevice(&dev) != cudaSuccess) PERSIST_REFUSE("cudaGetDevice failed");
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
-    if (!coop || sms < 1) return TRB_ERR_UNSUPPORTED;
+    if (!coop || sms < 1) PERSIST_REFUSE("no cooperative launch (coop %d, sms %d)", coop, sms);
     const bool mse_only = a.w_ncc == 0.f;
     const bool rot = a.gather != 0;
     auto kern = rot ? (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>)
                     : (mse_only ? affine3d_persist_kernel<true, false> : affine3d_persist_kernel<false, false>);
     const size_t kPersistSmem = rot ? Ring<true>::kSmem : Ring<false>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersistSmem);
-    if (e != cudaSuccess) { cudaGetLastError(); return TRB_ERR_UNSUPPORTED; }
+    if (e != cudaSuccess) { cudaGetLastError(); PERSIST_REFUSE("cudaFuncSetAttribute(smem %zu): %s", kPersistSmem, cudaGetErrorString(e)); }
     int occ = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPersistThreads, kPersistSmem) != cudaSuccess || occ < 1) {
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kPersistThreads, kPersistSmem);
+    if (e != cudaSuccess || occ < 1) {
         cudaGetLastError();
-        return TRB_ERR_UNSUPPORTED;
+        PERSIST_REFUSE("occupancy %d (%s)", occ, cudaGetErrorString(e));
     }
     const int tiles_x = (a.W + TX - 1) / TX, tiles_y = (a.H + TY - 1) / TY, tiles_z = (a.s_end - a.s_begin + TZ - 1) / TZ;
     const int cpp = tiles_x * tiles_y;
@@ -883,7 +887,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         unsigned cmax = 0;
         for (unsigned c : contrib) cmax = c > cmax ? c : cmax;
         if (max_touched > kStateSlots || cmax >= (1u << kCountBits)) {
-            if (p0 == 0) return TRB_ERR_UNSUPPORTED;
+            if (p0 == 0) PERSIST_REFUSE("decomposition: %d pairs per CTA, %u contributions", max_touched, cmax);
             set_error("persistent kernel: inconsistent sub-batch decomposition");
             return TRB_ERR_ARG;
         }
@@ -918,8 +922,11 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
             done += ne;
         }
     }
+    snprintf(g_persist_status, sizeof(g_persist_status), "launched: grid %d, %d SMs, %s variant, sub-batches of %d pair(s)",
+             (int)(sms < (long long)n_pairs * cpp * tiles_z ? sms : (long long)n_pairs * cpp * tiles_z), sms, rot ? "gather" : "tma", sub);
     return check_cuda(cudaGetLastError(), "affine3d_persist");
 }
+const char *persist_status() { return g_persist_status; }
 
 }  // namespace trb
 #ifdef TRB_TIMING

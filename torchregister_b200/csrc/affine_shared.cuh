@@ -18,6 +18,7 @@ int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int
 // persistent multi-epoch kernel (affine_persist.cu); TRB_ERR_UNSUPPORTED = nothing enqueued, take the per-epoch kernel
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream);
 void set_no_persist(bool v);
+const char *persist_status();
 // TMA-staged forward warp (warp_tma.cu)
 bool warp_tma_eligible(const float *moving, const float *out, int n_items, long long vol, int D, int H, int W);
 int launch_warp_affine_tma(const float *moving, float *out, int n_pairs, int n_channels, int D, int H, int W,

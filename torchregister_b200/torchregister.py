@@ -104,6 +104,7 @@ class Register():
             _, theta = fn(moving, target, **kw)
             self.theta = theta[-1]                    # best theta, [1,nd,nd+1] ([N,nd,nd+1] for a batch: extension)
             self.losses = probs[0].losses[0] if moving.shape[0] == 1 else probs[0].losses   # device tensor(s): loss log
+            self._last_problem = probs[0]             # final theta / params / best theta of the run (device state)
 
     def __call__(self, moving):
         '''
