@@ -306,6 +306,7 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
     const unsigned long long cmask = (1ull << kCountBits) - 1ull;
     const unsigned long long tq0 = PT_NOW();
     unsigned backoff = 32;
+    const unsigned backoff_max = pp.t.n_pairs <= 2 ? 96u : 1024u;   // few pairs: every CTA waits for this hand-over
     for (;;) {
         // cheap probe first: one word (the one the contributors add last), then the full check
         unsigned long long probe = 0ull;
@@ -325,8 +326,8 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
             if (__all_sync(kFull, ok)) break;
         }
         PT_INC(16);
-        __nanosleep(backoff);                      // 32 ns .. 1 us: short while the hand-over is imminent (single pair), cheap otherwise
-        if (backoff < 1024) backoff += backoff >> 1;
+        __nanosleep(backoff);                      // 32 ns .. 1 us: short while the hand-over is imminent (few pairs), cheap otherwise
+        if (backoff < backoff_max) backoff += backoff >> 1;
     }
     PT_ADD(2, tq0);
     const unsigned long long te0 = PT_NOW();
