@@ -217,6 +217,20 @@ int trb_flow_loss_grad(int ndim, const float *moving_dev, const float *target_de
                        float *loss_dev, float *dflow_dev, float *warped_dev_or_null,
                        void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* U-Net head fused with the node: replaces  y = padNd(y, x); flow = out(y); warp; similarity  of
+ * Attention_UNet.forward / flow_register.optimize (utils.py:553-557, warpings.py:211-215) and their backward.
+ * feat_dev: the decoder output [C][fd][fh][fw] (C <= 8, un-padded); w_dev [ndim][C], b_dev [ndim]: the 1x1 `out`
+ * convolution (device memory: the module's parameters as they are).  forward: writes flow_out_dev [ndim][D][H][W] (= Register.theta) and *loss_dev, leaves the loss
+ * coefficients in the workspace; backward (same workspace, after forward): dfeat_dev [C][fd][fh][fw] = d loss / d feat,
+ * dwb_dev[ndim*C + ndim] = d loss / d W, d loss / d b.  d loss / d flow is never written. */
+int trb_flow_head_forward(int ndim, const float *moving_dev, const float *target_dev, const float *feat_dev, int C,
+                          int fd, int fh, int fw, const float *w_dev, const float *b_dev, int D, int H, int W,
+                          float w_mse, float w_ncc, float *loss_dev, float *flow_out_dev,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+int trb_flow_head_backward(int ndim, const float *moving_dev, const float *target_dev, const float *flow_dev,
+                           const float *feat_dev, int C, int fd, int fh, int fw, const float *w_dev, int D, int H, int W,
+                           float *dfeat_dev, float *dwb_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* ---- EXTENSION: direct per-voxel flow optimisation (north_star items 2b/3) ---------------------
  * No counterpart in the reference (it optimises U-Net weights, warpings.py:178-233, and has no smoothness
  * term).  One epoch = trb_flow_direct_stats -> [all-reduce of the 6 moments when sharded] ->

@@ -306,7 +306,8 @@ def _flow_register_vs_device_oracle(criterions, weights, loss_fn, epochs=3):
     # update differ only through our warp/similarity/gradient node
     fr.optimize(mov.to(DEV), tgt.to(DEV), DEV, debug=False)
     assert abs(fr.losses[0] - ref_losses[0]) <= 1e-4 * abs(ref_losses[0]), (fr.losses, ref_losses)   # torch fp32 NCC reductions
-    assert torch.equal(fr.flow.detach(), ref_flows[0])
+    # (the fused head evaluates the 1x1 `out` convolution itself: same sum, its own rounding order)
+    assert torch.allclose(fr.flow.detach(), ref_flows[0], atol=2e-6)
     sd = fr.state_dict()
     _, _, sd1, _ = cpu_flow_loop(mov, tgt, _flowreg_state(g), int(g["n"]), 1e-3, 1, loss_fn, device=DEV)
     num = den = 0.0
@@ -899,3 +900,35 @@ def test_long_horizon_2d_default_loss_500_epochs_vs_reference():
     ref = g["s0_final_theta_f64"].reshape(2, 3)
     tol = max(1e-4 * np.abs(ref).max(), 2 * np.abs(g["s0_final_theta"].reshape(2, 3) - ref).max())
     assert np.abs(reg._last_problem.final_theta[0].cpu().numpy() - ref).max() <= tol if hasattr(reg, "_last_problem") else True
+
+
+@pytest.mark.parametrize("shape,weights", [((160, 168), (0.5, 0.5)), ((160, 168), (1.0, 0.0)), ((156, 160, 164), (0.5, 0.5))])
+def test_fused_unet_head_equals_unfused_path(shape, weights):
+    """padNd + 1x1 `out` conv + warp + similarity + backward in two kernels (the default in flow_register)
+    against the unfused path (torch pad / conv + the node): same loss, same flow, same parameter update."""
+    import torch.nn as nn
+    import torchregister_b200 as tr
+    from torchregister_b200.synth import make_pair
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    mov, tgt = make_pair(shape, "flow")
+    crit = [nn.MSELoss(), tr.NCCLoss()] if weights[1] else [nn.MSELoss()]
+    wts = list(weights) if weights[1] else [1.0]
+    torch.manual_seed(5)
+    a = tr.flow_register(shape, mode="bilinear", n=32, lr=1e-3, max_epochs=1, criterions=crit, weights=wts, stop_crit=-1.0)
+    sd0 = {k: v.clone() for k, v in a.state_dict().items()}
+    b = tr.flow_register(shape, mode="bilinear", n=32, lr=1e-3, max_epochs=1, criterions=crit, weights=wts, stop_crit=-1.0)
+    b.load_state_dict(sd0)
+    b.fuse_head = False
+    a, b = a.to(DEV), b.to(DEV)
+    a.optimize(mov.to(DEV), tgt.to(DEV), DEV, debug=False)
+    b.optimize(mov.to(DEV), tgt.to(DEV), DEV, debug=False)
+    assert abs(a.losses[0] - b.losses[0]) <= 2e-6 * abs(b.losses[0]), (a.losses, b.losses)
+    assert torch.allclose(a.flow, b.flow.detach(), atol=1e-6)
+    num = den = 0.0
+    for k, v in b.state_dict().items():
+        d_ref = (v - sd0[k].to(DEV)).double()
+        d_got = (a.state_dict()[k] - sd0[k].to(DEV)).double()
+        num += ((d_got - d_ref) ** 2).sum().item()
+        den += (d_ref ** 2).sum().item()
+    assert (num / max(den, 1e-300)) ** 0.5 <= 2e-3, "parameter step: relative L2 difference %.2e" % ((num / max(den, 1e-300)) ** 0.5)

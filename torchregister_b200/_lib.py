@@ -38,6 +38,10 @@ _SIGNATURES = {
     "trb_warp_flow": (_i, [_i, c_fp, c_fp, c_fp, _i, _i, _i, _i, c_fp]),
     "trb_warp_flow_vjp": (_i, [_i, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, c_fp]),
     "trb_flow_loss_grad": (_i, [_i, c_fp, c_fp, c_fp, _i, _i, _i, _f, _f, c_fp, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "trb_flow_head_forward": (_i, [_i, c_fp, c_fp, c_fp, _i, _i, _i, _i, c_fp, c_fp, _i, _i, _i,
+                                   _f, _f, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "trb_flow_head_backward": (_i, [_i, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, c_fp, _i, _i, _i,
+                                    c_fp, c_fp, c_fp, _sz, c_fp]),
     "trb_flow_direct_workspace_bytes": (_sz, []),
     "trb_flow_direct_stats": (_i, [_i, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, _f, c_fp, c_fp, _sz, c_fp]),
     "trb_flow_direct_update": (_i, [_i, c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, _f, _f, _f, _f,

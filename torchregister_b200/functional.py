@@ -108,7 +108,11 @@ class AffineProblem:
         self.xb = base_coords(self.W, self.device)
         self.yb = base_coords(self.H, self.device)
         self.zb = base_coords(self.D, self.device) if self.ndim == 3 else None
-        p0 = torch.as_tensor(params0, dtype=torch.float32, device=self.device).reshape(-1, self.np)
+        # the kernel-variant hint below needs the start parameters on the host: take them before the upload when the
+        # caller passed host data (no device round trip, no stream synchronisation)
+        p0_src = torch.as_tensor(params0, dtype=torch.float32)
+        p0_host = p0_src.detach().reshape(-1, self.np) if not p0_src.is_cuda else None
+        p0 = p0_src.to(self.device).reshape(-1, self.np)
         if p0.shape[0] == 1 and self.n_pairs > 1:
             p0 = p0.expand(self.n_pairs, self.np)
         if p0.shape[0] != self.n_pairs:
@@ -130,7 +134,7 @@ class AffineProblem:
         self.flags = 0
         if self.ndim == 3:
             if large_rotation is None:
-                large_rotation = self._start_needs_gather(p0)
+                large_rotation = self._start_needs_gather(p0 if p0_host is None else p0_host)
             self.flags = 1 if large_rotation else 0
 
     def _start_needs_gather(self, p0: torch.Tensor) -> bool:
@@ -300,6 +304,59 @@ def warp_affine_vjp(theta: torch.Tensor, moving: torch.Tensor, grad_out: torch.T
 # --------------------------------------------------------------------------- #
 # flow field
 # --------------------------------------------------------------------------- #
+_FLOW_WS = {}
+
+
+def _flow_ws(dev):
+    key = str(dev)
+    ws = _FLOW_WS.get(key)
+    if ws is None:
+        ws = torch.zeros(int(_lib.load().trb_flow_workspace_bytes()), dtype=torch.uint8, device=dev)
+        _FLOW_WS[key] = ws
+    return ws
+
+
+def flow_head_forward(moving, target, feat, weight, bias, w_mse, w_ncc):
+    """U-Net head fused with the node: flow = out(padNd(feat)) evaluated inside the kernel, then warp +
+    similarity.  feat [1,C,(d,)h,w] un-padded decoder output (C <= 8), weight [nd,C,1,(1,)1], bias [nd] the 1x1 `out`
+    convolution.  -> (loss [1], flow [1,nd,...]).  Leaves the loss coefficients in the per-device workspace for
+    flow_head_backward, which must follow on the same stream."""
+    require_cuda(moving, "moving"); require_cuda(target, "target"); require_cuda(feat, "feat")
+    ndim, D, H, W = _vol_dims(moving)
+    lib = _lib.load()
+    dev = moving.device
+    C = int(feat.shape[1])
+    fdims = [1] * (3 - ndim) + [int(v) for v in feat.shape[2:]]
+    f, wt, b = feat.detach().contiguous(), weight.detach().reshape(ndim, C).contiguous(), bias.detach().contiguous()
+    loss = torch.empty(1, dtype=torch.float32, device=dev)
+    flow = torch.empty((1, ndim) + tuple(moving.shape[2:]), dtype=torch.float32, device=dev)
+    ws = _flow_ws(dev)
+    with torch.cuda.device(dev):
+        check(lib.trb_flow_head_forward(ndim, moving.detach().contiguous().data_ptr(), target.detach().contiguous().data_ptr(),
+                                        f.data_ptr(), C, fdims[0], fdims[1], fdims[2], wt.data_ptr(), b.data_ptr(), D, H, W,
+                                        float(w_mse), float(w_ncc), loss.data_ptr(), flow.data_ptr(), ws.data_ptr(), ws.numel(),
+                                        _stream(dev)), "flow_head_forward")
+    return loss, flow
+
+
+def flow_head_backward(moving, target, flow, feat, weight):
+    """-> (d loss / d feat, d loss / d weight [nd,C], d loss / d bias [nd]) for the loss of the preceding flow_head_forward."""
+    ndim, D, H, W = _vol_dims(moving)
+    lib = _lib.load()
+    dev = moving.device
+    C = int(feat.shape[1])
+    fdims = [1] * (3 - ndim) + [int(v) for v in feat.shape[2:]]
+    f, wt = feat.detach().contiguous(), weight.detach().reshape(ndim, C).contiguous()
+    dfeat = torch.empty_like(f)
+    dwb = torch.empty(ndim * C + ndim, dtype=torch.float32, device=dev)
+    ws = _flow_ws(dev)
+    with torch.cuda.device(dev):
+        check(lib.trb_flow_head_backward(ndim, moving.detach().contiguous().data_ptr(), target.detach().contiguous().data_ptr(),
+                                         flow.detach().contiguous().data_ptr(), f.data_ptr(), C, fdims[0], fdims[1], fdims[2],
+                                         wt.data_ptr(), D, H, W, dfeat.data_ptr(), dwb.data_ptr(), ws.data_ptr(), ws.numel(),
+                                         _stream(dev)), "flow_head_backward")
+    return dfeat, dwb[: ndim * C].reshape(ndim, C), dwb[ndim * C:]
+
 def _check_flow(src: torch.Tensor, flow: torch.Tensor):
     require_cuda(src, "src")
     require_cuda(flow, "flow")
@@ -340,7 +397,6 @@ def warp_flow_vjp(src: torch.Tensor, flow: torch.Tensor, grad_out: torch.Tensor)
     return dflow
 
 
-_FLOW_WS = {}
 
 
 def flow_loss_grad(moving: torch.Tensor, target: torch.Tensor, flow: torch.Tensor, w_mse: float, w_ncc: float,

@@ -390,8 +390,9 @@ class Attention_UNet(nn.Module):
         self.maxpool = pool(kernel_size=2, stride=2)
         self.warp = SpatialTransformer(img_size, mode)
 
-    def flow_field(self, x, device):
-        """The network part only: x -> flow (no warp)."""
+    def features(self, x, device):
+        """Decoder output BEFORE the final zero padding and the 1x1 `out` convolution (reference utils.py:523-551):
+        [1, w0, ...] at the valid-convolution size.  flow_field(x) == out(padNd(features(x), x))."""
         y1 = self.layer1(x)
         y2 = self.layer2(self.maxpool(y1))
         y3 = self.layer3(self.maxpool(y2))
@@ -401,7 +402,11 @@ class Attention_UNet(nn.Module):
                                (self.skip2, y2, self.layer8), (self.skip1, y1, self.layer9)):
             gated, _ = skip(enc, y, device=device)
             y = dec(torch.cat((gated, padNd(y, gated, device=device)), dim=1))
-        return self.out(padNd(y, x, device=device))
+        return y
+
+    def flow_field(self, x, device):
+        """The network part only: x -> flow (no warp)."""
+        return self.out(padNd(self.features(x, device), x, device=device))
 
     def forward(self, x, device, out_att=False):
         flow = self.flow_field(x, device)

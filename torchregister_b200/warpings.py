@@ -171,9 +171,9 @@ def affine_register(moving, target, lr=1E-5, epochs=1000, per=0.1, device='cpu',
     nd = moving.dim() - 2
     wp = similarity_weights(criterions, weights, "affine_register")
     if theta0 is None:
-        start = torch.eye(nd, nd + 1, dtype=torch.float32, device=moving.device).reshape(1, -1)  # every pair starts at identity
+        start = torch.eye(nd, nd + 1, dtype=torch.float32).reshape(1, -1)                        # every pair starts at identity (host)
     else:
-        start = torch.as_tensor(theta0, dtype=torch.float32, device=moving.device).reshape(-1, nd * (nd + 1))
+        start = torch.as_tensor(theta0, dtype=torch.float32).reshape(-1, nd * (nd + 1))
     prob, warped, theta = _affine_like("affine", moving, target, lr, epochs, wp, start, debug, _want_warped, optm, betas, eps)
     if _problem_out is not None:
         _problem_out.append(prob)
@@ -238,6 +238,25 @@ class _FlowSimilarityFn(torch.autograd.Function):
         return dflow * grad_loss, None, None, None, None, None
 
 
+class _FlowHeadSimilarityFn(torch.autograd.Function):
+    """the U-Net's last steps — zero padding to the input size and the 1x1 `out` convolution (reference
+    utils.py:553-555) — fused with the warp + similarity node: flow is formed inside the forward kernel, d loss / d flow
+    never leaves the backward kernel, which emits d feat, d W, d b directly."""
+
+    @staticmethod
+    def forward(ctx, feat, weight, bias, moving, target, w_mse, w_ncc):
+        loss, flow = TF.flow_head_forward(moving, target, feat, weight, bias, w_mse, w_ncc)
+        ctx.save_for_backward(feat, weight, flow, moving, target)
+        ctx.mark_non_differentiable(flow)
+        return loss.reshape(()), flow
+
+    @staticmethod
+    def backward(ctx, grad_loss, _grad_flow):
+        feat, weight, flow, moving, target = ctx.saved_tensors
+        dfeat, dw, db = TF.flow_head_backward(moving, target, flow, feat, weight)
+        return dfeat.reshape(feat.shape) * grad_loss, dw.reshape(weight.shape) * grad_loss, db * grad_loss, None, None, None, None
+
+
 class flow_register(nn.Module):
     """Deformable registration: an Attention_UNet maps `moving` to a dense flow, optimised with SGD
     on the network weights (reference warpings.py:178-242).  The U-Net stays PyTorch/cuDNN; the
@@ -261,6 +280,7 @@ class flow_register(nn.Module):
         self.lr, self.max_epochs, self.stop_crit = lr, max_epochs, stop_crit
         self.optimizer = torch.optim.SGD(self.model.parameters(), lr)
         self.losses = []
+        self.fuse_head = True           # U-Net head (pad + 1x1 conv) fused into the node's kernels when it applies
 
     def forward(self, x, device):
         y, self.flow = self.model(x, device)
@@ -273,8 +293,24 @@ class flow_register(nn.Module):
         self.losses = []
         message = 'Reached max epochs'
         self.train()
+        out = self.model.out
+        fused_head = (not other and self.fuse_head and moving.shape[0] == 1 and moving.shape[1] == 1
+                      and out.in_channels <= 8 and out.bias is not None and all(k == 1 for k in out.kernel_size))
         for eps in range(self.max_epochs):
             self.optimizer.zero_grad()
+            if fused_head:
+                # padNd + the 1x1 `out` convolution + warp + similarity + their backward: two kernels (f-3)
+                feat = self.model.features(moving, device)
+                error, flow = _FlowHeadSimilarityFn.apply(feat, out.weight, out.bias, moving, target, w_mse, w_ncc)
+                self.flow = flow
+                error.backward()
+                self.optimizer.step()
+                self.warp = self.model.warp
+                self.losses.append(error.item())
+                if self.losses[-1] <= self.stop_crit:
+                    message = 'Converged to %f' % self.stop_crit
+                    break
+                continue
             flow = self.model.flow_field(moving, device)
             self.flow = flow
             if other:
