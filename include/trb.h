@@ -160,6 +160,14 @@ int trb_affine_moments(int ndim,
                        const float *state_dev, double *moments_dev,
                        void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* The same with option flags (TRB_FLAG_LARGE_ROTATION: gather variant, see trb_affine_optim_ex). */
+int trb_affine_moments_ex(int ndim,
+                          const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs,
+                          int D, int H, int W, int s_begin, int s_end,
+                          const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                          const float *state_dev, double *moments_dev, int flags,
+                          void *workspace_dev, size_t workspace_bytes, void *stream);
+
 /* extra_dev (optional, may be NULL): [n_pairs][13] fp64 = an additional loss term and its gradient w.r.t.
  * theta, evaluated outside (used for the NMI/KDE term, reference utils.py:224-259, until it is fused). */
 int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs,
@@ -191,6 +199,11 @@ int trb_warp_affine_vjp(int ndim, const float *moving_dev, const float *gout_dev
                         int D, int H, int W, const float *theta_dev,
                         const float *xb_dev, const float *yb_dev, const float *zb_dev,
                         double *dtheta_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+
+int trb_warp_affine_vjp_ex(int ndim, const float *moving_dev, const float *gout_dev,
+                           int D, int H, int W, const float *theta_dev,
+                           const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                           double *dtheta_dev, int flags, void *workspace_dev, size_t workspace_bytes, void *stream);
 
 /* ---- flow field ----------------------------------------------------------- */
 /* flow layout [ndim][D][H][W] fp32 in voxel units, channel i displaces spatial

@@ -178,3 +178,21 @@ def test_compose_theta_matches_chained_matrices():
         x = torch.randn(4, nd, 1, generator=g)
         chained = a[:, :, :nd] @ (b[:, :, :nd] @ x + b[:, :, nd:]) + a[:, :, nd:]
         assert torch.allclose(c[:, :, :nd] @ x + c[:, :, nd:], chained, atol=1e-5)
+
+
+def test_tile_fits_helper_runs_on_the_host():
+    """trb_affine_tile_fits (kernel-variant hint) is a pure host function: identity and small rotations fit the staged box,
+    the reference's own torch.rand(6) start (angles up to 1 rad, utils.py:317) does not."""
+    import ctypes as C
+    import math
+    from torchregister_b200 import _lib
+    lib = _lib.load()
+
+    def rot_z(a):
+        c, s = math.cos(a), math.sin(a)
+        return (C.c_float * 12)(c, -s, 0, 0, s, c, 0, 0, 0, 0, 1, 0)
+    assert lib.trb_affine_tile_fits(192, 192, 160, rot_z(0.0)) == 1
+    assert lib.trb_affine_tile_fits(192, 192, 160, rot_z(0.05)) == 1
+    assert lib.trb_affine_tile_fits(192, 192, 160, rot_z(0.5)) == 0
+    assert lib.trb_affine_tile_fits(256, 256, 256, rot_z(1.0)) == 0
+    assert lib.trb_affine_tile_fits(0, 0, 0, rot_z(0.0)) == 0

@@ -58,3 +58,35 @@ for name, p0 in (("small", small), ("rand(6) seed 0", rand0), ("10 deg z", torch
 for large in (False, True):
     us = timeit((192, 192, 160), rand0, large, n_pairs=8)
     print("batch8 rand(6) %s %.1f us/epoch" % ("gather" if large else "tma   ", us), flush=True)
+
+# unfused moments pass through the gather variant (large rotations) vs the per-epoch kernel / direct kernel
+m, t = make_pair((40, 48, 64), "rigid", seed=5, device=dev)
+ok2 = True
+for lo, hi in ((0, 40), (7, 29)):
+    res = []
+    for large, path in ((True, "auto"), (False, "auto"), (False, "direct")):
+        TF.set_kernel_path(path)
+        prob = TF.AffineProblem(m, t, "rigid", rand0.to(dev), 2, large_rotation=large)
+        res.append(prob.moments(lo, hi).cpu())
+    TF.set_kernel_path("auto")
+    # entries of one family (12 sums of signed gradients) cancel: compare against the family's largest entry
+    scale = torch.cat([res[2][:, :5].abs(), res[2][:, 5:].abs().reshape(-1, 3, 12).amax(dim=2, keepdim=True).expand(-1, 3, 12).reshape(-1, 36)], dim=1).clamp_min(1e-6)
+    e1 = ((res[0] - res[2]).abs() / scale).max().item(); e2 = ((res[1] - res[2]).abs() / scale).max().item()
+    ok2 &= e1 < 1e-4
+    print("moments slab [%d,%d): gather vs direct %.2e, per-epoch kernel vs direct %.2e" % (lo, hi, e1, e2))
+import torchregister_b200 as tr
+torch.manual_seed(0)
+a = tr.Register(mode="rigid", device=dev); a.optim(m, t, lr=1e-4, max_epochs=4)
+la = a.losses.cpu()
+torch.manual_seed(0)
+import torchregister_b200.warpings as WP
+b = tr.Register(mode="rigid", device=dev)
+orig = TF.AffineProblem._start_needs_gather
+TF.AffineProblem._start_needs_gather = lambda self, p0: False
+b.optim(m, t, lr=1e-4, max_epochs=4)
+TF.AffineProblem._start_needs_gather = orig
+lb = b.losses.cpu()
+e = ((la - lb).abs() / lb.abs()).max().item()
+ok2 &= e < 1e-5
+print("stock call (rand start, default loss incl. NMI): gather passes vs per-epoch kernel passes: loss rel diff %.2e" % e, la.tolist())
+print("ROT MOMENTS", "OK" if ok2 else "FAIL")

@@ -30,6 +30,9 @@ _SIGNATURES = {
     "trb_affine_tile_fits": (_i, [_i, _i, _i, C.POINTER(C.c_float)]),
     "trb_affine_moments": (_i, [_i, c_fp, c_fp, _ll, _i, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp,
                                 c_fp, _sz, c_fp]),
+    "trb_affine_moments_ex": (_i, [_i, c_fp, c_fp, _ll, _i, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i,
+                                   c_fp, _sz, c_fp]),
+    "trb_warp_affine_vjp_ex": (_i, [_i, c_fp, c_fp, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i, c_fp, _sz, c_fp]),
     "trb_affine_apply": (_i, [_i, _i, c_fp, _i, _i, _i, _i, c_fp, c_fp, _i, _i, _f, _f, _f, _i, _f, _f, _f, c_fp, c_fp]),
     "trb_warp_affine": (_i, [_i, c_fp, c_fp, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp]),
     "trb_warp_affine_batch": (_i, [_i, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, _i, c_fp]),

@@ -481,11 +481,11 @@ extern "C" int trb_affine_optim_peer(const float *moving_dev, const float *targe
     return launch_affine3d_tma(p, 1, true, epoch0, n_epochs, (cudaStream_t)stream);
 }
 
-extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
-                                  int n_pairs, int D, int H, int W, int s_begin, int s_end,
-                                  const float *xb_dev, const float *yb_dev, const float *zb_dev,
-                                  const float *state_dev, double *moments_dev,
-                                  void *workspace_dev, size_t workspace_bytes, void *stream)
+static int affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
+                               int n_pairs, int D, int H, int W, int s_begin, int s_end,
+                               const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                               const float *state_dev, double *moments_dev, int flags, bool want_target_sums,
+                               void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     AffineParams p{};
     int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
@@ -497,14 +497,42 @@ extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float
     p.s_begin = s_begin; p.s_end = s_end;
     p.state = const_cast<float *>(state_dev);
     p.moments_out = moments_dev;
+    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
-    if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs))
+    if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
+        if (p.gather) {
+            // large rotations: one pass of the persistent kernel's gather variant instead of the per-epoch kernel's
+            // uncached fallback (2-3x faster there); small rotations: the per-epoch kernel has the lower fixed cost
+            rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, want_target_sums ? 1 : 2);
+            if (rc != TRB_ERR_UNSUPPORTED) return rc;
+        }
         return launch_affine3d_tma(p, n_pairs, false, 0, 1, s);
+    }
     const int rows = (s_end - s_begin) * (ndim == 3 ? H : 1);
     const dim3 grid(blocks_per_pair(rows, n_pairs), n_pairs);
     if (ndim == 3) affine_moments_kernel<3, false><<<grid, kThreads, 0, s>>>(p);
     else affine_moments_kernel<2, false><<<grid, kThreads, 0, s>>>(p);
     return check_cuda(cudaGetLastError(), "affine_moments");
+}
+
+extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
+                                  int n_pairs, int D, int H, int W, int s_begin, int s_end,
+                                  const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                  const float *state_dev, double *moments_dev,
+                                  void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    return affine_moments_impl(ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, s_begin, s_end, xb_dev, yb_dev, zb_dev,
+                               state_dev, moments_dev, 0, true, workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int trb_affine_moments_ex(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
+                                     int n_pairs, int D, int H, int W, int s_begin, int s_end,
+                                     const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                     const float *state_dev, double *moments_dev, int flags,
+                                     void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    return affine_moments_impl(ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, s_begin, s_end, xb_dev, yb_dev, zb_dev,
+                               state_dev, moments_dev, flags, true, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs, int D, int H, int W,
@@ -567,6 +595,14 @@ extern "C" int trb_warp_affine_vjp(int ndim, const float *moving_dev, const floa
                                    const float *theta_dev, const float *xb_dev, const float *yb_dev, const float *zb_dev,
                                    double *dtheta_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
+    return trb_warp_affine_vjp_ex(ndim, moving_dev, gout_dev, D, H, W, theta_dev, xb_dev, yb_dev, zb_dev, dtheta_dev, 0,
+                                  workspace_dev, workspace_bytes, stream);
+}
+
+extern "C" int trb_warp_affine_vjp_ex(int ndim, const float *moving_dev, const float *gout_dev, int D, int H, int W,
+                                      const float *theta_dev, const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                                      double *dtheta_dev, int flags, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
     // Reuses the moments pass with gout in the target slot: sum_v gout_v * J_v is moment block [17..28].
     // The unfused pass only ever reads state[TRB_STATE_THETA .. +12), so a bare theta pointer is rebased.
     if (!dtheta_dev) { set_error("null dtheta"); return TRB_ERR_ARG; }
@@ -575,8 +611,8 @@ extern "C" int trb_warp_affine_vjp(int ndim, const float *moving_dev, const floa
         return TRB_ERR_WORKSPACE;
     }
     double *mom = (double *)((char *)workspace_dev + affine_ws_bytes(1));
-    int rc = trb_affine_moments(ndim, moving_dev, gout_dev, 0, 1, D, H, W, 0, ndim == 3 ? D : H, xb_dev, yb_dev, zb_dev,
-                                theta_dev - TRB_STATE_THETA, mom, workspace_dev, affine_ws_bytes(1), stream);
+    int rc = affine_moments_impl(ndim, moving_dev, gout_dev, 0, 1, D, H, W, 0, ndim == 3 ? D : H, xb_dev, yb_dev, zb_dev,
+                                 theta_dev - TRB_STATE_THETA, mom, flags, false, workspace_dev, affine_ws_bytes(1), stream);
     if (rc) return rc;
     vjp_extract_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mom, dtheta_dev, ndim, ndim == 3 ? D : 1, H, W);
     return check_cuda(cudaGetLastError(), "warp_affine_vjp");

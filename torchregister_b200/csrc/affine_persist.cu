@@ -66,7 +66,8 @@ struct __align__(16) PCol { int x0, y0, pair, pad; float coef[12]; };
 
 struct PersistParams {
     TmaParams t;
-    int tsum_blocks;                 // blocks per pair of target_sums_kernel (= count field of its words)
+    int tsum_blocks;                 // blocks per pair of target_sums_kernel (= count field of its words); 0: no target sums
+    int moments_only;                // 1: ONE pass at the theta in `state`, the 41 moments go to a.moments_out, no update
     int n_epochs;                    // epochs in this launch (<= chunk capacity of the accumulator region)
     unsigned long long *acc;         // [n_epochs][n_pairs][kAccWords], zeroed before the launch
     const unsigned *targets;         // tickets region; word [pair*kTicketStride + kTargetWord]
@@ -338,6 +339,12 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
     __syncwarp();
     if (tsum && lane == 0 && !bad) { mrow[0] = tsum[0]; mrow[2] = tsum[1]; }
     __syncwarp();
+    if (pp.moments_only) {                       // unfused pass (sharded NCCL form, NMI path, vjp): hand the sums out
+        if (writer)
+            for (int v = lane; v < TRB_MOMENTS; v += 32) a.moments_out[(size_t)pair * TRB_MOMENTS + v] = mrow[v];
+        __syncwarp();
+        return;
+    }
     if (a.peer.world > 1) {
         // one volume sharded into z-slabs over the GPUs of the box: the designated CTA of every rank pushes this
         // rank's 41 sums into every rank's mailbox over NVLink (peer.cuh), EVERY CTA of a rank then reads its own
@@ -598,10 +605,14 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                                 slot_target[n_slots] = pp.targets[(size_t)pair * kTicketStride + kTargetWord];
                                 slot_writer[n_slots] = (t.cg == pair * p.cols_per_pair && t.tz_i == 0) ? 1 : 0;
                             }
-                            if (need_tsum && lane < 2) slot_tsum[n_slots][lane] = tsum_read(pp.targets, pair, lane, (unsigned)pp.tsum_blocks);
+                            if (need_tsum && lane < 2) slot_tsum[n_slots][lane] = pp.tsum_blocks > 0 ? tsum_read(pp.targets, pair, lane, (unsigned)pp.tsum_blocks) : 0.0;
                             const float *src = p.a.state + (size_t)pair * TRB_STATE_FLOATS;
-                            state_s[n_slots * TRB_STATE_FLOATS + lane] = __ldcg(src + lane);
-                            state_s[n_slots * TRB_STATE_FLOATS + 32 + lane] = __ldcg(src + 32 + lane);
+                            if (pp.moments_only) {          // only theta is read (the caller may pass a bare theta rebased by -12)
+                                if (lane < 12) state_s[n_slots * TRB_STATE_FLOATS + TRB_STATE_THETA + lane] = __ldcg(src + TRB_STATE_THETA + lane);
+                            } else {
+                                state_s[n_slots * TRB_STATE_FLOATS + lane] = __ldcg(src + lane);
+                                state_s[n_slots * TRB_STATE_FLOATS + 32 + lane] = __ldcg(src + 32 + lane);
+                            }
                         }
                         ++n_slots;
                         last = pair;
@@ -634,6 +645,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                 if (!slot_writer[sl]) continue;
                 float *st = state_s + sl * TRB_STATE_FLOATS;
                 acquire_theta(pp, pp.n_epochs, slot_pair[sl], st, true, slot_target[sl], need_tsum ? slot_tsum[sl] : nullptr, accw, mrow, lane);
+                if (pp.moments_only) continue;
                 float *dst = p.a.state + (size_t)slot_pair[sl] * TRB_STATE_FLOATS;
                 dst[lane] = st[lane];
                 dst[32 + lane] = st[32 + lane];
@@ -782,7 +794,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             }
             const int cbuf = kcol & 1, use = kcol >> 1;
             if (use > 0) mbar_wait(red_empty + cbuf, (unsigned)(use - 1) & 1u);
-            warp_reduce_moments(acc, red + (cbuf * kConsumerWarps + warp) * kRedLdP, lane);
+            warp_reduce_moments2(acc, red + (cbuf * kConsumerWarps + warp) * kRedLdP, lane);
             __syncwarp();
             if (lane == 0) mbar_arrive(red_full + cbuf);
             ++kcol;
@@ -822,8 +834,11 @@ static thread_local char g_persist_status[256] = "never called";
 
 // Enqueue n_epochs fused epochs for n_pairs pairs with the persistent kernel.  Returns TRB_ERR_UNSUPPORTED (without
 // enqueuing anything) when the configuration does not fit it; the caller then takes the per-epoch kernel.
-int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream)
+int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream, int moments_mode)
 {
+    // moments_mode: 0 = fused epochs; 1 = one unfused pass (moments to a.moments_out); 2 = the same without target sums
+    const bool moments_only = moments_mode != 0;
+    if (moments_only) n_epochs = 1;
     if (g_no_persist || a.extra) PERSIST_REFUSE("disabled (kernel path / extra term)");
     if (a.peer.world > 1 && n_pairs != 1) PERSIST_REFUSE("peer exchange needs one pair");
     int dev = 0, sms = 0, coop = 0;
@@ -831,7 +846,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (!coop || sms < 1) PERSIST_REFUSE("no cooperative launch (coop %d, sms %d)", coop, sms);
-    const bool mse_only = a.w_ncc == 0.f;
+    const bool mse_only = !moments_only && a.w_ncc == 0.f;
     const bool rot = a.gather != 0;
     auto kern = rot ? (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>)
                     : (mse_only ? affine3d_persist_kernel<true, false> : affine3d_persist_kernel<false, false>);
@@ -897,8 +912,10 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         if (e != cudaSuccess) return check_cuda(e, "cudaMemcpy2DAsync(contributions)");
         pp.acc = reinterpret_cast<unsigned long long *>(as.partials);
         pp.targets = as.tickets;
-        pp.tsum_blocks = kTsumBlocks;
-        if (!mse_only) {
+        pp.tsum_blocks = (mse_only || moments_mode == 2) ? 0 : kTsumBlocks;
+        pp.moments_only = moments_only ? 1 : 0;
+        if (moments_only) pp.t.a.moments_out = a.moments_out + (size_t)p0 * TRB_MOMENTS;
+        if (pp.tsum_blocks > 0) {
             e = cudaMemset2DAsync(as.tickets + kTsumWord, kTicketStride * sizeof(unsigned), 0, 2 * kLimbs * sizeof(unsigned long long), (size_t)np, stream);
             if (e != cudaSuccess) return check_cuda(e, "cudaMemset2DAsync(target sums)");
             const long long slab = (long long)as.H * as.W;

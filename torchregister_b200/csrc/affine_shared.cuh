@@ -16,7 +16,7 @@ struct AffineParams;
 bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs);
 int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int n_launch, cudaStream_t stream);
 // persistent multi-epoch kernel (affine_persist.cu); TRB_ERR_UNSUPPORTED = nothing enqueued, take the per-epoch kernel
-int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream);
+int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream, int moments_mode = 0);
 void set_no_persist(bool v);
 const char *persist_status();
 // TMA-staged forward warp (warp_tma.cu)

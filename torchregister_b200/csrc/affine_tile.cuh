@@ -526,6 +526,49 @@ __device__ __forceinline__ void warp_reduce_moments(const float (&acc)[TRB_MOMEN
     }
 }
 
+// the same with the nine values beyond 32 reduced "transposed" as well (padded to 16: 16 shuffles instead of 45)
+__device__ __forceinline__ void warp_reduce_moments2(const float (&acc)[TRB_MOMENTS], float *dst /*[41] smem*/, int lane)
+{
+    float v[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = acc[i];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+#pragma unroll
+        for (int i = 0; i < off; ++i) {
+            const float send = up ? v[i] : v[i + off];
+            const float keep = up ? v[i + off] : v[i];
+            v[i] = keep + __shfl_xor_sync(kFull, send, off);
+        }
+    }
+    dst[lane] = v[0];
+    float w[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) w[i] = (32 + i < TRB_MOMENTS) ? acc[32 + i] : 0.f;
+#pragma unroll
+    for (int off = 16, cnt = 16; off >= 1; off >>= 1) {
+        const bool up = (lane & off) != 0;
+        if (cnt > 1) {
+            const int half = cnt / 2;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (i < half) {
+                    const float send = up ? w[i] : w[i + half];
+                    const float keep = up ? w[i + half] : w[i];
+                    w[i] = keep + __shfl_xor_sync(kFull, send, off);
+                }
+            }
+            cnt = half;
+        } else {
+            w[0] += __shfl_xor_sync(kFull, w[0], off);
+        }
+    }
+    // lane l holds value 32 + ((l >> 1) & 15) (lanes l and l ^ 1 the same total)
+    const int idx = 32 + ((lane >> 1) & 15);
+    if ((lane & 1) == 0 && idx < TRB_MOMENTS) dst[idx] = w[0];
+}
+
 // ---- host side ---------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
                                   const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,

@@ -201,10 +201,10 @@ class AffineProblem:
         if out is None:
             out = torch.empty(self.n_pairs, MOMENTS, dtype=torch.float64, device=self.device)
         with torch.cuda.device(self.device):
-            check(self.lib.trb_affine_moments(
+            check(self.lib.trb_affine_moments_ex(
                 self.ndim, self.moving.data_ptr(), self.target.data_ptr(), self.pair_stride, self.n_pairs,
                 self.D, self.H, self.W, int(s_begin), int(s_end), self.xb.data_ptr(), self.yb.data_ptr(),
-                _ptr(self.zb), self.state.data_ptr(), out.data_ptr(), self.workspace.data_ptr(),
+                _ptr(self.zb), self.state.data_ptr(), out.data_ptr(), int(self.flags), self.workspace.data_ptr(),
                 self.workspace.numel(), _stream(self.device)), "affine_moments")
         return out
 
@@ -279,7 +279,7 @@ def warp_affine(theta: torch.Tensor, moving: torch.Tensor, out: Optional[torch.T
     return out
 
 
-def warp_affine_vjp(theta: torch.Tensor, moving: torch.Tensor, grad_out: torch.Tensor) -> torch.Tensor:
+def warp_affine_vjp(theta: torch.Tensor, moving: torch.Tensor, grad_out: torch.Tensor, large_rotation: bool = False) -> torch.Tensor:
     """d theta (fp64 [ndim, ndim+1]) = sum_v grad_out_v * d warped_v / d theta; single channel."""
     require_cuda(moving, "moving")
     require_cuda(grad_out, "grad_out")
@@ -295,9 +295,10 @@ def warp_affine_vjp(theta: torch.Tensor, moving: torch.Tensor, grad_out: torch.T
     xb, yb = base_coords(W, dev), base_coords(H, dev)
     zb = base_coords(D, dev) if ndim == 3 else None
     with torch.cuda.device(dev):
-        check(lib.trb_warp_affine_vjp(ndim, moving.contiguous().data_ptr(), grad_out.contiguous().data_ptr(),
-                                      D, H, W, th.data_ptr(), xb.data_ptr(), yb.data_ptr(), _ptr(zb),
-                                      out.data_ptr(), ws.data_ptr(), ws.numel(), _stream(dev)), "warp_affine_vjp")
+        check(lib.trb_warp_affine_vjp_ex(ndim, moving.contiguous().data_ptr(), grad_out.contiguous().data_ptr(),
+                                         D, H, W, th.data_ptr(), xb.data_ptr(), yb.data_ptr(), _ptr(zb),
+                                         out.data_ptr(), 1 if large_rotation else 0, ws.data_ptr(), ws.numel(), _stream(dev)),
+              "warp_affine_vjp")
     return out.reshape(ndim, ndim + 1)
 
 

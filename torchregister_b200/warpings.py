@@ -133,15 +133,16 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
         n_slices = int(moving.shape[2])
         n_pairs = int(moving.shape[0])
         terms = [TF.NmiTerm(target[i:i + 1]) for i in range(n_pairs)]     # NMILoss() defaults: bandwidth 3, alpha 1000
+        big = bool(prob.flags & 1)            # start theta is a large rotation: gather kernels for the three passes
         extra = torch.zeros(n_pairs, 13, dtype=torch.float64, device=moving.device)
         for _ in range(epochs):
             theta = prob.theta
             mom = prob.moments(0, n_slices)
             for i in range(n_pairs):
-                warped = TF.warp_affine(theta[i], moving[i:i + 1])
+                warped = TF.warp_affine(theta[i], moving[i:i + 1], large_rotation=big)
                 term, gw = terms[i].loss_grad(warped, w_nmi)
                 extra[i, 0:1] = term
-                extra[i, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta[i], moving[i:i + 1], gw).reshape(-1)
+                extra[i, 1:1 + nd * (nd + 1)] = TF.warp_affine_vjp(theta[i], moving[i:i + 1], gw, large_rotation=big).reshape(-1)
             prob.apply(mom, lr, w_mse, w_ncc, optimiser=opt, betas=betas, eps=eps, extra=extra)
     final_theta, best_theta = prob.final_theta, prob.best_theta          # [1, nd, nd+1]
     # the reference keeps the warped volumes of the final and best epochs; we never write them during
