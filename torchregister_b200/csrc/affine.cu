@@ -500,7 +500,8 @@ static int affine_moments_impl(int ndim, const float *moving_dev, const float *t
     p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
-        if (p.gather) {
+        static const bool force_persist = getenv("TRB_MOMENTS_PERSIST") != nullptr;
+        if (p.gather || force_persist) {
             // large rotations: one pass of the persistent kernel's gather variant instead of the per-epoch kernel's
             // uncached fallback (2-3x faster there); small rotations: the per-epoch kernel has the lower fixed cost
             rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, want_target_sums ? 1 : 2);

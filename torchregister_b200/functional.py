@@ -124,6 +124,7 @@ class AffineProblem:
         ws_bytes = int(self.lib.trb_affine_workspace_bytes(self.n_pairs))
         self.workspace = torch.zeros(ws_bytes, dtype=torch.uint8, device=self.device)   # zero: tickets start at 0
         self.epoch = 0
+        self._default_scratch = None          # run_default: warped volumes + d term / d warped
         with torch.cuda.device(self.device):
             check(self.lib.trb_affine_init_state(self.ndim, MODE[mode], self.state.data_ptr(), self.n_pairs,
                                                  _stream(self.device)), "affine_init_state")
@@ -170,6 +171,30 @@ class AffineProblem:
                 self.state.data_ptr(), self.loss_log.data_ptr(), self.loss_log.shape[1], self.epoch, n_epochs,
                 float(w_mse), float(w_ncc), float(lr), OPT[optimiser], float(betas[0]), float(betas[1]), float(eps),
                 int(self.flags), self.workspace.data_ptr(), self.workspace.numel(), _stream(self.device)), "affine_optim")
+        self.epoch += n_epochs
+
+    def run_default(self, n_epochs: int, lr: float, w_mse: float, w_ncc: float, w_nmi: float, term: "NmiSourceTerm",
+                    optimiser: str = "sgd", betas=(0.9, 0.999), eps: float = 1e-8) -> None:
+        """Enqueue `n_epochs` epochs of the reference's DEFAULT loss [MSE, NCC, NMI] (warpings.py:36-40,123-159) with one
+        C-ABI call: the NMI term runs in its source-space form (`term`, built on this problem's targets).  3-D,
+        single-channel volumes."""
+        if n_epochs <= 0:
+            return
+        if self.epoch + n_epochs > self.max_epochs:
+            raise ValueError("max_epochs exceeded")
+        if self.ndim != 3 or self.pair_stride != self.D * self.H * self.W or term.n_pairs != self.n_pairs:
+            raise ValueError("run_default handles [N,1,D,H,W] volumes and a term built on the same batch")
+        if self._default_scratch is None:
+            self._default_scratch = torch.empty((2,) + tuple(self.target.shape), dtype=torch.float32, device=self.device)
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_affine_optim_nmi(
+                MODE[self.mode], self.moving.data_ptr(), self.target.data_ptr(), self.n_pairs, self.D, self.H, self.W,
+                self.xb.data_ptr(), self.yb.data_ptr(), _ptr(self.zb), self.state.data_ptr(), self.loss_log.data_ptr(),
+                self.loss_log.shape[1], self.epoch, n_epochs, float(w_mse), float(w_ncc), float(w_nmi), float(lr),
+                OPT[optimiser], float(betas[0]), float(betas[1]), float(eps), int(self.flags), term.bandwidth, term.alpha,
+                term.lo, term.hi, self._default_scratch[0].data_ptr(), self._default_scratch[1].data_ptr(),
+                term.workspace.data_ptr(), term.workspace.numel(), self.workspace.data_ptr(), self.workspace.numel(),
+                _stream(self.device)), "affine_optim_nmi")
         self.epoch += n_epochs
 
     # -- sharded (z-slab) form, fused: the epoch kernel all-reduces the moments itself through peer memory
@@ -461,6 +486,57 @@ class NmiTerm:
             check(self.lib.trb_nmi_loss_grad(self.ndim, w.data_ptr(), self.D, self.H, self.W, self.bandwidth, self.alpha,
                                              float(weight), self.loss.data_ptr(), _ptr(gout), self.workspace.data_ptr(),
                                              self.workspace.numel(), _stream(self.device)), "nmi_loss_grad")
+        return self.loss, gout
+
+
+class NmiSourceTerm:
+    """The same term for a BATCH of 3-D pairs, evaluated in source-voxel space (csrc/nmi_src.cu): no resampled arrays, one
+    pass over the warped volumes + one pass writing the gradient.  Needs all values of the targets and of every warped
+    volume inside [lo, hi] with hi - lo <= 0.6 * bandwidth (`bounds()` derives them; images normalised to [0,1] qualify
+    with the default bandwidth 3); the loss is NaN if a value leaves the bounds."""
+
+    MAX_RANGE = 0.6          # in bandwidths (Hermite-moment regime of the KDE)
+
+    @staticmethod
+    def bounds(moving: torch.Tensor, target: torch.Tensor):
+        """Value bounds that hold for the targets and for ANY warp of the moving volumes (a trilinear sample with zero
+        padding is a convex combination of voxel values and 0).  One host synchronisation."""
+        v = torch.stack([moving.amin(), target.amin(), moving.amax(), target.amax()]).tolist()
+        return min(0.0, v[0], v[1]), max(0.0, v[2], v[3])
+
+    @classmethod
+    def eligible(cls, moving: torch.Tensor, lo: float, hi: float, bandwidth: float = 3.0) -> bool:
+        return moving.dim() == 5 and moving.shape[1] == 1 and (hi - lo) <= cls.MAX_RANGE * bandwidth and lo <= hi
+
+    def __init__(self, target: torch.Tensor, lo: float, hi: float, bandwidth: float = 3.0, alpha: float = 1000.0):
+        require_cuda(target, "target")
+        self.lib = _lib.load()
+        if target.dim() != 5 or target.shape[1] != 1:
+            raise ValueError("NmiSourceTerm expects [N,1,D,H,W] targets")
+        self.device = target.device
+        self.n_pairs, _, self.D, self.H, self.W = (int(v) for v in target.shape)
+        self.bandwidth, self.alpha, self.lo, self.hi = float(bandwidth), float(alpha), float(lo), float(hi)
+        n = int(self.lib.trb_nmi_src_workspace_bytes(self.n_pairs, self.D, self.H, self.W))
+        self.workspace = torch.empty(n, dtype=torch.uint8, device=self.device)
+        self.loss = torch.zeros(self.n_pairs, dtype=torch.float64, device=self.device)
+        t = target.detach().contiguous().float()
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_nmi_src_prepare(t.data_ptr(), self.D * self.H * self.W, self.n_pairs, self.D, self.H, self.W,
+                                               self.bandwidth, self.lo, self.hi, self.workspace.data_ptr(),
+                                               self.workspace.numel(), _stream(self.device)), "nmi_src_prepare")
+
+    def loss_grad(self, warped: torch.Tensor, weight: float = 1.0, want_grad: bool = True):
+        """-> (weight*loss per pair, [N] fp64 device tensor overwritten by the next call; weight * d loss / d warped or None)."""
+        require_cuda(warped, "warped")
+        if tuple(warped.shape) != (self.n_pairs, 1, self.D, self.H, self.W):
+            raise ValueError("warped must have the targets' [N,1,D,H,W] shape")
+        w = warped.detach().contiguous().float()
+        gout = torch.empty_like(w) if want_grad else None
+        with torch.cuda.device(self.device):
+            check(self.lib.trb_nmi_src_loss_grad(w.data_ptr(), self.D * self.H * self.W, self.n_pairs, self.D, self.H, self.W,
+                                                 self.bandwidth, self.alpha, float(weight), self.lo, self.hi,
+                                                 self.loss.data_ptr(), 1, _ptr(gout), self.workspace.data_ptr(),
+                                                 self.workspace.numel(), _stream(self.device)), "nmi_src_loss_grad")
         return self.loss, gout
 
 

@@ -107,6 +107,19 @@ def _warp_batch(theta, moving):
     return TF.warp_affine(theta, moving)
 
 
+_NMI_FORM = 'auto'
+
+
+def set_nmi_form(form: str = 'auto') -> None:
+    """Evaluation of the default loss's NMI term in the rigid/affine loops: 'auto' (source-space form inside one C-ABI loop
+    when the volumes allow it, else the per-epoch form on the resampled 200^n arrays), 'resampled' (always the latter;
+    tests / A-B timing) or 'source' (raise if the source-space form cannot be used)."""
+    global _NMI_FORM
+    if form not in ('auto', 'resampled', 'source'):
+        raise ValueError("form must be 'auto', 'resampled' or 'source'")
+    _NMI_FORM = form
+
+
 def _optimiser_name(optm) -> str:
     """'SGD' (the reference's only optimiser, warpings.py:58,131) or 'ADAM' (keyword-only extension; the reference's
     docstring names an `optm` parameter it never implements, torchregister.py:28-29)."""
@@ -132,7 +145,17 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
         nd = moving.dim() - 2
         n_slices = int(moving.shape[2])
         n_pairs = int(moving.shape[0])
-        terms = [TF.NmiTerm(target[i:i + 1]) for i in range(n_pairs)]     # NMILoss() defaults: bandwidth 3, alpha 1000
+        if nd == 3 and _NMI_FORM != 'resampled':
+            # 3-D volumes whose value range is narrow against the KDE bandwidth (e.g. normalised to [0,1]): the whole loop is
+            # ONE C-ABI call, the NMI term evaluated in source-voxel space (csrc/nmi_src.cu); no per-epoch host work
+            lo, hi = TF.NmiSourceTerm.bounds(prob.moving, prob.target)
+            if TF.NmiSourceTerm.eligible(prob.moving, lo, hi):
+                term = TF.NmiSourceTerm(prob.target, lo, hi)                 # NMILoss() defaults: bandwidth 3, alpha 1000
+                prob.run_default(epochs, lr, w_mse, w_ncc, w_nmi, term, optimiser=opt, betas=betas, eps=eps)
+                epochs = 0
+            elif _NMI_FORM == 'source':
+                raise ValueError("source-space NMI needs a value range <= 0.6 bandwidths (got [%g, %g])" % (lo, hi))
+        terms = [TF.NmiTerm(target[i:i + 1]) for i in range(n_pairs)] if epochs else []
         big = bool(prob.flags & 1)            # start theta is a large rotation: gather kernels for the three passes
         extra = torch.zeros(n_pairs, 13, dtype=torch.float64, device=moving.device)
         for _ in range(epochs):
