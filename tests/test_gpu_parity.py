@@ -542,6 +542,106 @@ def test_nmi_kernels_vs_torch_restatement(shape, scale):
     assert none is None and loss3.item() == loss
 
 
+@pytest.mark.parametrize("shape,n", [((24, 32, 40), 1), ((24, 32, 64), 3), ((40, 47, 33), 2), ((210, 96, 230), 1), ((160, 192, 192), 1)])
+def test_nmi_source_space_term_vs_torch_restatement(shape, n):
+    """csrc/nmi_src.cu (source-voxel space, power moments about a fixed centre, batched over pairs) against the fp64
+    PyTorch restatement of the reference's arithmetic on the resampled 200^3 arrays, and against csrc/nmi.cu: up- and
+    down-sampling shapes, a shape without 16-byte rows (scalar loads), several pairs per call.  Same tolerance rule as
+    test_nmi_kernels_vs_torch_restatement."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    pairs = [make_pair(shape, "rigid", device=DEV, seed=900 + i) for i in range(n)]
+    yp, y = torch.cat([p[0] for p in pairs]).contiguous(), torch.cat([p[1] for p in pairs]).contiguous()
+    lo, hi = TF.NmiSourceTerm.bounds(yp, y)
+    assert TF.NmiSourceTerm.eligible(yp, lo, hi)
+    term = TF.NmiSourceTerm(y, lo, hi)
+    loss, g = term.loss_grad(yp, 1.0)
+    loss = loss.clone()
+    for i in range(n):
+        l64, g64 = _nmi_restatement(y[i:i + 1], yp[i:i + 1], torch.float64)
+        l32, g32 = _nmi_restatement(y[i:i + 1], yp[i:i + 1], torch.float32)
+        assert abs(loss[i].item() - l64) <= max(1e-4 * abs(l64), 2 * abs(l32 - l64)), (i, loss[i].item(), l64, l32)
+        gmax = g64.abs().max().item()
+        err = (g[i:i + 1].double() - g64).abs().max().item()
+        err32 = (g32.double() - g64).abs().max().item()
+        assert err <= max(1e-4 * gmax, 2 * err32), (i, err, err32, gmax)
+        old_l, old_g = TF.NmiTerm(y[i:i + 1]).loss_grad(yp[i:i + 1], 1.0)
+        assert abs(loss[i].item() - old_l.item()) <= max(1e-4 * abs(l64), 2 * abs(l32 - l64))
+        assert (g[i:i + 1] - old_g).abs().max().item() <= max(1e-4 * gmax, 2 * err32)
+    # weight scales both outputs; a forward-only call and a repeated call give the same loss (the range re-arms itself)
+    loss2, g2 = term.loss_grad(yp, 0.25)
+    assert torch.allclose(loss2, 0.25 * loss, rtol=1e-9, atol=1e-12) and torch.allclose(g2, 0.25 * g, rtol=1e-5, atol=1e-9 * g.abs().max().item())
+    loss3, none = term.loss_grad(yp, 1.0, want_grad=False)
+    assert none is None and torch.equal(loss3, loss)
+
+
+def test_nmi_source_space_bounds_are_enforced():
+    """The truncated series is only valid inside the caller's value bounds: a range wider than 0.6 bandwidths is refused
+    (TRB_ERR_UNSUPPORTED -> RuntimeError) and a value outside the promised bounds turns the loss into NaN instead of a
+    silently wrong number."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((24, 32, 40), "rigid", device=DEV)
+    with pytest.raises(RuntimeError):
+        TF.NmiSourceTerm(tgt * 255.0, 0.0, 255.0)
+    assert not TF.NmiSourceTerm.eligible(mov * 255.0, 0.0, 255.0)
+    lo, hi = TF.NmiSourceTerm.bounds(mov, tgt)
+    term = TF.NmiSourceTerm(tgt, lo, hi)
+    bad = mov.clone()
+    bad[0, 0, 3, 4, 5] = hi + 0.5
+    loss, _ = term.loss_grad(bad, 1.0)
+    assert torch.isnan(loss).all()
+    loss, _ = term.loss_grad(mov, 1.0)
+    assert torch.isfinite(loss).all()
+
+
+@pytest.mark.parametrize("shape,n,mode,optm", [((24, 32, 64), 2, "rigid", "SGD"), ((40, 64, 64), 1, "affine", "SGD"),
+                                               ((24, 20, 16), 2, "affine", "ADAM"), ((33, 40, 48), 1, "rigid", "SGD")])
+def test_default_loss_loop_one_call_equals_per_epoch_loop(shape, n, mode, optm):
+    """The reference's DEFAULT criterions [MSE, NCC, NMI] (warpings.py:36-40,123-159): all epochs enqueued by ONE C-ABI call
+    (trb_affine_optim_nmi: moments pass that also stores the warped volumes, source-space NMI, second moments pass for
+    its d/dtheta, fused update) against the per-epoch loop on the resampled-array kernels — TMA-eligible and direct-kernel
+    shapes, batches, both optimisers.  Per-epoch loss 1e-4 relative, theta 2e-6 (north_star tolerances)."""
+    from torchregister_b200 import warpings as WP
+    from torchregister_b200.synth import make_pair
+    pairs = [make_pair(shape, mode, device=DEV, seed=700 + i) for i in range(n)]
+    mov, tgt = torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
+    p0 = torch.zeros(1, 6) if mode == "rigid" else torch.eye(3, 4).reshape(1, -1)
+    lr = 1e-3 if optm == "ADAM" else (1e-3 if mode == "rigid" else 1e-5)
+    res = {}
+    try:
+        for form in ("resampled", "source"):
+            WP.set_nmi_form(form)
+            prob, _, (ft, bt) = WP._affine_like(mode, mov, tgt, lr, 6, (0.33, 0.33, 0.33), p0, False, want_warped=False, optm=optm)
+            res[form] = (prob.losses.clone(), ft.clone(), bt.clone())
+    finally:
+        WP.set_nmi_form("auto")
+    a, b = res["source"], res["resampled"]
+    assert torch.allclose(a[0], b[0], rtol=1e-4, atol=0), (a[0], b[0])
+    assert (a[1] - b[1]).abs().max().item() <= 2e-6 and (a[2] - b[2]).abs().max().item() <= 2e-6
+    assert (a[0][:, -1] < a[0][:, 0]).all()
+
+
+def test_register_default_weights_3d_runs_the_one_call_loop():
+    """Stock call `Register('affine').optim(m, t)` on a normalised 3-D pair: default weights .33/.33/.33 -> the one-call
+    loop; the result is the same as with the per-epoch form."""
+    import torchregister_b200 as tr
+    from torchregister_b200 import warpings as WP
+    from torchregister_b200.synth import make_pair
+    mov, tgt = make_pair((24, 32, 64), "affine", device=DEV)
+    out = {}
+    try:
+        for form in ("source", "resampled"):
+            WP.set_nmi_form(form)
+            reg = tr.Register(mode="affine", device=DEV)
+            reg.optim(mov, tgt, lr=1e-5, max_epochs=5)
+            out[form] = (reg.losses.clone(), reg.theta.clone())
+    finally:
+        WP.set_nmi_form("auto")
+    assert torch.allclose(out["source"][0], out["resampled"][0], rtol=1e-4)
+    assert (out["source"][1] - out["resampled"][1]).abs().max().item() <= 2e-6
+
+
 @pytest.mark.parametrize("shape,scale", [((64, 48), 1.0), ((256, 256), 255.0), ((300, 180), 40.0)])
 def test_nmi_kernels_vs_cpu_oracle(shape, scale):
     """The same kernels against oracle/torch_port.nmi_loss — the line-by-line restatement of utils.py:18-79,224-259 that

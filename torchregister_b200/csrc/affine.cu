@@ -481,12 +481,13 @@ extern "C" int trb_affine_optim_peer(const float *moving_dev, const float *targe
     return launch_affine3d_tma(p, 1, true, epoch0, n_epochs, (cudaStream_t)stream);
 }
 
-static int affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
-                               int n_pairs, int D, int H, int W, int s_begin, int s_end,
-                               const float *xb_dev, const float *yb_dev, const float *zb_dev,
-                               const float *state_dev, double *moments_dev, int flags, bool want_target_sums,
-                               void *workspace_dev, size_t workspace_bytes, void *stream)
+int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
+                             int n_pairs, int D, int H, int W, int s_begin, int s_end,
+                             const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                             const float *state_dev, double *moments_dev, int flags, bool want_target_sums,
+                             float *warped_out, bool *wrote_warped, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
+    if (wrote_warped) *wrote_warped = false;
     AffineParams p{};
     int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
                          workspace_dev, workspace_bytes);
@@ -500,12 +501,16 @@ static int affine_moments_impl(int ndim, const float *moving_dev, const float *t
     p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
-        static const bool force_persist = getenv("TRB_MOMENTS_PERSIST") != nullptr;
-        if (p.gather || force_persist) {
+        if (p.gather) {
             // large rotations: one pass of the persistent kernel's gather variant instead of the per-epoch kernel's
             // uncached fallback (2-3x faster there); small rotations: the per-epoch kernel has the lower fixed cost
             rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, want_target_sums ? 1 : 2);
             if (rc != TRB_ERR_UNSUPPORTED) return rc;
+        }
+        // the per-epoch kernel stores the warped samples on request (whole volumes of single-channel pairs only)
+        if (warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W) {
+            p.warped_out = warped_out;
+            if (wrote_warped) *wrote_warped = true;
         }
         return launch_affine3d_tma(p, n_pairs, false, 0, 1, s);
     }
@@ -523,7 +528,7 @@ extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float
                                   void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     return affine_moments_impl(ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, s_begin, s_end, xb_dev, yb_dev, zb_dev,
-                               state_dev, moments_dev, 0, true, workspace_dev, workspace_bytes, stream);
+                               state_dev, moments_dev, 0, true, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int trb_affine_moments_ex(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
@@ -533,7 +538,7 @@ extern "C" int trb_affine_moments_ex(int ndim, const float *moving_dev, const fl
                                      void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     return affine_moments_impl(ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, s_begin, s_end, xb_dev, yb_dev, zb_dev,
-                               state_dev, moments_dev, flags, true, workspace_dev, workspace_bytes, stream);
+                               state_dev, moments_dev, flags, true, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs, int D, int H, int W,
@@ -613,7 +618,7 @@ extern "C" int trb_warp_affine_vjp_ex(int ndim, const float *moving_dev, const f
     }
     double *mom = (double *)((char *)workspace_dev + affine_ws_bytes(1));
     int rc = affine_moments_impl(ndim, moving_dev, gout_dev, 0, 1, D, H, W, 0, ndim == 3 ? D : H, xb_dev, yb_dev, zb_dev,
-                                 theta_dev - TRB_STATE_THETA, mom, flags, false, workspace_dev, affine_ws_bytes(1), stream);
+                                 theta_dev - TRB_STATE_THETA, mom, flags, false, nullptr, nullptr, workspace_dev, affine_ws_bytes(1), stream);
     if (rc) return rc;
     vjp_extract_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mom, dtheta_dev, ndim, ndim == 3 ? D : 1, H, W);
     return check_cuda(cudaGetLastError(), "warp_affine_vjp");

@@ -15,6 +15,12 @@ constexpr int kMaxSlots = 1024;      // partial-sum slots per pair in the worksp
 struct AffineParams;
 bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs);
 int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int n_launch, cudaStream_t stream);
+// moments of slices [s_begin, s_end) for all pairs (trb_affine_moments_ex); warped_out (optional, 3-D): the warped volumes
+// as a by-product when the TMA kernel takes the pass — *wrote_warped says whether it did
+int affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs, int D, int H,
+                        int W, int s_begin, int s_end, const float *xb_dev, const float *yb_dev, const float *zb_dev,
+                        const float *state_dev, double *moments_dev, int flags, bool want_target_sums, float *warped_out,
+                        bool *wrote_warped, void *workspace_dev, size_t workspace_bytes, void *stream);
 // persistent multi-epoch kernel (affine_persist.cu); TRB_ERR_UNSUPPORTED = nothing enqueued, take the per-epoch kernel
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream, int moments_mode = 0);
 void set_no_persist(bool v);
@@ -39,6 +45,7 @@ struct AffineParams {
     float w_mse, w_ncc, lr;
     int mode, optimiser;
     float beta1, beta2, adam_eps;
+    float *warped_out;           // optional [n_pairs][D][H][W]: the unfused 3-D TMA moments pass also stores the warped volume
     const double *extra;         // optional [n_pairs][13]: extra loss term and its d/dtheta (e.g. the NMI term), or NULL
     int extra_pair;              // row of `extra` (set by the epilogue wrappers)
     int gather;                  // 1: large-rotation variant of the persistent kernel (L1 gathers instead of TMA-staged boxes)

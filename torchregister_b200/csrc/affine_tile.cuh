@@ -125,8 +125,8 @@ struct Acc {
 // one pair of voxels (same x,y; z and z+1).  box_m: smem byte address of the staged box.
 // SECOND=false masks voxel b.
 template <int BX, int BY, bool SECOND, bool MSE_ONLY>
-__device__ __forceinline__ void pair_step(uint32_t box_m, float Mrel, float2 ix, float2 iy, float2 iz,
-                                          float2 t, float2 zf, Acc &A)
+__device__ __forceinline__ float2 pair_step(uint32_t box_m, float Mrel, float2 ix, float2 iy, float2 iz,
+                                            float2 t, float2 zf, Acc &A)
 {
     // floor() = round-down add of 1.5*2^23 (FADD.RM) and subtracting it again; FRND on the XU pipe was
     // tried instead (it frees 6 packed fp32 ops per pair) but its latency lengthened the dependent
@@ -193,6 +193,7 @@ __device__ __forceinline__ void pair_step(uint32_t box_m, float Mrel, float2 ix,
             A.Q[2][r] = __ffma2_rn(wzf, G[r], A.Q[2][r]);
         }
     }
+    return val;                          // the two warped samples (z, z + 1)
 }
 
 // ---- second formulation of the per-voxel arithmetic (round 2; used by affine_persist.cu) ------------------------------
@@ -322,8 +323,8 @@ __device__ __forceinline__ void voxel_direct2(const float *__restrict__ mov, int
 
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
 template <bool MSE_ONLY>
-__device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
-                                             float t, float zf, Acc &A)
+__device__ __forceinline__ float voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
+                                              float t, float zf, Acc &A)
 {
     ix = fminf(fmaxf(ix, -4.f), (float)W + 4.f);        // keeps the magic-number floor in range
     iy = fminf(fmaxf(iy, -4.f), (float)H + 4.f);
@@ -367,6 +368,7 @@ __device__ __forceinline__ void voxel_direct(const float *__restrict__ mov, int 
             A.Q[0][r].x = fmaf(zf, g, A.Q[0][r].x); A.Q[1][r].x = fmaf(zf, tg, A.Q[1][r].x); A.Q[2][r].x = fmaf(zf, wg, A.Q[2][r].x);
         }
     }
+    return val;
 }
 
 // Work decomposition.  A COLUMN is the full z-run of tiles at one (pair, y-tile, x-tile).  Columns are

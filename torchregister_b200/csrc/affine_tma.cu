@@ -296,6 +296,9 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
             }
         }
         const float *__restrict__ mov = p.a.moving + (size_t)pair * p.a.pair_stride;
+        // unfused pass: the warped samples are a by-product the caller may want (default-loss loop: the NMI term)
+        const size_t HWs = (size_t)H * W;
+        float *wcol = (!FUSED && p.a.warped_out && valid) ? p.a.warped_out + (size_t)pair * HWs * D + (size_t)y * W + x : nullptr;
         Acc A;
 #pragma unroll
         for (int i = 0; i < 5; ++i) A.s[i] = f2(0.f);
@@ -349,7 +352,8 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                             case 2: t = make_float2(lds_f<4 * TX * TY * 4>(tg), lds_f<5 * TX * TY * 4>(tg)); break;
                             default: t = make_float2(lds_f<6 * TX * TY * 4>(tg), lds_f<7 * TX * TY * 4>(tg)); break;
                             }
-                            pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            const float2 wv = pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            if (!FUSED && wcol) { __stcs(wcol + (size_t)(z0 + 2 * j) * HWs, wv.x); __stcs(wcol + (size_t)(z0 + 2 * j + 1) * HWs, wv.y); }
                             zf = __fadd2_rn(zf, f2(2.f));
                         }
                     } else {
@@ -362,15 +366,20 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                             const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
                             const float2 t = make_float2(lds_f_dyn(tg + zz * (TX * TY * 4)),
                                                          lds_f_dyn(tg + (second ? zz + 1 : zz) * (TX * TY * 4)));
-                            if (second) pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
-                            else pair_step<BX, BY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            const float2 wv = second ? pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A)
+                                                     : pair_step<BX, BY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            if (!FUSED && wcol) {
+                                __stcs(wcol + (size_t)(z0 + zz) * HWs, wv.x);
+                                if (second) __stcs(wcol + (size_t)(z0 + zz + 1) * HWs, wv.y);
+                            }
                         }
                     }
                 } else {
                     for (int zz = 0; zz < nz; ++zz) {
                         const float zf = (float)(z0 + zz);
-                        voxel_direct<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
-                                     lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                        const float wv = voxel_direct<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]),
+                                                                fmaf(sz[2], zf, pxy[2]), lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                        if (!FUSED && wcol) __stcs(wcol + (size_t)(z0 + zz) * HWs, wv);
                     }
                 }
             }

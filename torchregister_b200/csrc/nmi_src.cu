@@ -21,6 +21,7 @@
 // one (trilinear samples with zero padding are convex combinations of voxel values and 0); the loss is NaN if a
 // value ever leaves them.  Results equal nmi.cu's moment form up to both truncations (2e-11) and summation order.
 #include "nmi_shared.cuh"
+#include "affine_shared.cuh"
 
 namespace trb {
 
@@ -539,12 +540,15 @@ extern "C" int trb_affine_optim_nmi(int mode, const float *moving_dev, const flo
     cudaStream_t s = (cudaStream_t)stream;
     const int nt = (n_pairs * 12 + 127) / 128;
     for (int e = 0; e < n_epochs; ++e) {
-        rc = trb_affine_moments_ex(3, moving_dev, target_dev, vol, n_pairs, D, H, W, 0, D, xb_dev, yb_dev, zb_dev, state_dev, mom, flags,
-                                   workspace_dev, workspace_bytes, stream);
+        bool have_warped = false;
+        rc = affine_moments_impl(3, moving_dev, target_dev, vol, n_pairs, D, H, W, 0, D, xb_dev, yb_dev, zb_dev, state_dev, mom, flags, true,
+                                 warped_scratch_dev, &have_warped, workspace_dev, workspace_bytes, stream);
         if (rc) return rc;
-        nmi_src_theta_kernel<<<nt, 128, 0, s>>>(state_dev, theta, n_pairs);
-        rc = trb_warp_affine_batch(3, moving_dev, warped_scratch_dev, n_pairs, 1, D, H, W, theta, xb_dev, yb_dev, zb_dev, flags, stream);
-        if (rc) return rc;
+        if (!have_warped) {             // the pass ran on a kernel without the by-product (shape / rotation): separate warp
+            nmi_src_theta_kernel<<<nt, 128, 0, s>>>(state_dev, theta, n_pairs);
+            rc = trb_warp_affine_batch(3, moving_dev, warped_scratch_dev, n_pairs, 1, D, H, W, theta, xb_dev, yb_dev, zb_dev, flags, stream);
+            if (rc) return rc;
+        }
         rc = src_loss_grad(warped_scratch_dev, vol, n_pairs, D, H, W, bandwidth, alpha, w_nmi, lo, hi, extra, 13, gout_scratch_dev, ws, s);
         if (rc) return rc;
         rc = trb_affine_moments_ex(3, moving_dev, gout_scratch_dev, vol, n_pairs, D, H, W, 0, D, xb_dev, yb_dev, zb_dev, state_dev, mom2,
