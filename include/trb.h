@@ -335,25 +335,25 @@ int trb_nmi_loss_grad(int ndim, const float *warped_dev, int D, int H, int W, fl
                       float weight, double *loss_dev, float *gout_dev, void *workspace_dev,
                       size_t workspace_bytes, void *stream);
 
-/* Same term in SOURCE-voxel space (3-D, batched over pairs; csrc/nmi_src.cu): no resampled arrays, one pass over the warped
+/* Same term in SOURCE-voxel space (2-D and 3-D, batched over pairs; csrc/nmi_src.cu): no resampled arrays, one pass over the warped
  * volumes for 12 Hermite moments per chunk about a fixed centre, one pass writing d term / d warped.  Valid when all values
  * of target and warped volumes lie in [lo, hi] with hi - lo <= 0.6 * bandwidth (TRB_ERR_UNSUPPORTED otherwise; the loss is
  * NaN if a value leaves the bounds).  volumes: [n_pairs] x D*H*W, pair_stride floats apart.
  * trb_nmi_src_prepare: once per batch of targets.  trb_nmi_src_loss_grad: loss_dev[pair*loss_stride] = weight*loss (fp64),
  * gout_dev (same layout as warped_dev; NULL: forward only) = weight * d loss / d warped. */
-size_t trb_nmi_src_workspace_bytes(int n_pairs, int D, int H, int W);
-int trb_nmi_src_prepare(const float *target_dev, long long pair_stride, int n_pairs, int D, int H, int W, float bandwidth,
-                        float lo, float hi, void *workspace_dev, size_t workspace_bytes, void *stream);
-int trb_nmi_src_loss_grad(const float *warped_dev, long long pair_stride, int n_pairs, int D, int H, int W, float bandwidth,
-                          float alpha, float weight, float lo, float hi, double *loss_dev, int loss_stride,
+size_t trb_nmi_src_workspace_bytes(int ndim, int n_pairs, int D, int H, int W);
+int trb_nmi_src_prepare(int ndim, const float *target_dev, long long pair_stride, int n_pairs, int D, int H, int W,
+                        float bandwidth, float lo, float hi, void *workspace_dev, size_t workspace_bytes, void *stream);
+int trb_nmi_src_loss_grad(int ndim, const float *warped_dev, long long pair_stride, int n_pairs, int D, int H, int W,
+                          float bandwidth, float alpha, float weight, float lo, float hi, double *loss_dev, int loss_stride,
                           float *gout_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
 
-/* The rigid / affine loop with the reference's DEFAULT criterions [MSE, NCC, NMI] (warpings.py:36-40,60-93,123-159), 3-D,
+/* The rigid / affine loop with the reference's DEFAULT criterions [MSE, NCC, NMI] (warpings.py:36-40,60-93,123-159),
  * n_epochs epochs enqueued by one call (no host work per epoch): MSE/NCC moments -> warp with the current theta -> NMI
  * term (source-space form above; trb_nmi_src_prepare must have run on nmi_workspace_dev with these targets and bounds)
  * -> its d/dtheta by a second moments pass -> fused update and bookkeeping as trb_affine_apply.  moving/target:
- * [n_pairs][D][H][W] contiguous; warped_scratch_dev / gout_scratch_dev: same size; workspace_dev as trb_affine_moments. */
-int trb_affine_optim_nmi(int mode, const float *moving_dev, const float *target_dev, int n_pairs, int D, int H, int W,
+ * [n_pairs][(D)][H][W] contiguous (ndim == 2: D is ignored); warped_scratch_dev / gout_scratch_dev: same size; workspace_dev as trb_affine_moments. */
+int trb_affine_optim_nmi(int ndim, int mode, const float *moving_dev, const float *target_dev, int n_pairs, int D, int H, int W,
                          const float *xb_dev, const float *yb_dev, const float *zb_dev, float *state_dev,
                          float *loss_log_dev, int log_stride, int epoch0, int n_epochs, float w_mse, float w_ncc,
                          float w_nmi, float lr, int optimiser, float beta1, float beta2, float adam_eps, int flags,

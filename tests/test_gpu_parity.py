@@ -542,11 +542,12 @@ def test_nmi_kernels_vs_torch_restatement(shape, scale):
     assert none is None and loss3.item() == loss
 
 
-@pytest.mark.parametrize("shape,n", [((24, 32, 40), 1), ((24, 32, 64), 3), ((40, 47, 33), 2), ((210, 96, 230), 1), ((160, 192, 192), 1)])
+@pytest.mark.parametrize("shape,n", [((24, 32, 40), 1), ((24, 32, 64), 3), ((40, 47, 33), 2), ((210, 96, 230), 1), ((160, 192, 192), 1),
+                                     ((64, 48), 2), ((256, 256), 1), ((300, 180), 1), ((7, 9), 1), ((45, 51), 2)])
 def test_nmi_source_space_term_vs_torch_restatement(shape, n):
     """csrc/nmi_src.cu (source-voxel space, power moments about a fixed centre, batched over pairs) against the fp64
-    PyTorch restatement of the reference's arithmetic on the resampled 200^3 arrays, and against csrc/nmi.cu: up- and
-    down-sampling shapes, a shape without 16-byte rows (scalar loads), several pairs per call.  Same tolerance rule as
+    PyTorch restatement of the reference's arithmetic on the resampled 200^n arrays, and against csrc/nmi.cu: 2-D and 3-D,
+    up- and down-sampling shapes, shapes without 16-byte rows (scalar loads), several pairs per call.  Same tolerance rule as
     test_nmi_kernels_vs_torch_restatement."""
     TF = _tf()
     from torchregister_b200.synth import make_pair
@@ -596,7 +597,8 @@ def test_nmi_source_space_bounds_are_enforced():
 
 
 @pytest.mark.parametrize("shape,n,mode,optm", [((24, 32, 64), 2, "rigid", "SGD"), ((40, 64, 64), 1, "affine", "SGD"),
-                                               ((24, 20, 16), 2, "affine", "ADAM"), ((33, 40, 48), 1, "rigid", "SGD")])
+                                               ((24, 20, 16), 2, "affine", "ADAM"), ((33, 40, 48), 1, "rigid", "SGD"),
+                                               ((64, 48), 2, "rigid", "SGD"), ((256, 256), 1, "affine", "SGD"), ((45, 51), 1, "rigid", "ADAM")])
 def test_default_loss_loop_one_call_equals_per_epoch_loop(shape, n, mode, optm):
     """The reference's DEFAULT criterions [MSE, NCC, NMI] (warpings.py:36-40,123-159): all epochs enqueued by ONE C-ABI call
     (trb_affine_optim_nmi: moments pass that also stores the warped volumes, source-space NMI, second moments pass for
@@ -606,7 +608,8 @@ def test_default_loss_loop_one_call_equals_per_epoch_loop(shape, n, mode, optm):
     from torchregister_b200.synth import make_pair
     pairs = [make_pair(shape, mode, device=DEV, seed=700 + i) for i in range(n)]
     mov, tgt = torch.cat([p[0] for p in pairs]), torch.cat([p[1] for p in pairs])
-    p0 = torch.zeros(1, 6) if mode == "rigid" else torch.eye(3, 4).reshape(1, -1)
+    nd = len(shape)
+    p0 = torch.zeros(1, 6 if nd == 3 else 3) if mode == "rigid" else torch.eye(nd, nd + 1).reshape(1, -1)
     lr = 1e-3 if optm == "ADAM" else (1e-3 if mode == "rigid" else 1e-5)
     res = {}
     try:
@@ -683,15 +686,22 @@ def test_nmi_module_uses_kernels_and_is_differentiable():
     assert torch.isfinite(both)
 
 
-def test_default_weights_with_nmi_vs_reference_golden():
+@pytest.mark.parametrize("form", ["source", "resampled"])
+def test_default_weights_with_nmi_vs_reference_golden(form):
     """Register defaults (0.33*MSE + 0.33*NCC + 0.33*NMI): the golden run is the unmodified reference incl. its real
     NMI term (2-D).  The NMI term itself is fp32 rounding noise for data in [0,1] (|NMI-1| ~ 1e-6), so it is
-    compared on the total loss and theta."""
+    compared on the total loss and theta.  Both evaluations of the term: the one-call loop with the source-space form
+    (what the stock call takes for such data) and the per-epoch loop on the resampled arrays."""
     import torchregister_b200 as tr
+    from torchregister_b200 import warpings as WP
     g = load_golden("rigid2d_default")
     mov, tgt = torch.from_numpy(g["moving"]), torch.from_numpy(g["target"])
     reg = tr.Register(mode="rigid", device=DEV)
-    reg.optim(mov, tgt, lr=float(g["lr"]), max_epochs=int(g["epochs"]), reg0=torch.from_numpy(g["p0"]))
+    WP.set_nmi_form(form)
+    try:
+        reg.optim(mov, tgt, lr=float(g["lr"]), max_epochs=int(g["epochs"]), reg0=torch.from_numpy(g["p0"]))
+    finally:
+        WP.set_nmi_form("auto")
     losses = reg.losses.cpu().numpy()
     assert np.allclose(losses, g["losses"], rtol=2e-4, atol=2e-4), (losses, g["losses"])
     assert np.abs(reg.theta.cpu().numpy() - g["best_theta"]).max() <= 1e-5

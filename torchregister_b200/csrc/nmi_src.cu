@@ -27,8 +27,16 @@ namespace trb {
 
 constexpr int kMomPad = 16;                  // moment rows are padded to 16 columns
 constexpr int kPow = 8;                      // power moments per chunk (series in u*y, |u*y| <= 0.09: (0.09)^8/8! = 1e-13)
-constexpr int kChunks3 = 8;                  // 200^3 viewed as 8 chunks of 100^3 = 25 slices of 200x200 each
-constexpr int kChunkSlices = kRes / kChunks3;
+constexpr int kMaxChunks = 8;                // 3-D: 200^3 viewed as 8 chunks of 100^3 = 25 slices of 200x200 each;
+                                             // 2-D: 200^2 as 4 chunks of 100^2 = 50 rows of 200 each
+// A 2-D image [H][W] is handled as the volume [H][1][W]: the chunks cut its rows like they cut the slices of a volume, and
+// the 200 resampled copies of the single "row" of a slice multiply every weight by the same constant, which cancels in the
+// normalised histograms and in the gradient.
+struct SrcDims { int K, D, H, W; };
+static SrcDims src_dims(int ndim, int D, int H, int W)
+{
+    return ndim == 3 ? SrcDims{8, D, H, W} : SrcDims{4, H, 1, W};
+}
 
 struct SrcLayout {
     int B;                                   // blocks (partial rows) per chunk in the moments pass
@@ -36,18 +44,18 @@ struct SrcLayout {
     size_t off_keys, off_tabs, off_mxy, off_momT, off_part, off_gtab, off_scal, off_mom, off_mom2, off_extra, off_theta, total;
 };
 
-constexpr int kMaxChunkSlices = 256;         // source slices one chunk can read (D <= 2000)
+constexpr int kMaxChunkSlices = 256;         // source slices (rows in 2-D) one chunk can read
 constexpr int kMomBlocks = 74;               // 8 chunks x 74 = 592 = 4 blocks on each of the 148 SMs: one wave per pair
 constexpr int kBatch = 8;                    // values per thread whose loads are in flight together
 constexpr int kGradSeg = 256 * kBatch * 2;   // voxels per block of the gradient pass
 
 static size_t align256s(size_t v) { return (v + 255) & ~(size_t)255; }
 
-static SrcLayout src_layout(int n_pairs, int D, int H, int W)
+static SrcLayout src_layout(int n_pairs, int K, int D, int H, int W)
 {
     SrcLayout L{};
     const size_t vol = (size_t)D * H * W, hw = (size_t)H * W;
-    L.B = (int)(vol / kChunks3 / (256 * kBatch));
+    L.B = (int)(vol / K / (256 * kBatch));
     if (L.B < 1) L.B = 1;
     if (L.B > kMomBlocks) L.B = kMomBlocks;
     L.GB = (int)((hw + kGradSeg - 1) / kGradSeg);
@@ -56,9 +64,9 @@ static SrcLayout src_layout(int n_pairs, int D, int H, int W)
     L.off_keys = o; o = align256s(o + n * 4 * sizeof(int));                                   // t_min t_max w_min w_max
     L.off_tabs = o; o = align256s(o + ((size_t)W + H + 2 * (size_t)D) * sizeof(int));        // mulx | muly | zlo | zhi
     L.off_mxy = o; o = align256s(o + hw * sizeof(unsigned short));                            // mulx * muly per (y, x)
-    L.off_momT = o; o = align256s(o + n * kChunks3 * kMomPad * sizeof(double));
-    L.off_part = o; o = align256s(o + n * kChunks3 * (size_t)L.B * kMomPad * sizeof(double));
-    L.off_gtab = o; o = align256s(o + n * kChunks3 * kMomPad * sizeof(float));
+    L.off_momT = o; o = align256s(o + n * kMaxChunks * kMomPad * sizeof(double));
+    L.off_part = o; o = align256s(o + n * kMaxChunks * (size_t)L.B * kMomPad * sizeof(double));
+    L.off_gtab = o; o = align256s(o + n * kMaxChunks * kMomPad * sizeof(float));
     L.off_scal = o; o = align256s(o + n * 16 * sizeof(double));                               // K chunk terms + ticket
     L.off_mom = o; o = align256s(o + n * TRB_MOMENTS * sizeof(double));
     L.off_mom2 = o; o = align256s(o + n * TRB_MOMENTS * sizeof(double));
@@ -90,9 +98,9 @@ __global__ void nmi_src_plane_kernel(int W, int H, const int *__restrict__ tabs,
     if (i < W * H) mxy[i] = (unsigned short)(tabs[i % W] * tabs[W + i / W]);      // <= 200 * 200
 }
 
-__device__ __forceinline__ int chunk_overlap(int zl, int zh, int k)
+__device__ __forceinline__ int chunk_overlap(int zl, int zh, int k, int cs)
 {
-    return max(0, min(zh, (k + 1) * kChunkSlices) - max(zl, k * kChunkSlices));
+    return max(0, min(zh, (k + 1) * cs) - max(zl, k * cs));
 }
 
 __global__ void nmi_src_reset_kernel(int *keys, int n_pairs, int off)
@@ -102,11 +110,11 @@ __global__ void nmi_src_reset_kernel(int *keys, int n_pairs, int off)
 }
 
 // source slices [zf, zl] read by chunk k's 25 resampled slices (the resample map is monotone)
-__device__ __forceinline__ void chunk_slices(int k, int D, int &zf, int &zl)
+__device__ __forceinline__ void chunk_slices(int k, int cs, int D, int &zf, int &zl)
 {
     const float sz = (float)D / (float)kRes;
-    zf = nearest_src(k * kChunkSlices, sz, D);
-    zl = nearest_src((k + 1) * kChunkSlices - 1, sz, D);
+    zf = nearest_src(k * cs, sz, D);
+    zl = nearest_src((k + 1) * cs - 1, sz, D);
 }
 
 // i = q * hw + r, 0 <= r < hw, for 0 <= i < 2^31 (float estimate, corrected)
@@ -140,12 +148,12 @@ __global__ void __launch_bounds__(256) nmi_src_moments_kernel(const float *__res
     __shared__ double red[8][kPow];
     __shared__ float rmn[8], rmx[8];
     __shared__ int mzk[kMaxChunkSlices];
-    const int b = blockIdx.x, B = gridDim.x, k = blockIdx.y, pair = blockIdx.z;
+    const int b = blockIdx.x, B = gridDim.x, k = blockIdx.y, K = gridDim.y, cs = kRes / K, pair = blockIdx.z;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int *zlo = tabs + W + H, *zhi = zlo + D;
     int zf, zl;
-    chunk_slices(k, D, zf, zl);
-    for (int z = zf + threadIdx.x; z <= zl; z += 256) mzk[z - zf] = chunk_overlap(zlo[z], zhi[z], k);
+    chunk_slices(k, cs, D, zf, zl);
+    for (int z = zf + threadIdx.x; z <= zl; z += 256) mzk[z - zf] = chunk_overlap(zlo[z], zhi[z], k, cs);
     __syncthreads();
     constexpr int V = VEC ? 4 : 1, U = VEC ? 2 : 8;            // voxels per item, items per thread in flight
     const int hw = H * W / V;                                   // items per slice
@@ -205,7 +213,7 @@ __global__ void __launch_bounds__(256) nmi_src_moments_kernel(const float *__res
 #pragma unroll
             for (int w = 0; w < 8; ++w) sm += red[w][threadIdx.x];
         }
-        part[(((size_t)pair * kChunks3 + k) * B + b) * kMomPad + threadIdx.x] = sm;
+        part[(((size_t)pair * K + k) * B + b) * kMomPad + threadIdx.x] = sm;
     }
     if (threadIdx.x == 32) {
 #pragma unroll
@@ -254,7 +262,7 @@ __global__ void __launch_bounds__(256) nmi_src_epilogue_kernel(const double *__r
     __shared__ double rowW[kMomPad];
     __shared__ double sh[kPow + 1][8];
     __shared__ bool is_last;
-    const int b = threadIdx.x, k = blockIdx.x, pair = blockIdx.y, K = kChunks3;
+    const int b = threadIdx.x, k = blockIdx.x, pair = blockIdx.y, K = gridDim.x;
     {
         const int col = b & 15, ln = b >> 4;
         const double *p = part + ((size_t)pair * K + k) * B * kMomPad;
@@ -350,7 +358,7 @@ __global__ void __launch_bounds__(256) nmi_src_epilogue_kernel(const double *__r
 template <bool VEC>
 __global__ void __launch_bounds__(256) nmi_src_grad_kernel(const float *__restrict__ vol, long long pair_stride, int D, int H, int W,
                                                             const int *__restrict__ tabs, const unsigned short *__restrict__ mxy,
-                                                            const float *__restrict__ gtab, float mid, float inv_h,
+                                                            const float *__restrict__ gtab, int K, float mid, float inv_h,
                                                             float *__restrict__ gout)
 {
     __shared__ float coef[kMomPad];
@@ -360,9 +368,9 @@ __global__ void __launch_bounds__(256) nmi_src_grad_kernel(const float *__restri
     if (threadIdx.x < kMomPad) {
         float c = 0.f;
         if (threadIdx.x < kPow)
-            for (int k = 0; k < kChunks3; ++k) {
-                const int w = chunk_overlap(zl, zh, k);
-                if (w) c = fmaf((float)w, gtab[((size_t)pair * kChunks3 + k) * kMomPad + threadIdx.x], c);
+            for (int k = 0; k < K; ++k) {
+                const int w = chunk_overlap(zl, zh, k, kRes / K);
+                if (w) c = fmaf((float)w, gtab[((size_t)pair * K + k) * kMomPad + threadIdx.x], c);
             }
         coef[threadIdx.x] = c;
     }
@@ -411,28 +419,33 @@ __global__ void __launch_bounds__(256) nmi_src_grad_kernel(const float *__restri
     }
 }
 
-__global__ void nmi_src_theta_kernel(const float *__restrict__ state, float *__restrict__ theta, int n_pairs)
+__global__ void nmi_src_theta_kernel(const float *__restrict__ state, float *__restrict__ theta, int n_pairs, int nt)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n_pairs * 12) theta[i] = state[(size_t)(i / 12) * TRB_STATE_FLOATS + TRB_STATE_THETA + i % 12];
+    if (i < n_pairs * nt) theta[i] = state[(size_t)(i / nt) * TRB_STATE_FLOATS + TRB_STATE_THETA + i % nt];
 }
 
 // d term / d theta from the moments pass run with d term / d warped in the target slot (block [17..28] = sum gout * J)
-__global__ void nmi_src_extract_kernel(const double *__restrict__ mom2, double *__restrict__ extra, int n_pairs, int D, int H, int W)
+__global__ void nmi_src_extract_kernel(const double *__restrict__ mom2, double *__restrict__ extra, int n_pairs, int ndim, int D, int H, int W)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= n_pairs * 12) return;
-    const int pair = i / 12, j = i % 12, r = j / 4;
+    const int nc = ndim + 1, nt = ndim * nc;
+    if (i >= n_pairs * nt) return;
+    const int pair = i / nt, j = i % nt, r = j / nc;
     const double scale = r == 0 ? 0.5 * W : (r == 1 ? 0.5 * H : 0.5 * D);
     extra[(size_t)pair * 13 + 1 + j] = mom2[(size_t)pair * TRB_MOMENTS + 17 + j] * scale;
 }
 
-static int src_validate(int n_pairs, int D, int H, int W, float bandwidth, float lo, float hi, const void *ws, size_t ws_bytes)
+static int src_validate(int ndim, int n_pairs, int D, int H, int W, float bandwidth, float lo, float hi, const void *ws, size_t ws_bytes)
 {
+    if (ndim != 2 && ndim != 3) { set_error("ndim must be 2 or 3 (got %d)", ndim); return TRB_ERR_ARG; }
     if (n_pairs < 1 || n_pairs > 65535) { set_error("n_pairs must be in 1..65535 (got %d)", n_pairs); return TRB_ERR_ARG; }
-    if (D < 1 || H < 1 || W < 1) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
-    if (D > 2000) { set_error("source-space NMI handles D <= 2000 (got %d)", D); return TRB_ERR_UNSUPPORTED; }
-    if ((unsigned long long)D * H * W >= (1ull << 31)) { set_error("volume too large"); return TRB_ERR_UNSUPPORTED; }
+    if (H < 1 || W < 1 || (ndim == 3 && D < 1)) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
+    const SrcDims d = src_dims(ndim, D, H, W);
+    if ((long long)d.D * (kRes / d.K) / kRes + 2 > kMaxChunkSlices || d.D > 65535) {
+        set_error("source-space NMI: %d slices / rows is too many for one chunk table", d.D); return TRB_ERR_UNSUPPORTED;
+    }
+    if ((unsigned long long)d.D * d.H * d.W >= (1ull << 31)) { set_error("volume too large"); return TRB_ERR_UNSUPPORTED; }
     if (!(bandwidth > 0.f)) { set_error("bandwidth must be positive"); return TRB_ERR_ARG; }
     if (!(lo <= hi)) { set_error("value bounds must satisfy lo <= hi"); return TRB_ERR_ARG; }
     if (hi - lo > 0.6f * bandwidth) {
@@ -440,7 +453,7 @@ static int src_validate(int n_pairs, int D, int H, int W, float bandwidth, float
                   (double)(hi - lo), (double)bandwidth);
         return TRB_ERR_UNSUPPORTED;
     }
-    const SrcLayout L = src_layout(n_pairs, D, H, W);
+    const SrcLayout L = src_layout(n_pairs, d.K, d.D, d.H, d.W);
     if (!ws || ws_bytes < L.total) { set_error("workspace too small: need %zu bytes", L.total); return TRB_ERR_WORKSPACE; }
     return TRB_OK;
 }
@@ -450,22 +463,23 @@ static bool src_vec_ok(const float *p, long long pair_stride, int H, int W)
     return ((size_t)H * W) % 4 == 0 && pair_stride % 4 == 0 && ((uintptr_t)p & 15) == 0;
 }
 
-static int src_loss_grad(const float *warped, long long pair_stride, int n_pairs, int D, int H, int W, float bandwidth, float alpha,
+static int src_loss_grad(const float *warped, long long pair_stride, int n_pairs, const SrcDims &d, float bandwidth, float alpha,
                          float weight, float lo, float hi, double *loss_dev, int loss_stride, float *gout, char *ws, cudaStream_t s)
 {
-    const SrcLayout L = src_layout(n_pairs, D, H, W);
+    const int K = d.K, D = d.D, H = d.H, W = d.W;
+    const SrcLayout L = src_layout(n_pairs, K, D, H, W);
     int *keys = (int *)(ws + L.off_keys), *tabs = (int *)(ws + L.off_tabs);
     const unsigned short *mxy = (const unsigned short *)(ws + L.off_mxy);
     double *momT = (double *)(ws + L.off_momT), *part = (double *)(ws + L.off_part), *scal = (double *)(ws + L.off_scal);
     float *gtab = (float *)(ws + L.off_gtab);
     const float mid = 0.5f * (lo + hi), inv_h = 1.f / bandwidth;
     const bool vec = src_vec_ok(warped, pair_stride, H, W) && (!gout || src_vec_ok(gout, pair_stride, H, W));
-    if (vec) nmi_src_moments_kernel<true><<<dim3(L.B, kChunks3, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, mid, inv_h, part, keys, 2);
-    else nmi_src_moments_kernel<false><<<dim3(L.B, kChunks3, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, mid, inv_h, part, keys, 2);
-    nmi_src_epilogue_kernel<false><<<dim3(kChunks3, n_pairs), 256, 0, s>>>(part, L.B, momT, keys, mid, lo, hi, bandwidth, (double)alpha,
-                                                                           (double)weight, gtab, scal, loss_dev, loss_stride);
-    if (gout && vec) nmi_src_grad_kernel<true><<<dim3(L.GB, D, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, gtab, mid, inv_h, gout);
-    else if (gout) nmi_src_grad_kernel<false><<<dim3(L.GB, D, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, gtab, mid, inv_h, gout);
+    if (vec) nmi_src_moments_kernel<true><<<dim3(L.B, K, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, mid, inv_h, part, keys, 2);
+    else nmi_src_moments_kernel<false><<<dim3(L.B, K, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, mid, inv_h, part, keys, 2);
+    nmi_src_epilogue_kernel<false><<<dim3(K, n_pairs), 256, 0, s>>>(part, L.B, momT, keys, mid, lo, hi, bandwidth, (double)alpha,
+                                                                    (double)weight, gtab, scal, loss_dev, loss_stride);
+    if (gout && vec) nmi_src_grad_kernel<true><<<dim3(L.GB, D, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, gtab, K, mid, inv_h, gout);
+    else if (gout) nmi_src_grad_kernel<false><<<dim3(L.GB, D, n_pairs), 256, 0, s>>>(warped, pair_stride, D, H, W, tabs, mxy, gtab, K, mid, inv_h, gout);
     return check_cuda(cudaGetLastError(), "nmi_src_loss_grad");
 }
 
@@ -473,54 +487,57 @@ static int src_loss_grad(const float *warped, long long pair_stride, int n_pairs
 
 using namespace trb;
 
-extern "C" size_t trb_nmi_src_workspace_bytes(int n_pairs, int D, int H, int W)
+extern "C" size_t trb_nmi_src_workspace_bytes(int ndim, int n_pairs, int D, int H, int W)
 {
-    if (n_pairs < 1 || D < 1 || H < 1 || W < 1) return 0;
-    return src_layout(n_pairs, D, H, W).total;
+    if ((ndim != 2 && ndim != 3) || n_pairs < 1 || H < 1 || W < 1 || (ndim == 3 && D < 1)) return 0;
+    const SrcDims d = src_dims(ndim, D, H, W);
+    return src_layout(n_pairs, d.K, d.D, d.H, d.W).total;
 }
 
-extern "C" int trb_nmi_src_prepare(const float *target_dev, long long pair_stride, int n_pairs, int D, int H, int W, float bandwidth,
-                                   float lo, float hi, void *workspace_dev, size_t workspace_bytes, void *stream)
+extern "C" int trb_nmi_src_prepare(int ndim, const float *target_dev, long long pair_stride, int n_pairs, int D, int H, int W,
+                                   float bandwidth, float lo, float hi, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
-    int rc = src_validate(n_pairs, D, H, W, bandwidth, lo, hi, workspace_dev, workspace_bytes);
+    int rc = src_validate(ndim, n_pairs, D, H, W, bandwidth, lo, hi, workspace_dev, workspace_bytes);
     if (rc) return rc;
     if (!target_dev) { set_error("null target"); return TRB_ERR_ARG; }
-    const SrcLayout L = src_layout(n_pairs, D, H, W);
+    const SrcDims d = src_dims(ndim, D, H, W);
+    const SrcLayout L = src_layout(n_pairs, d.K, d.D, d.H, d.W);
     char *ws = (char *)workspace_dev;
     int *keys = (int *)(ws + L.off_keys), *tabs = (int *)(ws + L.off_tabs);
     unsigned short *mxy = (unsigned short *)(ws + L.off_mxy);
     double *momT = (double *)(ws + L.off_momT), *part = (double *)(ws + L.off_part);
     cudaStream_t s = (cudaStream_t)stream;
     const float mid = 0.5f * (lo + hi), inv_h = 1.f / bandwidth;
-    nmi_src_tables_kernel<<<(W + H + D + 127) / 128, 128, 0, s>>>(W, H, D, tabs);
-    nmi_src_plane_kernel<<<(W * H + 255) / 256, 256, 0, s>>>(W, H, tabs, mxy);
+    nmi_src_tables_kernel<<<(d.W + d.H + d.D + 127) / 128, 128, 0, s>>>(d.W, d.H, d.D, tabs);
+    nmi_src_plane_kernel<<<(d.W * d.H + 255) / 256, 256, 0, s>>>(d.W, d.H, tabs, mxy);
     nmi_src_reset_kernel<<<(n_pairs + 127) / 128, 128, 0, s>>>(keys, n_pairs, 0);
     nmi_src_reset_kernel<<<(n_pairs + 127) / 128, 128, 0, s>>>(keys, n_pairs, 2);
     cudaMemsetAsync(ws + L.off_scal, 0, (size_t)n_pairs * 16 * sizeof(double), s);      // chunk terms + the epilogue's tickets
-    if (src_vec_ok(target_dev, pair_stride, H, W))
-        nmi_src_moments_kernel<true><<<dim3(L.B, kChunks3, n_pairs), 256, 0, s>>>(target_dev, pair_stride, D, H, W, tabs, mxy, mid, inv_h, part, keys, 0);
+    if (src_vec_ok(target_dev, pair_stride, d.H, d.W))
+        nmi_src_moments_kernel<true><<<dim3(L.B, d.K, n_pairs), 256, 0, s>>>(target_dev, pair_stride, d.D, d.H, d.W, tabs, mxy, mid, inv_h, part, keys, 0);
     else
-        nmi_src_moments_kernel<false><<<dim3(L.B, kChunks3, n_pairs), 256, 0, s>>>(target_dev, pair_stride, D, H, W, tabs, mxy, mid, inv_h, part, keys, 0);
-    nmi_src_epilogue_kernel<true><<<dim3(kChunks3, n_pairs), 256, 0, s>>>(part, L.B, momT, keys, mid, lo, hi, bandwidth, 0.0, 0.0, nullptr,
-                                                                          nullptr, nullptr, 0);
+        nmi_src_moments_kernel<false><<<dim3(L.B, d.K, n_pairs), 256, 0, s>>>(target_dev, pair_stride, d.D, d.H, d.W, tabs, mxy, mid, inv_h, part, keys, 0);
+    nmi_src_epilogue_kernel<true><<<dim3(d.K, n_pairs), 256, 0, s>>>(part, L.B, momT, keys, mid, lo, hi, bandwidth, 0.0, 0.0, nullptr,
+                                                                     nullptr, nullptr, 0);
     return check_cuda(cudaGetLastError(), "nmi_src_prepare");
 }
 
-extern "C" int trb_nmi_src_loss_grad(const float *warped_dev, long long pair_stride, int n_pairs, int D, int H, int W, float bandwidth,
-                                     float alpha, float weight, float lo, float hi, double *loss_dev, int loss_stride,
-                                     float *gout_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
+extern "C" int trb_nmi_src_loss_grad(int ndim, const float *warped_dev, long long pair_stride, int n_pairs, int D, int H, int W,
+                                     float bandwidth, float alpha, float weight, float lo, float hi, double *loss_dev,
+                                     int loss_stride, float *gout_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
-    int rc = src_validate(n_pairs, D, H, W, bandwidth, lo, hi, workspace_dev, workspace_bytes);
+    int rc = src_validate(ndim, n_pairs, D, H, W, bandwidth, lo, hi, workspace_dev, workspace_bytes);
     if (rc) return rc;
     if (!warped_dev || !loss_dev || loss_stride < 1) { set_error("null pointer / loss stride"); return TRB_ERR_ARG; }
-    return src_loss_grad(warped_dev, pair_stride, n_pairs, D, H, W, bandwidth, alpha, weight, lo, hi, loss_dev, loss_stride, gout_dev,
-                         (char *)workspace_dev, (cudaStream_t)stream);
+    return src_loss_grad(warped_dev, pair_stride, n_pairs, src_dims(ndim, D, H, W), bandwidth, alpha, weight, lo, hi, loss_dev, loss_stride,
+                         gout_dev, (char *)workspace_dev, (cudaStream_t)stream);
 }
 
 // The reference's loop with its DEFAULT criterions [MSE, NCC, NMI] (warpings.py:36-40,123-159), every epoch enqueued from
-// here: MSE/NCC moments (all pairs) -> warp with the current theta -> NMI term and d term / d warped -> chained to theta
-// by a second moments pass (d term / d warped in the target slot) -> update, best-theta and loss bookkeeping on the device.
-extern "C" int trb_affine_optim_nmi(int mode, const float *moving_dev, const float *target_dev, int n_pairs, int D, int H, int W,
+// here: MSE/NCC moments (all pairs; the 3-D TMA pass also stores the warped volumes) -> NMI term and d term / d warped ->
+// chained to theta by a second moments pass (d term / d warped in the target slot) -> update, best-theta and loss
+// bookkeeping on the device.
+extern "C" int trb_affine_optim_nmi(int ndim, int mode, const float *moving_dev, const float *target_dev, int n_pairs, int D, int H, int W,
                                     const float *xb_dev, const float *yb_dev, const float *zb_dev, float *state_dev,
                                     float *loss_log_dev, int log_stride, int epoch0, int n_epochs, float w_mse, float w_ncc,
                                     float w_nmi, float lr, int optimiser, float beta1, float beta2, float adam_eps, int flags,
@@ -528,34 +545,36 @@ extern "C" int trb_affine_optim_nmi(int mode, const float *moving_dev, const flo
                                     float *gout_scratch_dev, void *nmi_workspace_dev, size_t nmi_workspace_bytes,
                                     void *workspace_dev, size_t workspace_bytes, void *stream)
 {
-    int rc = src_validate(n_pairs, D, H, W, bandwidth, lo, hi, nmi_workspace_dev, nmi_workspace_bytes);
+    int rc = src_validate(ndim, n_pairs, D, H, W, bandwidth, lo, hi, nmi_workspace_dev, nmi_workspace_bytes);
     if (rc) return rc;
     if (!moving_dev || !target_dev || !state_dev || !warped_scratch_dev || !gout_scratch_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
     if (loss_log_dev && epoch0 + n_epochs > log_stride) { set_error("loss log too short"); return TRB_ERR_ARG; }
-    const SrcLayout L = src_layout(n_pairs, D, H, W);
+    const SrcDims d = src_dims(ndim, D, H, W);
+    const SrcLayout L = src_layout(n_pairs, d.K, d.D, d.H, d.W);
     char *ws = (char *)nmi_workspace_dev;
     double *mom = (double *)(ws + L.off_mom), *mom2 = (double *)(ws + L.off_mom2), *extra = (double *)(ws + L.off_extra);
     float *theta = (float *)(ws + L.off_theta);
-    const long long vol = (long long)D * H * W;
+    const int Dn = ndim == 3 ? D : 1, slices = ndim == 3 ? D : H, nt = ndim * (ndim + 1);
+    const long long vol = (long long)Dn * H * W;
     cudaStream_t s = (cudaStream_t)stream;
-    const int nt = (n_pairs * 12 + 127) / 128;
+    const int nb = (n_pairs * nt + 127) / 128;
     for (int e = 0; e < n_epochs; ++e) {
         bool have_warped = false;
-        rc = affine_moments_impl(3, moving_dev, target_dev, vol, n_pairs, D, H, W, 0, D, xb_dev, yb_dev, zb_dev, state_dev, mom, flags, true,
-                                 warped_scratch_dev, &have_warped, workspace_dev, workspace_bytes, stream);
+        rc = affine_moments_impl(ndim, moving_dev, target_dev, vol, n_pairs, Dn, H, W, 0, slices, xb_dev, yb_dev, zb_dev, state_dev, mom, flags,
+                                 true, warped_scratch_dev, &have_warped, workspace_dev, workspace_bytes, stream);
         if (rc) return rc;
-        if (!have_warped) {             // the pass ran on a kernel without the by-product (shape / rotation): separate warp
-            nmi_src_theta_kernel<<<nt, 128, 0, s>>>(state_dev, theta, n_pairs);
-            rc = trb_warp_affine_batch(3, moving_dev, warped_scratch_dev, n_pairs, 1, D, H, W, theta, xb_dev, yb_dev, zb_dev, flags, stream);
+        if (!have_warped) {             // the pass ran on a kernel without the by-product (2-D / shape / rotation): separate warp
+            nmi_src_theta_kernel<<<nb, 128, 0, s>>>(state_dev, theta, n_pairs, nt);
+            rc = trb_warp_affine_batch(ndim, moving_dev, warped_scratch_dev, n_pairs, 1, Dn, H, W, theta, xb_dev, yb_dev, zb_dev, flags, stream);
             if (rc) return rc;
         }
-        rc = src_loss_grad(warped_scratch_dev, vol, n_pairs, D, H, W, bandwidth, alpha, w_nmi, lo, hi, extra, 13, gout_scratch_dev, ws, s);
+        rc = src_loss_grad(warped_scratch_dev, vol, n_pairs, d, bandwidth, alpha, w_nmi, lo, hi, extra, 13, gout_scratch_dev, ws, s);
         if (rc) return rc;
-        rc = trb_affine_moments_ex(3, moving_dev, gout_scratch_dev, vol, n_pairs, D, H, W, 0, D, xb_dev, yb_dev, zb_dev, state_dev, mom2,
+        rc = trb_affine_moments_ex(ndim, moving_dev, gout_scratch_dev, vol, n_pairs, Dn, H, W, 0, slices, xb_dev, yb_dev, zb_dev, state_dev, mom2,
                                    flags, workspace_dev, workspace_bytes, stream);
         if (rc) return rc;
-        nmi_src_extract_kernel<<<nt, 128, 0, s>>>(mom2, extra, n_pairs, D, H, W);
-        rc = trb_affine_apply(3, mode, mom, n_pairs, D, H, W, state_dev, loss_log_dev, log_stride, epoch0 + e, w_mse, w_ncc, lr, optimiser,
+        nmi_src_extract_kernel<<<nb, 128, 0, s>>>(mom2, extra, n_pairs, ndim, Dn, H, W);
+        rc = trb_affine_apply(ndim, mode, mom, n_pairs, Dn, H, W, state_dev, loss_log_dev, log_stride, epoch0 + e, w_mse, w_ncc, lr, optimiser,
                               beta1, beta2, adam_eps, extra, stream);
         if (rc) return rc;
     }

@@ -176,19 +176,18 @@ class AffineProblem:
     def run_default(self, n_epochs: int, lr: float, w_mse: float, w_ncc: float, w_nmi: float, term: "NmiSourceTerm",
                     optimiser: str = "sgd", betas=(0.9, 0.999), eps: float = 1e-8) -> None:
         """Enqueue `n_epochs` epochs of the reference's DEFAULT loss [MSE, NCC, NMI] (warpings.py:36-40,123-159) with one
-        C-ABI call: the NMI term runs in its source-space form (`term`, built on this problem's targets).  3-D,
-        single-channel volumes."""
+        C-ABI call: the NMI term runs in its source-space form (`term`, built on this problem's targets)."""
         if n_epochs <= 0:
             return
         if self.epoch + n_epochs > self.max_epochs:
             raise ValueError("max_epochs exceeded")
-        if self.ndim != 3 or self.pair_stride != self.D * self.H * self.W or term.n_pairs != self.n_pairs:
-            raise ValueError("run_default handles [N,1,D,H,W] volumes and a term built on the same batch")
+        if term.n_pairs != self.n_pairs or term.ndim != self.ndim:
+            raise ValueError("run_default needs a term built on the same batch")
         if self._default_scratch is None:
             self._default_scratch = torch.empty((2,) + tuple(self.target.shape), dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             check(self.lib.trb_affine_optim_nmi(
-                MODE[self.mode], self.moving.data_ptr(), self.target.data_ptr(), self.n_pairs, self.D, self.H, self.W,
+                self.ndim, MODE[self.mode], self.moving.data_ptr(), self.target.data_ptr(), self.n_pairs, self.D, self.H, self.W,
                 self.xb.data_ptr(), self.yb.data_ptr(), _ptr(self.zb), self.state.data_ptr(), self.loss_log.data_ptr(),
                 self.loss_log.shape[1], self.epoch, n_epochs, float(w_mse), float(w_ncc), float(w_nmi), float(lr),
                 OPT[optimiser], float(betas[0]), float(betas[1]), float(eps), int(self.flags), term.bandwidth, term.alpha,
@@ -490,7 +489,7 @@ class NmiTerm:
 
 
 class NmiSourceTerm:
-    """The same term for a BATCH of 3-D pairs, evaluated in source-voxel space (csrc/nmi_src.cu): no resampled arrays, one
+    """The same term for a BATCH of 2-D or 3-D pairs, evaluated in source-voxel space (csrc/nmi_src.cu): no resampled arrays, one
     pass over the warped volumes + one pass writing the gradient.  Needs all values of the targets and of every warped
     volume inside [lo, hi] with hi - lo <= 0.6 * bandwidth (`bounds()` derives them; images normalised to [0,1] qualify
     with the default bandwidth 3); the loss is NaN if a value leaves the bounds."""
@@ -506,34 +505,37 @@ class NmiSourceTerm:
 
     @classmethod
     def eligible(cls, moving: torch.Tensor, lo: float, hi: float, bandwidth: float = 3.0) -> bool:
-        return moving.dim() == 5 and moving.shape[1] == 1 and (hi - lo) <= cls.MAX_RANGE * bandwidth and lo <= hi
+        return moving.dim() in (4, 5) and moving.shape[1] == 1 and (hi - lo) <= cls.MAX_RANGE * bandwidth and lo <= hi
 
     def __init__(self, target: torch.Tensor, lo: float, hi: float, bandwidth: float = 3.0, alpha: float = 1000.0):
         require_cuda(target, "target")
         self.lib = _lib.load()
-        if target.dim() != 5 or target.shape[1] != 1:
-            raise ValueError("NmiSourceTerm expects [N,1,D,H,W] targets")
+        if target.dim() not in (4, 5) or target.shape[1] != 1:
+            raise ValueError("NmiSourceTerm expects [N,1,(D,)H,W] targets")
         self.device = target.device
-        self.n_pairs, _, self.D, self.H, self.W = (int(v) for v in target.shape)
+        self.ndim, self.D, self.H, self.W = _vol_dims(target)
+        self.n_pairs = int(target.shape[0])
+        self.shape = tuple(target.shape)
+        self.vol = self.D * self.H * self.W
         self.bandwidth, self.alpha, self.lo, self.hi = float(bandwidth), float(alpha), float(lo), float(hi)
-        n = int(self.lib.trb_nmi_src_workspace_bytes(self.n_pairs, self.D, self.H, self.W))
+        n = int(self.lib.trb_nmi_src_workspace_bytes(self.ndim, self.n_pairs, self.D, self.H, self.W))
         self.workspace = torch.empty(n, dtype=torch.uint8, device=self.device)
         self.loss = torch.zeros(self.n_pairs, dtype=torch.float64, device=self.device)
         t = target.detach().contiguous().float()
         with torch.cuda.device(self.device):
-            check(self.lib.trb_nmi_src_prepare(t.data_ptr(), self.D * self.H * self.W, self.n_pairs, self.D, self.H, self.W,
+            check(self.lib.trb_nmi_src_prepare(self.ndim, t.data_ptr(), self.vol, self.n_pairs, self.D, self.H, self.W,
                                                self.bandwidth, self.lo, self.hi, self.workspace.data_ptr(),
                                                self.workspace.numel(), _stream(self.device)), "nmi_src_prepare")
 
     def loss_grad(self, warped: torch.Tensor, weight: float = 1.0, want_grad: bool = True):
         """-> (weight*loss per pair, [N] fp64 device tensor overwritten by the next call; weight * d loss / d warped or None)."""
         require_cuda(warped, "warped")
-        if tuple(warped.shape) != (self.n_pairs, 1, self.D, self.H, self.W):
-            raise ValueError("warped must have the targets' [N,1,D,H,W] shape")
+        if tuple(warped.shape) != self.shape:
+            raise ValueError("warped must have the targets' shape %s" % (self.shape,))
         w = warped.detach().contiguous().float()
         gout = torch.empty_like(w) if want_grad else None
         with torch.cuda.device(self.device):
-            check(self.lib.trb_nmi_src_loss_grad(w.data_ptr(), self.D * self.H * self.W, self.n_pairs, self.D, self.H, self.W,
+            check(self.lib.trb_nmi_src_loss_grad(self.ndim, w.data_ptr(), self.vol, self.n_pairs, self.D, self.H, self.W,
                                                  self.bandwidth, self.alpha, float(weight), self.lo, self.hi,
                                                  self.loss.data_ptr(), 1, _ptr(gout), self.workspace.data_ptr(),
                                                  self.workspace.numel(), _stream(self.device)), "nmi_src_loss_grad")

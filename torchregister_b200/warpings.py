@@ -145,8 +145,8 @@ def _affine_like(mode, moving, target, lr, epochs, weights3, params0, debug, wan
         nd = moving.dim() - 2
         n_slices = int(moving.shape[2])
         n_pairs = int(moving.shape[0])
-        if nd == 3 and _NMI_FORM != 'resampled':
-            # 3-D volumes whose value range is narrow against the KDE bandwidth (e.g. normalised to [0,1]): the whole loop is
+        if _NMI_FORM != 'resampled':
+            # volumes whose value range is narrow against the KDE bandwidth (e.g. normalised to [0,1]): the whole loop is
             # ONE C-ABI call, the NMI term evaluated in source-voxel space (csrc/nmi_src.cu); no per-epoch host work
             lo, hi = TF.NmiSourceTerm.bounds(prob.moving, prob.target)
             if TF.NmiSourceTerm.eligible(prob.moving, lo, hi):
