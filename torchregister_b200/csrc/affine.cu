@@ -504,10 +504,16 @@ int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *tar
         if (p.gather) {
             // large rotations: one pass of the persistent kernel's gather variant instead of the per-epoch kernel's
             // uncached fallback (2-3x faster there); small rotations: the per-epoch kernel has the lower fixed cost
+            // both TMA-tile kernels store the warped samples on request (whole volumes of single-channel pairs only)
+            const bool store = warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W;
+            if (store) p.warped_out = warped_out;
             rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, want_target_sums ? 1 : 2);
-            if (rc != TRB_ERR_UNSUPPORTED) return rc;
+            if (rc != TRB_ERR_UNSUPPORTED) {
+                if (rc == TRB_OK && store && wrote_warped) *wrote_warped = true;
+                return rc;
+            }
+            p.warped_out = nullptr;
         }
-        // the per-epoch kernel stores the warped samples on request (whole volumes of single-channel pairs only)
         if (warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W) {
             p.warped_out = warped_out;
             if (wrote_warped) *wrote_warped = true;

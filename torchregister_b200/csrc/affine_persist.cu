@@ -735,12 +735,16 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                     }
                 }
             } else if (ROT) {
-                // gathers through L1; several z steps in flight per thread
+                // gathers through L1; several z steps in flight per thread.  The unfused pass also leaves the warped samples
+                // (default-loss loop: the NMI term needs them)
+                float *wcol = (pp.moments_only && p.a.warped_out)
+                                  ? p.a.warped_out + (size_t)(mov - p.a.moving) + ((size_t)(int)m.zf0 * H + y) * W + x : nullptr;
 #pragma unroll 4
                 for (int zz = 0; zz < nz; ++zz) {
                     const float zf = m.zf0 + (float)zz;
-                    voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
-                                           lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    const float wv = voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]),
+                                                             fmaf(sz[2], zf, pxy[2]), lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    if (wcol) __stcs(wcol + (size_t)zz * H * W, wv);
                 }
             } else {
                 for (int zz = 0; zz < nz; ++zz) {
@@ -881,6 +885,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         as.tickets = a.tickets + (size_t)p0 * kTicketStride;
         if (a.loss_log) as.loss_log = a.loss_log + (size_t)p0 * a.log_stride;
         as.extra = nullptr;
+        if (a.warped_out) as.warped_out = a.warped_out + (size_t)p0 * a.pair_stride;
         CUtensorMap map_mov, map_tgt;
         int rc = make_map(&map_mov, as.moving, np, as.pair_stride, as.D, as.H, as.W, kBX, kBY, kBZ);
         if (rc) return rc;

@@ -292,8 +292,8 @@ __device__ __forceinline__ void pair_step2(uint32_t box_m, float Mrel, float2 ix
 
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers (Acc2 form)
 template <bool MSE_ONLY>
-__device__ __forceinline__ void voxel_direct2(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
-                                              float t, float zf, Acc2 &A)
+__device__ __forceinline__ float voxel_direct2(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
+                                               float t, float zf, Acc2 &A)
 {
     ix = fminf(fmaxf(ix, -4.f), (float)W + 4.f);        // keeps the magic-number floor in range
     iy = fminf(fmaxf(iy, -4.f), (float)H + 4.f);
@@ -319,6 +319,7 @@ __device__ __forceinline__ void voxel_direct2(const float *__restrict__ mov, int
     const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
     const float G0 = fmaf(tz, dx1 - dx0, dx0);
     moments_accumulate<MSE_ONLY>(t, zf, val, G0, G1, G2, A);
+    return val;
 }
 
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
