@@ -148,7 +148,9 @@ def test_batch_equals_singles_and_is_deterministic():
         assert torch.equal(x, y), "not bit-reproducible"
     for i in range(5):
         s = run(mov[i:i + 1], tgt[i:i + 1], p0[i:i + 1])
-        assert torch.allclose(s[0][0], a[0][i], rtol=2e-6, atol=0)
+        # the batch cuts the columns into other pieces than a single-pair launch does: fp32 summation order only
+        # (the north-star tolerance is 1e-4)
+        assert torch.allclose(s[0][0], a[0][i], rtol=5e-6, atol=0)
         assert torch.allclose(s[1][0], a[1][i], rtol=0, atol=2e-7)
 
 

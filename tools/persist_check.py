@@ -41,7 +41,7 @@ for c in cases:
     rt2 = (a[1] - d[1]).abs().max().item()
     a2 = run("auto", *c)
     rep = bool((a2[0] == a[0]).all() and (a2[1] == a[1]).all())
-    good = rl < 2e-5 and rt < 2e-6 and rb < 2e-6 and rep
+    good = rl < 5e-5 and rt < 2e-6 and rb < 2e-6 and rep      # north-star tolerance: 1e-4 / 1e-4
     ok &= good
     print("case", c[:4], c[6], "loss rel vs tma %.2e theta %.2e best %.2e | vs direct %.2e %.2e | reproducible %s %s"
           % (rl, rt, rb, rl2, rt2, rep, "OK" if good else "FAIL"), flush=True)

@@ -703,24 +703,23 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             if (!ROT && (m.flags & kFits)) {
                 const float Mrel = m.Mrel;
                 const float zf0 = m.zf0;
-                if (nz == TZ) {
+                // full tiles (and half tiles: volumes whose depth is a multiple of TZ/2) run unrolled with immediate offsets
+                auto run_steps = [&](auto NS) {
                     float2 zf = make_float2(zf0, zf0 + 1.f);
-#pragma unroll
-                    for (int j = 0; j < TZ / 2; ++j) {
+                    static_for<0, decltype(NS)::value>([&](auto J) {
+                        constexpr int j = decltype(J)::value;
                         const float2 ix = __ffma2_rn(f2(sz[0]), zf, f2(pxy[0]));
                         const float2 iy = __ffma2_rn(f2(sz[1]), zf, f2(pxy[1]));
                         const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
-                        float2 t;
-                        switch (j) {      // immediates: the target tile advances TX*TY*4 bytes per z
-                        case 0: t = make_float2(lds_f<0 * TX * TY * 4>(tg), lds_f<1 * TX * TY * 4>(tg)); break;
-                        case 1: t = make_float2(lds_f<2 * TX * TY * 4>(tg), lds_f<3 * TX * TY * 4>(tg)); break;
-                        case 2: t = make_float2(lds_f<4 * TX * TY * 4>(tg), lds_f<5 * TX * TY * 4>(tg)); break;
-                        default: t = make_float2(lds_f<6 * TX * TY * 4>(tg), lds_f<7 * TX * TY * 4>(tg)); break;
-                        }
+                        // immediates: the target tile advances TX*TY*4 bytes per z
+                        const float2 t = make_float2(lds_f<(2 * j) * TX * TY * 4>(tg), lds_f<(2 * j + 1) * TX * TY * 4>(tg));
                         pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                         zf = __fadd2_rn(zf, f2(2.f));
-                    }
-                } else {
+                    });
+                };
+                if (nz == TZ) run_steps(std::integral_constant<int, TZ / 2>{});
+                else if (TZ >= 16 && nz == TZ / 2) run_steps(std::integral_constant<int, TZ / 4>{});
+                else {
                     for (int zz = 0; zz < nz; zz += 2) {
                         const bool second = zz + 1 < nz;
                         const float za = zf0 + (float)zz;

@@ -332,30 +332,17 @@ affine3d_tma_kernel(const TmaParams p, const __grid_constant__ CUtensorMap map_m
                     const float zf0 = (float)z0;
                     if (nz == TZ) {
                         float2 zf = make_float2(zf0, zf0 + 1.f);
-#ifdef TRB_NO_UNROLL
-#pragma unroll 1
-#else
-#pragma unroll
-#endif
-                        for (int j = 0; j < TZ / 2; ++j) {
+                        static_for<0, TZ / 2>([&](auto J) {
+                            constexpr int j = decltype(J)::value;
                             const float2 ix = __ffma2_rn(f2(sz[0]), zf, f2(pxy[0]));
                             const float2 iy = __ffma2_rn(f2(sz[1]), zf, f2(pxy[1]));
                             const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
-                            float2 t;
-#ifdef TRB_NO_UNROLL
-                            t = make_float2(lds_f_dyn(tg + (2 * j) * (TX * TY * 4)), lds_f_dyn(tg + (2 * j + 1) * (TX * TY * 4)));
-                            if (false)
-#endif
-                            switch (j) {      // immediates: the target tile advances TX*TY*4 bytes per z
-                            case 0: t = make_float2(lds_f<0 * TX * TY * 4>(tg), lds_f<1 * TX * TY * 4>(tg)); break;
-                            case 1: t = make_float2(lds_f<2 * TX * TY * 4>(tg), lds_f<3 * TX * TY * 4>(tg)); break;
-                            case 2: t = make_float2(lds_f<4 * TX * TY * 4>(tg), lds_f<5 * TX * TY * 4>(tg)); break;
-                            default: t = make_float2(lds_f<6 * TX * TY * 4>(tg), lds_f<7 * TX * TY * 4>(tg)); break;
-                            }
+                            // immediates: the target tile advances TX*TY*4 bytes per z
+                            const float2 t = make_float2(lds_f<(2 * j) * TX * TY * 4>(tg), lds_f<(2 * j + 1) * TX * TY * 4>(tg));
                             const float2 wv = pair_step<BX, BY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
                             if (!FUSED && wcol) { __stcs(wcol + (size_t)(z0 + 2 * j) * HWs, wv.x); __stcs(wcol + (size_t)(z0 + 2 * j + 1) * HWs, wv.y); }
                             zf = __fadd2_rn(zf, f2(2.f));
-                        }
+                        });
                     } else {
                         for (int zz = 0; zz < nz; zz += 2) {
                             const bool second = zz + 1 < nz;
