@@ -47,7 +47,7 @@ UNIT = "voxel-warps/s"
 CHUNK_EPOCHS = 249                  # epochs per persistent launch (accumulator region of the workspace)
 # Second roofline of the epoch kernel (profiles/r02_microbench_ffma2_operands.txt): the packed-fp32
 # stream of one voxel-pair step costs ~158 cycles per sub-partition at the measured operand-delivery rates
-# (register-file reads, not DRAM); a 32x16x8 tile is 16 such steps per sub-partition.
+# (register-file reads, not DRAM); a 32x16x16 tile is 32 such steps per sub-partition.
 STEP_CYCLES_BOUND = 158.0
 SM_MHZ = 1965.0
 
@@ -74,9 +74,9 @@ def _peaks():
 
 
 def issue_bound_us(shape, pairs, sms=148):
-    tiles = pairs * ((shape[2] + 31) // 32) * ((shape[1] + 15) // 16) * ((shape[0] + 7) // 8)
+    tiles = pairs * ((shape[2] + 31) // 32) * ((shape[1] + 15) // 16) * ((shape[0] + 15) // 16)
     per_cta = -(-tiles // sms)
-    return per_cta * 16 * STEP_CYCLES_BOUND / SM_MHZ
+    return per_cta * 32 * STEP_CYCLES_BOUND / SM_MHZ
 
 
 class ClockSampler:
