@@ -85,6 +85,11 @@ const char *trb_affine_kernel_status(void);
 /* Bytes of scratch (dev) needed by trb_affine_* for `n_pairs` pairs. */
 size_t trb_affine_workspace_bytes(int n_pairs);
 
+/* Write start parameters from HOST memory into state[.][0..n_params) of n_pairs pairs (n_rows == 1: the same row for
+ * every pair, else n_rows == n_pairs).  The values travel as kernel arguments: asynchronous, stream ordered, no pinned
+ * memory and no host wait behind the work already queued on the stream.  Call trb_affine_init_state afterwards. */
+int trb_affine_set_params(float *state_dev, int n_pairs, int n_params, const float *params_host, int n_rows, void *stream);
+
 /* Fill state[.][12..23] (theta) from state[.][0..11] (params) and reset
  * best/adam slots.  Replaces Regressor()/Theta.forward at loop entry
  * (utils.py:287-330) and the identity bias of warpings.py:47-48,54-55. */

@@ -298,6 +298,15 @@ __global__ void vjp_extract_kernel(const double *moments, double *dtheta, int nd
     dtheta[i] = moments[17 + i] * scale;      // sum_v gout_v * J_v (gout rides in the "target" slot)
 }
 
+// start parameters handed over as kernel ARGUMENTS: an upload that neither needs pinned memory nor blocks the host behind
+// the work already queued on the stream (a pageable cudaMemcpy does)
+struct ParamBlock { static constexpr int kPairs = 64; float v[kPairs * 12]; };
+__global__ void affine_set_params_kernel(float *state, int n, int n_params, const ParamBlock b)
+{
+    const int i = threadIdx.x / 12, j = threadIdx.x % 12;
+    if (i < n && j < n_params) state[(size_t)i * TRB_STATE_FLOATS + TRB_STATE_PARAMS + j] = b.v[i * 12 + j];
+}
+
 // ---- host side ---------------------------------------------------------------------------
 static int g_sm_count[64] = {};       // per device ordinal
 static bool g_force_direct = false;   // test hook: trb_set_kernel_path(1) pins the non-TMA kernel
@@ -354,6 +363,21 @@ static int validate_common(int ndim, int n_pairs, int D, int H, int W)
     if (H < 1 || W < 1 || (ndim == 3 && D < 1)) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
     if ((long long)(ndim == 3 ? D : 1) * H * W >= (1ll << 31)) { set_error("volume too large for 32-bit row indexing"); return TRB_ERR_UNSUPPORTED; }
     return TRB_OK;
+}
+
+extern "C" int trb_affine_set_params(float *state_dev, int n_pairs, int n_params, const float *params_host, int n_rows, void *stream)
+{
+    if (!state_dev || !params_host || n_pairs < 1) { set_error("null state / params"); return TRB_ERR_ARG; }
+    if (n_params < 1 || n_params > 12 || (n_rows != 1 && n_rows != n_pairs)) { set_error("bad n_params / n_rows"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    for (int p0 = 0; p0 < n_pairs; p0 += ParamBlock::kPairs) {
+        const int n = n_pairs - p0 < ParamBlock::kPairs ? n_pairs - p0 : ParamBlock::kPairs;
+        ParamBlock b{};
+        for (int i = 0; i < n; ++i)
+            for (int j = 0; j < n_params; ++j) b.v[i * 12 + j] = params_host[(size_t)(n_rows == 1 ? 0 : p0 + i) * n_params + j];
+        affine_set_params_kernel<<<1, ParamBlock::kPairs * 12, 0, s>>>(state_dev + (size_t)p0 * TRB_STATE_FLOATS, n, n_params, b);
+    }
+    return check_cuda(cudaGetLastError(), "affine_set_params");
 }
 
 extern "C" int trb_affine_init_state(int ndim, int mode, float *state_dev, int n_pairs, void *stream)

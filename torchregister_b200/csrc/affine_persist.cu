@@ -835,6 +835,12 @@ void set_no_persist(bool v) { g_no_persist = v; }
 static thread_local char g_persist_status[256] = "never called";
 #define PERSIST_REFUSE(...) do { snprintf(g_persist_status, sizeof(g_persist_status), __VA_ARGS__); return TRB_ERR_UNSUPPORTED; } while (0)
 
+struct ContribBlock { static constexpr int kPairs = 256; unsigned v[kPairs]; };
+__global__ void set_contributions_kernel(unsigned *tickets, int n, const ContribBlock b)
+{
+    if ((int)threadIdx.x < n) tickets[(size_t)threadIdx.x * kTicketStride + kTargetWord] = b.v[threadIdx.x];
+}
+
 // Enqueue n_epochs fused epochs for n_pairs pairs with the persistent kernel.  Returns TRB_ERR_UNSUPPORTED (without
 // enqueuing anything) when the configuration does not fit it; the caller then takes the per-epoch kernel.
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream, int moments_mode)
@@ -911,9 +917,14 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
             set_error("persistent kernel: inconsistent sub-batch decomposition");
             return TRB_ERR_ARG;
         }
-        e = cudaMemcpy2DAsync(as.tickets + kTargetWord, kTicketStride * sizeof(unsigned), contrib.data(), sizeof(unsigned),
-                              sizeof(unsigned), (size_t)np, cudaMemcpyHostToDevice, stream);
-        if (e != cudaSuccess) return check_cuda(e, "cudaMemcpy2DAsync(contributions)");
+        // contribution counts go up as kernel arguments: a pageable cudaMemcpyAsync would block the host until the work
+        // already queued on the stream (e.g. the previous stage's epochs) has drained
+        for (int c0 = 0; c0 < np; c0 += ContribBlock::kPairs) {
+            ContribBlock cb{};
+            const int n = min(ContribBlock::kPairs, np - c0);
+            for (int i = 0; i < n; ++i) cb.v[i] = contrib[c0 + i];
+            set_contributions_kernel<<<1, ContribBlock::kPairs, 0, stream>>>(as.tickets + (size_t)c0 * kTicketStride, n, cb);
+        }
         pp.acc = reinterpret_cast<unsigned long long *>(as.partials);
         pp.targets = as.tickets;
         pp.tsum_blocks = (mse_only || moments_mode == 2) ? 0 : kTsumBlocks;

@@ -111,14 +111,24 @@ class AffineProblem:
         # the kernel-variant hint below needs the start parameters on the host: take them before the upload when the
         # caller passed host data (no device round trip, no stream synchronisation)
         p0_src = torch.as_tensor(params0, dtype=torch.float32)
-        p0_host = p0_src.detach().reshape(-1, self.np) if not p0_src.is_cuda else None
-        p0 = p0_src.to(self.device).reshape(-1, self.np)
-        if p0.shape[0] == 1 and self.n_pairs > 1:
-            p0 = p0.expand(self.n_pairs, self.np)
-        if p0.shape[0] != self.n_pairs:
-            raise ValueError("params0 must have %d rows" % self.n_pairs)
+        p0_host = p0_src.detach().reshape(-1, self.np).contiguous() if not p0_src.is_cuda else None
         self.state = torch.zeros(self.n_pairs, STATE_FLOATS, dtype=torch.float32, device=self.device)
-        self.state[:, : self.np] = p0
+        if p0_host is not None:
+            # host parameters go up as kernel arguments: a pageable H2D copy would block the caller until everything
+            # already queued on the stream (e.g. the previous stage's epochs) has finished
+            if p0_host.shape[0] not in (1, self.n_pairs):
+                raise ValueError("params0 must have %d rows" % self.n_pairs)
+            with torch.cuda.device(self.device):
+                check(self.lib.trb_affine_set_params(self.state.data_ptr(), self.n_pairs, self.np, p0_host.data_ptr(),
+                                                     int(p0_host.shape[0]), _stream(self.device)), "affine_set_params")
+            p0 = None
+        else:
+            p0 = p0_src.to(self.device).reshape(-1, self.np)
+            if p0.shape[0] == 1 and self.n_pairs > 1:
+                p0 = p0.expand(self.n_pairs, self.np)
+            if p0.shape[0] != self.n_pairs:
+                raise ValueError("params0 must have %d rows" % self.n_pairs)
+            self.state[:, : self.np] = p0
         self.max_epochs = int(max_epochs)
         self.loss_log = torch.zeros(self.n_pairs, max(self.max_epochs, 1), dtype=torch.float32, device=self.device)
         ws_bytes = int(self.lib.trb_affine_workspace_bytes(self.n_pairs))
