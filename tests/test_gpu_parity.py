@@ -735,6 +735,34 @@ def test_tma_kernel_many_pairs_group_reduction():
     assert torch.allclose(a[0], d[0], rtol=1e-4) and torch.allclose(a[1], d[1], atol=2e-6)
 
 
+def test_many_pairs_host_start_parameters_and_contribution_upload():
+    """Start parameters given on the host travel as kernel arguments in blocks of 64 pairs, the persistent kernel's
+    contribution counts in blocks of 256: 300 small pairs (one column each) cross both block sizes.  Same result as with
+    device-resident parameters and as the direct kernel."""
+    TF = _tf()
+    from torchregister_b200.synth import make_pair
+    n, shape = 300, (16, 16, 32)
+    base = [make_pair(shape, "rigid", seed=40 + i) for i in range(6)]
+    mov = torch.cat([base[i % 6][0] for i in range(n)]).to(DEV)
+    tgt = torch.cat([base[(i + 1) % 6][1] for i in range(n)]).to(DEV)
+    p0 = torch.tensor([[0.001 * (i % 17), -0.002, 0.003, 0.01 * (i % 5), -0.02, 0.01] for i in range(n)])
+    def run(p, path):
+        TF.set_kernel_path(path)
+        try:
+            prob = TF.AffineProblem(mov, tgt, "rigid", p, 3)
+            prob.run(3, 1e-3, 0.5, 0.5)
+            return prob.losses.clone(), prob.final_theta.clone(), prob.params.clone()
+        finally:
+            TF.set_kernel_path("auto")
+    host = run(p0, "auto")
+    devp = run(p0.to(DEV), "auto")
+    assert torch.equal(host[0], devp[0]) and torch.equal(host[1], devp[1])
+    direct = run(p0, "direct")
+    assert torch.allclose(host[0], direct[0], rtol=1e-4) and torch.allclose(host[1], direct[1], atol=2e-6)
+    one = TF.AffineProblem(mov, tgt, "rigid", p0[:1], 1)            # one row: broadcast to every pair
+    assert torch.equal(one.params, p0[:1].to(DEV).expand(n, 6))
+
+
 def test_register_batch_extension_and_dtype():
     """EXTENSION: Register on a batch of independent pairs ([N,1,...]) equals N single-pair runs; float64 /
     CPU inputs are moved to float32 on the device like the reference's `.to(dtype=torch.float, device=device)`."""
