@@ -508,9 +508,11 @@ extern "C" int trb_affine_optim_peer(const float *moving_dev, const float *targe
 int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
                              int n_pairs, int D, int H, int W, int s_begin, int s_end,
                              const float *xb_dev, const float *yb_dev, const float *zb_dev,
-                             const float *state_dev, double *moments_dev, int flags, bool want_target_sums,
+                             const float *state_dev, double *moments_dev, int flags, int target_sums,
                              float *warped_out, bool *wrote_warped, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
+    // target_sums: 0 = the caller does not need sum t / sum t^2 (vjp pass), 1 = compute them, 2 = an earlier call with 1 on
+    // this workspace and these targets left them valid (only the persistent kernel keeps them apart from the pass)
     if (wrote_warped) *wrote_warped = false;
     AffineParams p{};
     int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
@@ -525,20 +527,22 @@ int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *tar
     p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
-        if (p.gather) {
-            // large rotations: one pass of the persistent kernel's gather variant instead of the per-epoch kernel's
-            // uncached fallback (2-3x faster there); small rotations: the per-epoch kernel has the lower fixed cost
-            // both TMA-tile kernels store the warped samples on request (whole volumes of single-channel pairs only)
-            const bool store = warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W;
+        // both TMA-tile kernels store the warped samples on request (whole volumes of single-channel pairs only)
+        const bool store = warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W;
+        // One pass of the persistent kernel (steady-state rate of the fused loop, ~15 us of cooperative launch + publish)
+        // against the per-epoch kernel (lower fixed cost, 25 % slower per tile): large rotations always (its gather
+        // variant is 2-3x faster than the per-epoch kernel's uncached fallback), else from ~10 tiles per SM on
+        const long long tiles = (long long)n_pairs * ((W + TX - 1) / TX) * ((H + TY - 1) / TY) * ((s_end - s_begin + TZ - 1) / TZ);
+        if (p.gather || tiles >= 10LL * sm_count()) {
             if (store) p.warped_out = warped_out;
-            rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, want_target_sums ? 1 : 2);
+            rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, target_sums == 0 ? 2 : (target_sums == 2 ? 3 : 1));
             if (rc != TRB_ERR_UNSUPPORTED) {
                 if (rc == TRB_OK && store && wrote_warped) *wrote_warped = true;
                 return rc;
             }
             p.warped_out = nullptr;
         }
-        if (warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W) {
+        if (store) {
             p.warped_out = warped_out;
             if (wrote_warped) *wrote_warped = true;
         }
@@ -558,7 +562,7 @@ extern "C" int trb_affine_moments(int ndim, const float *moving_dev, const float
                                   void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     return affine_moments_impl(ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, s_begin, s_end, xb_dev, yb_dev, zb_dev,
-                               state_dev, moments_dev, 0, true, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
+                               state_dev, moments_dev, 0, 1, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int trb_affine_moments_ex(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride,
@@ -568,7 +572,7 @@ extern "C" int trb_affine_moments_ex(int ndim, const float *moving_dev, const fl
                                      void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     return affine_moments_impl(ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, s_begin, s_end, xb_dev, yb_dev, zb_dev,
-                               state_dev, moments_dev, flags, true, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
+                               state_dev, moments_dev, flags, 1, nullptr, nullptr, workspace_dev, workspace_bytes, stream);
 }
 
 extern "C" int trb_affine_apply(int ndim, int mode, const double *moments_dev, int n_pairs, int D, int H, int W,
@@ -648,7 +652,7 @@ extern "C" int trb_warp_affine_vjp_ex(int ndim, const float *moving_dev, const f
     }
     double *mom = (double *)((char *)workspace_dev + affine_ws_bytes(1));
     int rc = affine_moments_impl(ndim, moving_dev, gout_dev, 0, 1, D, H, W, 0, ndim == 3 ? D : H, xb_dev, yb_dev, zb_dev,
-                                 theta_dev - TRB_STATE_THETA, mom, flags, false, nullptr, nullptr, workspace_dev, affine_ws_bytes(1), stream);
+                                 theta_dev - TRB_STATE_THETA, mom, flags, 0, nullptr, nullptr, workspace_dev, affine_ws_bytes(1), stream);
     if (rc) return rc;
     vjp_extract_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(mom, dtheta_dev, ndim, ndim == 3 ? D : 1, H, W);
     return check_cuda(cudaGetLastError(), "warp_affine_vjp");

@@ -236,7 +236,8 @@ __device__ double rigid_chain_component(const float *p, const double *g, int j)
 // Warp-cooperative form of affine_epilogue_core<3, true>: lane i owns entry i of theta / params, so nothing lives in
 // per-thread arrays (the helper warps run on 64 registers and local memory is an L2 round trip here: the serial form
 // took 5 us, most of it spill traffic).  Same expression per entry as the serial form.  st, gs: shared memory.
-__device__ float affine_epilogue_warp(const double *M, const AffineParams &p, int epoch, float *st, double *gs, int lane)
+// (force-inlined: a call would pass the kernel parameters by address, i.e. copy all of them to local memory at kernel entry)
+__device__ __forceinline__ float affine_epilogue_warp(const double *M, const AffineParams &p, int epoch, float *st, double *gs, int lane)
 {
     const double n = (double)p.D * (double)p.H * (double)p.W;
     const LossCoef lc = loss_coefficients(n, M[0], M[1], M[2], M[3], M[4], (double)p.w_mse, (double)p.w_ncc);
@@ -297,7 +298,7 @@ __device__ float affine_epilogue_warp(const double *M, const AffineParams &p, in
 // e_rel == 0: the state loaded at kernel start is current.  Otherwise wait for the pair's accumulator of epoch
 // e_rel-1 to be complete (every word's count field == contributions per epoch), rebuild the 41 moments and run the
 // epilogue on the private state.  All 32 lanes take part.
-__device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, float *st, bool writer, unsigned target,
+__device__ __forceinline__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, float *st, bool writer, unsigned target,
                               const double *tsum /* sum t, sum t^2 of the pair, or NULL (MSE only) */,
                               unsigned long long *accw, double *mrow, int lane)
 {
@@ -400,7 +401,9 @@ __device__ void acquire_theta(const PersistParams &pp, int e_rel, int pair, floa
 // then falls back to uncached global gathers, 5.5x slower).  This variant stages only the target tile (64 KB of shared
 // memory instead of 219 KB, which leaves ~128 KB of L1), maps a warp onto an 8x4 (x,y) patch instead of a 32-voxel row —
 // the 8 corner loads of a patch touch a compact source region — and gathers the moving volume through L1.
-template <bool MSE_ONLY, bool ROT>
+// STORE (unfused one-pass mode only): the staged path also leaves the warped samples in a.warped_out (the gather
+// variant decides that at run time)
+template <bool MSE_ONLY, bool ROT, bool STORE = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensorMap map_mov,
                         const __grid_constant__ CUtensorMap map_tgt)
@@ -660,6 +663,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
     bool valid = false;
     float xv = 0.f, yv = 0.f, pxy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f};
     const float *__restrict__ mov = p.a.moving;
+    float *wcol0 = nullptr;              // STORE: this thread's column of the warped output
     Acc2 A;
     int kcol = 0;
     for (int it = 0;; ++it) {
@@ -688,6 +692,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                 sz[r] = pc.coef[r * 4 + 2] * inv_d2;
             }
             mov = p.a.moving + (size_t)pc.pair * p.a.pair_stride;
+            if constexpr (STORE) wcol0 = p.a.warped_out + (size_t)pc.pair * p.a.pair_stride + (size_t)y * W + x;
 #pragma unroll
             for (int i = 0; i < 12; ++i) A.a[i] = f2(0.f);
 #ifdef TRB_TIMING
@@ -713,7 +718,15 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                         const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
                         // immediates: the target tile advances TX*TY*4 bytes per z
                         const float2 t = make_float2(lds_f<(2 * j) * TX * TY * 4>(tg), lds_f<(2 * j + 1) * TX * TY * 4>(tg));
-                        pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        if constexpr (STORE) {
+                            const float2 wv = pair_step2w<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            const size_t HWs = (size_t)H * W;
+                            float *wz = wcol0 + (size_t)(int)zf0 * HWs;
+                            __stcs(wz + (size_t)(2 * j) * HWs, wv.x);
+                            __stcs(wz + (size_t)(2 * j + 1) * HWs, wv.y);
+                        } else {
+                            pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        }
                         zf = __fadd2_rn(zf, f2(2.f));
                     });
                 };
@@ -729,8 +742,17 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                         const float2 iz = __ffma2_rn(f2(sz[2]), zf, f2(pxy[2]));
                         const float2 t = make_float2(lds_f_dyn(tg + zz * (TX * TY * 4)),
                                                      lds_f_dyn(tg + (second ? zz + 1 : zz) * (TX * TY * 4)));
-                        if (second) pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
-                        else pair_step2<kBX, kBY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        if constexpr (STORE) {
+                            const float2 wv = second ? pair_step2w<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A)
+                                                     : pair_step2w<kBX, kBY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            const size_t HWs = (size_t)H * W;
+                            float *wz = wcol0 + (size_t)(int)zf0 * HWs;
+                            __stcs(wz + (size_t)zz * HWs, wv.x);
+                            if (second) __stcs(wz + (size_t)(zz + 1) * HWs, wv.y);
+                        } else {
+                            if (second) pair_step2<kBX, kBY, true, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                            else pair_step2<kBX, kBY, false, MSE_ONLY>(box_addr, Mrel, ix, iy, iz, t, zf, A);
+                        }
                     }
                 }
             } else if (ROT) {
@@ -748,8 +770,9 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
             } else {
                 for (int zz = 0; zz < nz; ++zz) {
                     const float zf = m.zf0 + (float)zz;
-                    voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
-                                           lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    const float wv = voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]),
+                                                             fmaf(sz[2], zf, pxy[2]), lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    if constexpr (STORE) __stcs(wcol0 + ((size_t)(int)m.zf0 + zz) * H * W, wv);
                 }
             }
         }
@@ -845,7 +868,8 @@ __global__ void set_contributions_kernel(unsigned *tickets, int n, const Contrib
 // enqueuing anything) when the configuration does not fit it; the caller then takes the per-epoch kernel.
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream, int moments_mode)
 {
-    // moments_mode: 0 = fused epochs; 1 = one unfused pass (moments to a.moments_out); 2 = the same without target sums
+    // moments_mode: 0 = fused epochs; 1 = one unfused pass (moments to a.moments_out); 2 = the same without target sums;
+    // 3 = as 1, the target sums of an earlier mode-1 call on this workspace and these targets are still valid
     const bool moments_only = moments_mode != 0;
     if (moments_only) n_epochs = 1;
     if (g_no_persist || a.extra) PERSIST_REFUSE("disabled (kernel path / extra term)");
@@ -857,8 +881,10 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
     if (!coop || sms < 1) PERSIST_REFUSE("no cooperative launch (coop %d, sms %d)", coop, sms);
     const bool mse_only = !moments_only && a.w_ncc == 0.f;
     const bool rot = a.gather != 0;
+    const bool store = moments_only && !rot && a.warped_out != nullptr;
     auto kern = rot ? (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>)
-                    : (mse_only ? affine3d_persist_kernel<true, false> : affine3d_persist_kernel<false, false>);
+                    : (mse_only ? affine3d_persist_kernel<true, false>
+                                : (store ? affine3d_persist_kernel<false, false, true> : affine3d_persist_kernel<false, false>));
     const size_t kPersistSmem = rot ? Ring<true>::kSmem : Ring<false>::kSmem;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kPersistSmem);
     if (e != cudaSuccess) { cudaGetLastError(); PERSIST_REFUSE("cudaFuncSetAttribute(smem %zu): %s", kPersistSmem, cudaGetErrorString(e)); }
@@ -930,7 +956,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         pp.tsum_blocks = (mse_only || moments_mode == 2) ? 0 : kTsumBlocks;
         pp.moments_only = moments_only ? 1 : 0;
         if (moments_only) pp.t.a.moments_out = a.moments_out + (size_t)p0 * TRB_MOMENTS;
-        if (pp.tsum_blocks > 0) {
+        if (pp.tsum_blocks > 0 && moments_mode != 3) {
             e = cudaMemset2DAsync(as.tickets + kTsumWord, kTicketStride * sizeof(unsigned), 0, 2 * kLimbs * sizeof(unsigned long long), (size_t)np, stream);
             if (e != cudaSuccess) return check_cuda(e, "cudaMemset2DAsync(target sums)");
             const long long slab = (long long)as.H * as.W;

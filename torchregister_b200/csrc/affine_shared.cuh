@@ -16,10 +16,11 @@ struct AffineParams;
 bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs);
 int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int n_launch, cudaStream_t stream);
 // moments of slices [s_begin, s_end) for all pairs (trb_affine_moments_ex); warped_out (optional, 3-D): the warped volumes
-// as a by-product when the TMA kernel takes the pass — *wrote_warped says whether it did
+// as a by-product when a TMA-tile kernel takes the pass — *wrote_warped says whether it did; target_sums: 0 not needed,
+// 1 compute, 2 still valid from an earlier call with 1 on the same workspace and targets
 int affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs, int D, int H,
                         int W, int s_begin, int s_end, const float *xb_dev, const float *yb_dev, const float *zb_dev,
-                        const float *state_dev, double *moments_dev, int flags, bool want_target_sums, float *warped_out,
+                        const float *state_dev, double *moments_dev, int flags, int target_sums, float *warped_out,
                         bool *wrote_warped, void *workspace_dev, size_t workspace_bytes, void *stream);
 // persistent multi-epoch kernel (affine_persist.cu); TRB_ERR_UNSUPPORTED = nothing enqueued, take the per-epoch kernel
 int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epochs, cudaStream_t stream, int moments_mode = 0);

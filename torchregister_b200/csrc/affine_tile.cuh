@@ -311,6 +311,54 @@ __device__ __forceinline__ void pair_step2(uint32_t box_m, float Mrel, float2 ix
     }
 }
 
+// the same two functions returning the warped sample(s) (unfused pass that also stores the warped volume)
+template <int BX, int BY, bool MSE_ONLY>
+__device__ __forceinline__ float voxel_staged_w(uint32_t q, float tx, float ty, float tz, float t, float z, Acc2 &A)
+{
+    constexpr int SY = BX * 4, SZ = BX * BY * 4;
+    const float2 P0 = make_float2(lds_f<0>(q), lds_f<SZ>(q)), P1 = make_float2(lds_f<4>(q), lds_f<SZ + 4>(q));
+    const float2 R0 = make_float2(lds_f<SY>(q), lds_f<SZ + SY>(q)), R1 = make_float2(lds_f<SY + 4>(q), lds_f<SZ + SY + 4>(q));
+    const float2 dP = sub2(P1, P0), dR = sub2(R1, R0);                   // (d00, d10), (d01, d11)
+    const float2 vA = __ffma2_rn(f2(tx), dP, P0), vB = __ffma2_rn(f2(tx), dR, R0);   // (v00, v10), (v01, v11)
+    const float2 e = sub2(vB, vA);                                        // (e0, e1)
+    const float2 w = __ffma2_rn(f2(ty), e, vA);                           // (w0, w1)
+    const float2 dx = __ffma2_rn(f2(ty), sub2(dR, dP), dP);               // (dx0, dx1)
+    const float G2 = w.y - w.x;
+    const float val = fmaf(tz, G2, w.x);
+    const float G1 = fmaf(tz, e.y - e.x, e.x);
+    const float G0 = fmaf(tz, dx.y - dx.x, dx.x);
+    moments_accumulate<MSE_ONLY>(t, z, val, G0, G1, G2, A);
+    return val;
+}
+
+// two voxels (same x,y; z and z+1): coordinates, floor, fraction and index stay packed over the two voxels (their
+// operands are per-thread constants, i.e. broadcasts); SECOND = false skips voxel b.
+template <int BX, int BY, bool SECOND, bool MSE_ONLY>
+__device__ __forceinline__ float2 pair_step2w(uint32_t box_m, float Mrel, float2 ix, float2 iy, float2 iz, float2 t, float2 zf, Acc2 &A)
+{
+#ifdef TRB_XU_FLOOR
+    // floor on the (otherwise idle) XU pipe: FRND.FLOOR, 16 lanes/clk/SM, instead of two packed adds on the fp32 pipe
+    const float2 fx = make_float2(floorf(ix.x), floorf(ix.y)), fy = make_float2(floorf(iy.x), floorf(iy.y)),
+                 fz = make_float2(floorf(iz.x), floorf(iz.y));
+#else
+    const float2 M = f2(kMagic), nM = f2(-kMagic);
+    const float2 flx = __fadd2_rd(ix, M), fly = __fadd2_rd(iy, M), flz = __fadd2_rd(iz, M);
+    const float2 fx = __fadd2_rn(flx, nM), fy = __fadd2_rn(fly, nM), fz = __fadd2_rn(flz, nM);
+#endif
+    const float2 tx = sub2(ix, fx), ty = sub2(iy, fy), tz = sub2(iz, fz);
+    const float2 tb = __ffma2_rn(f2(kIdxScale * (float)(BX * BY)), fz,
+                                 __ffma2_rn(f2(kIdxScale * (float)BX), fy, __ffma2_rn(f2(kIdxScale), fx, f2(Mrel))));
+    const uint32_t qa = box_m + ((uint32_t)__float_as_int(tb.x) << 2);
+    float2 w;                            // the two warped samples (z, z + 1)
+    w.x = voxel_staged_w<BX, BY, MSE_ONLY>(qa, tx.x, ty.x, tz.x, t.x, zf.x, A);
+    w.y = 0.f;
+    if (SECOND) {
+        const uint32_t qb = box_m + ((uint32_t)__float_as_int(tb.y) << 2);
+        w.y = voxel_staged_w<BX, BY, MSE_ONLY>(qb, tx.y, ty.y, tz.y, t.y, zf.y, A);
+    }
+    return w;
+}
+
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers (Acc2 form)
 template <bool MSE_ONLY>
 __device__ __forceinline__ float voxel_direct2(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
