@@ -366,6 +366,18 @@ int trb_affine_optim_nmi(int ndim, int mode, const float *moving_dev, const floa
                          float *gout_scratch_dev, void *nmi_workspace_dev, size_t nmi_workspace_bytes,
                          void *workspace_dev, size_t workspace_bytes, void *stream);
 
+/* ---- InstanceNorm of the flow U-Net (csrc/instnorm.cu) --------------------------------
+ * Replaces nn.InstanceNorm3d / nn.InstanceNorm2d (affine=False, no running statistics) of Attention_UNet
+ * (utils.py:368-520) and autograd's backward, optionally fused with the ReLU in front of it (relu != 0:
+ * y = IN(max(x, 0))).  x, y, dy, dx: [n_inst][S] contiguous (n_inst = N*C instances of S spatial elements);
+ * stats_dev [n_inst][2] = (mean, rstd) written by forward and read by backward; coef_dev [n_inst][2] scratch. */
+size_t trb_instnorm_workspace_bytes(int n_inst, long long S);
+int trb_instnorm_forward(const float *x_dev, float *y_dev, int n_inst, long long S, float eps, int relu,
+                         float *stats_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
+int trb_instnorm_backward(const float *x_dev, const float *dy_dev, float *dx_dev, int n_inst, long long S, int relu,
+                          const float *stats_dev, float *coef_dev, void *workspace_dev, size_t workspace_bytes,
+                          void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -735,6 +735,71 @@ def test_tma_kernel_many_pairs_group_reduction():
     assert torch.allclose(a[0], d[0], rtol=1e-4) and torch.allclose(a[1], d[1], atol=2e-6)
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 60, 62, 64), (1, 4, 31, 29, 27), (2, 3, 40, 36), (1, 32, 9, 10, 11), (1, 1, 5, 7)])
+@pytest.mark.parametrize("relu", [False, True])
+def test_instance_norm_kernels_vs_torch(shape, relu):
+    """csrc/instnorm.cu (the U-Net's InstanceNorm, optionally with the ReLU in front of it folded in) against
+    nn.InstanceNorm{2,3}d(relu?(x)) in float64: forward and backward, vector and scalar loads, several instances."""
+    import torch.nn as nn
+    import torch.nn.functional as F
+    from torchregister_b200.utils import InstanceNorm2dB200, InstanceNorm3dB200
+    torch.manual_seed(3)
+    x = (torch.randn(shape, device=DEV) * 1.7 + 0.3).requires_grad_(True)
+    g = torch.randn(shape, device=DEV)
+    mod = (InstanceNorm3dB200 if len(shape) == 5 else InstanceNorm2dB200)(shape[1]).to(DEV)
+    mod.fuse_relu = relu
+    y = mod(x)
+    (dx,) = torch.autograd.grad(y, x, g)
+    x64 = x.detach().double().requires_grad_(True)
+    ref = (nn.InstanceNorm3d if len(shape) == 5 else nn.InstanceNorm2d)(shape[1]).double()
+    y64 = ref(F.relu(x64) if relu else x64)
+    (dx64,) = torch.autograd.grad(y64, x64, g.double())
+    assert (y.double() - y64).abs().max().item() <= 2e-5
+    assert (dx.double() - dx64).abs().max().item() <= 2e-5 * max(1.0, dx64.abs().max().item())
+    # the fp32 PyTorch module is no closer to float64 than we are
+    x32 = x.detach().clone().requires_grad_(True)
+    y32 = (nn.InstanceNorm3d if len(shape) == 5 else nn.InstanceNorm2d)(shape[1])(F.relu(x32) if relu else x32)
+    assert (y.double() - y64).abs().max().item() <= 4 * (y32.double() - y64).abs().max().item() + 1e-6
+
+
+def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
+    """Attention_UNet with the InstanceNorm kernels (ReLU folded in) against the same network — same parameter names, same
+    weights — built from stock nn.ReLU + nn.InstanceNorm3d: flow and parameter gradients."""
+    import torch.nn as nn
+    import torchregister_b200 as tr
+    from torchregister_b200 import utils as U
+    from torchregister_b200.synth import make_pair
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    shape = (156, 160, 164)
+    mov, _ = make_pair(shape, "flow", device=DEV)
+    torch.manual_seed(5)
+    net = tr.Attention_UNet(shape, mode="bilinear", n=32).to(DEV)
+    flow = net.flow_field(mov, DEV)
+    loss = (flow ** 2).mean() + flow.mean()
+    grads = torch.autograd.grad(loss, list(net.parameters()))
+    # stock modules in the same positions
+    def stock(m):
+        for name, child in list(m.named_children()):
+            if isinstance(child, U._InstanceNormB200):
+                new = (nn.InstanceNorm3d if isinstance(child, nn.InstanceNorm3d) else nn.InstanceNorm2d)(child.num_features)
+                relu = child.fuse_relu
+                setattr(m, name, nn.Sequential(nn.ReLU(), new) if relu else new)
+            else:
+                stock(child)
+    import copy
+    ref = copy.deepcopy(net)
+    stock(ref)
+    flow_r = ref.flow_field(mov, DEV)
+    loss_r = (flow_r ** 2).mean() + flow_r.mean()
+    grads_r = torch.autograd.grad(loss_r, list(ref.parameters()))
+    assert (flow - flow_r).abs().max().item() <= 1e-4 * max(1.0, flow_r.abs().max().item())
+    num = sum(((a - b) ** 2).sum() for a, b in zip(grads, grads_r)).sqrt().item()
+    den = sum((b ** 2).sum() for b in grads_r).sqrt().item()
+    assert num <= 2e-3 * den, (num, den)
+    assert [k for k, _ in net.state_dict().items()] == [k for k, _ in ref.state_dict().items()]
+
+
 def test_many_pairs_host_start_parameters_and_contribution_upload():
     """Start parameters given on the host travel as kernel arguments in blocks of 64 pairs, the persistent kernel's
     contribution counts in blocks of 256: 300 small pairs (one column each) cross both block sizes.  Same result as with

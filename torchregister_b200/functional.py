@@ -552,6 +552,51 @@ class NmiSourceTerm:
         return self.loss, gout
 
 
+# --------------------------------------------------------------------------- #
+# InstanceNorm of the flow U-Net
+# --------------------------------------------------------------------------- #
+_IN_WS = {}
+
+
+def _instnorm_ws(device, n_inst: int, S: int) -> torch.Tensor:
+    need = int(_lib.load().trb_instnorm_workspace_bytes(n_inst, S))
+    ws = _IN_WS.get(str(device))
+    if ws is None or ws.numel() < need:
+        ws = torch.empty(max(need, 1 << 20), dtype=torch.uint8, device=device)
+        _IN_WS[str(device)] = ws
+    return ws
+
+
+def instance_norm_forward(x: torch.Tensor, eps: float = 1e-5, relu: bool = False):
+    """y = InstanceNorm(relu?(x)) for x [N,C,*spatial] (affine=False, no running statistics) -> (y, stats [N*C,2])."""
+    require_cuda(x, "x")
+    x = x.contiguous()
+    n_inst = int(x.shape[0] * x.shape[1])
+    S = x.numel() // n_inst
+    y = torch.empty_like(x)
+    stats = torch.empty(n_inst, 2, dtype=torch.float32, device=x.device)
+    ws = _instnorm_ws(x.device, n_inst, S)
+    with torch.cuda.device(x.device):
+        check(_lib.load().trb_instnorm_forward(x.data_ptr(), y.data_ptr(), n_inst, S, float(eps), int(bool(relu)), stats.data_ptr(),
+                                               ws.data_ptr(), ws.numel(), _stream(x.device)), "instnorm_forward")
+    return y, stats
+
+
+def instance_norm_backward(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, relu: bool = False) -> torch.Tensor:
+    require_cuda(dy, "dy")
+    x, dy = x.contiguous(), dy.contiguous()
+    n_inst = int(x.shape[0] * x.shape[1])
+    S = x.numel() // n_inst
+    dx = torch.empty_like(x)
+    coef = torch.empty(n_inst, 2, dtype=torch.float32, device=x.device)
+    ws = _instnorm_ws(x.device, n_inst, S)
+    with torch.cuda.device(x.device):
+        check(_lib.load().trb_instnorm_backward(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), n_inst, S, int(bool(relu)),
+                                                stats.data_ptr(), coef.data_ptr(), ws.data_ptr(), ws.numel(),
+                                                _stream(x.device)), "instnorm_backward")
+    return dx
+
+
 class DirectFlowProblem:
     """Per-voxel flow field optimised with SGD or Adam on
     loss = w_mse*MSE + w_ncc*100*(1-NCC) + smooth * mean_axes(mean(forward_diff(flow)^2)).
