@@ -762,9 +762,38 @@ def test_instance_norm_kernels_vs_torch(shape, relu):
     assert (y.double() - y64).abs().max().item() <= 4 * (y32.double() - y64).abs().max().item() + 1e-6
 
 
+@pytest.mark.parametrize("n,ci,co,shape,bias", [(1, 1, 2, (20, 22, 40), True), (1, 4, 2, (12, 35, 133), True), (2, 2, 2, (9, 10, 11), True),
+                                                (1, 3, 4, (8, 8, 8), False), (1, 4, 4, (5, 6, 7), True), (1, 2, 1, (3, 3, 3), True)])
+def test_thin_conv3d_kernels_vs_torch(n, ci, co, shape, bias):
+    """csrc/thinconv.cu (3x3x3 valid convolutions with <= 4 channels each way) against F.conv3d in float64: output, input
+    gradient, weight and bias gradients; ragged rows, batches, smallest volume."""
+    import torch.nn.functional as F
+    from torchregister_b200.utils import Conv3dB200
+    torch.manual_seed(11)
+    conv = Conv3dB200(ci, co, kernel_size=3, bias=bias).to(DEV)
+    x = torch.randn(n, ci, *shape, device=DEV, requires_grad=True)
+    y = conv(x)
+    g = torch.randn_like(y)
+    grads = torch.autograd.grad(y, [x, conv.weight] + ([conv.bias] if bias else []), g)
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = conv.weight.detach().double().requires_grad_(True)
+    b64 = conv.bias.detach().double().requires_grad_(True) if bias else None
+    y64 = F.conv3d(x64, w64, b64)
+    ref = torch.autograd.grad(y64, [x64, w64] + ([b64] if bias else []), g.double())
+    assert tuple(y.shape) == tuple(y64.shape)
+    assert (y.double() - y64).abs().max().item() <= 1e-5 * max(1.0, y64.abs().max().item())
+    for a, b_ in zip(grads, ref):
+        assert (a.double() - b_).abs().max().item() <= 2e-5 * max(1.0, b_.abs().max().item())
+    # no input gradient requested (first layer of the U-Net): same weight gradient
+    y2 = conv(x.detach())
+    (gw2,) = torch.autograd.grad(y2, [conv.weight], g)
+    assert torch.equal(gw2, grads[1])
+
+
 def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
-    """Attention_UNet with the InstanceNorm kernels (ReLU folded in) against the same network — same parameter names, same
-    weights — built from stock nn.ReLU + nn.InstanceNorm3d: flow and parameter gradients."""
+    """Attention_UNet with the InstanceNorm kernels (ReLU folded in) and the thin-convolution kernels against the same network
+    — same parameter names, same weights — built from stock nn.Conv3d + nn.ReLU + nn.InstanceNorm3d (cuDNN, TF32 off): flow
+    and parameter gradients."""
     import torch.nn as nn
     import torchregister_b200 as tr
     from torchregister_b200 import utils as U
@@ -781,7 +810,9 @@ def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
     # stock modules in the same positions
     def stock(m):
         for name, child in list(m.named_children()):
-            if isinstance(child, U._InstanceNormB200):
+            if isinstance(child, U.Conv3dB200):
+                child.__class__ = nn.Conv3d                  # same attributes: cuDNN instead of csrc/thinconv.cu
+            elif isinstance(child, U._InstanceNormB200):
                 new = (nn.InstanceNorm3d if isinstance(child, nn.InstanceNorm3d) else nn.InstanceNorm2d)(child.num_features)
                 relu = child.fuse_relu
                 setattr(m, name, nn.Sequential(nn.ReLU(), new) if relu else new)
@@ -793,7 +824,11 @@ def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
     flow_r = ref.flow_field(mov, DEV)
     loss_r = (flow_r ** 2).mean() + flow_r.mean()
     grads_r = torch.autograd.grad(loss_r, list(ref.parameters()))
-    assert (flow - flow_r).abs().max().item() <= 1e-4 * max(1.0, flow_r.abs().max().item())
+    # every layer kernel is checked against float64 at 1e-5 (test_thin_conv3d_kernels_vs_torch,
+    # test_instance_norm_kernels_vs_torch); through a 20-layer chain with a normalisation after every convolution two float32
+    # evaluations differ by ~1.5e-4 relative in the flow (measured), the network itself is float32-only like the reference's
+    scale = max(1.0, flow_r.abs().max().item())
+    assert (flow - flow_r).abs().max().item() <= 5e-4 * scale, ((flow - flow_r).abs().max().item(), scale)
     num = sum(((a - b) ** 2).sum() for a, b in zip(grads, grads_r)).sqrt().item()
     den = sum((b ** 2).sum() for b in grads_r).sqrt().item()
     assert num <= 2e-3 * den, (num, den)

@@ -63,6 +63,9 @@ _SIGNATURES = {
     "trb_nmi_workspace_bytes": (_sz, [_i, _i, _i, _i]),
     "trb_nmi_prepare": (_i, [_i, c_fp, _i, _i, _i, _f, c_fp, _sz, c_fp]),
     "trb_nmi_loss_grad": (_i, [_i, c_fp, _i, _i, _i, _f, _f, _f, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "trb_thinconv3_workspace_bytes": (_sz, [_i, _i]),
+    "trb_thinconv3_forward": (_i, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, _i, c_fp]),
+    "trb_thinconv3_backward": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, _i, c_fp, _sz, c_fp]),
     "trb_instnorm_workspace_bytes": (_sz, [_i, _ll]),
     "trb_instnorm_forward": (_i, [c_fp, c_fp, _i, _ll, _f, _i, c_fp, c_fp, _sz, c_fp]),
     "trb_instnorm_backward": (_i, [c_fp, c_fp, c_fp, _i, _ll, _i, c_fp, c_fp, c_fp, _sz, c_fp]),

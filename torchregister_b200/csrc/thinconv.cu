@@ -1,0 +1,275 @@
+// thinconv.cu — SURVEY.md §8 f-3 (U-Net-side work of flow mode): 3x3x3 valid convolutions with very few channels
+// (C_in, C_out <= 4), forward, input gradient and weight / bias gradient.
+//
+// Replaces, from the reference (paths relative to /root/reference/src/TorchRegister/):
+//   the full-resolution nn.Conv3d(kernel_size=3) layers of Attention_UNet (layer1, layer9; utils.py:409-520) at the
+//   reference's width divisor n = 32 (channels 1 -> 2 -> 2 and 4 -> 2 -> 2), and autograd's backward of them.
+//
+// Why: cuDNN maps these onto tensor-core implicit GEMMs whose tiles are 64..256 output channels wide and converts
+// NCDHW <-> NHWC around them; with 2 output channels that is 74 ms of a 106 ms epoch at 256^3 (four layers; torch.profiler,
+// profiles/r02_unet_flow_profile.txt).  As a gather/stencil this is 27 * C_in loads and 27 * C_in * C_out FMAs per voxel
+// — L1-resident loads, weights as constant-bank operands (copied device -> constant memory on the stream): no layout
+// change, no im2col.
+//   forward: one thread per output voxel, all C_out at once.
+//   dgrad  : one thread per input voxel, all C_in at once (dy read with bounds predicates = the zero extension).
+//   wgrad  : groups (c_in, dz): a warp walks rows of the output, 9 * C_out (+ C_out for the bias) running sums per
+//            thread, block partials in fp64, fixed-order final sum (deterministic).
+#include "common.cuh"
+
+namespace trb {
+
+constexpr int kTcMaxC = 4;
+__constant__ float c_tc_w[kTcMaxC * kTcMaxC * 27];
+__constant__ float c_tc_b[kTcMaxC];
+
+// y[co][z][y][x] = b[co] + sum_{ci,dz,dy,dx} w[co][ci][dz][dy][dx] * x[ci][z+dz][y+dy][x+dx]
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) thinconv_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int D, int H, int W,
+                                                            int has_bias)
+{
+    const int OD = D - 2, OH = H - 2, OW = W - 2;
+    const int ox = blockIdx.x * 128 + (threadIdx.x & 127);
+    const int oy = blockIdx.y * 2 + (threadIdx.x >> 7);
+    const int oz = blockIdx.z;
+    if (ox >= OW || oy >= OH) return;
+    const size_t HW = (size_t)H * W, vol = HW * D, ovol = (size_t)OD * OH * OW;
+    float acc[CO];
+#pragma unroll
+    for (int co = 0; co < CO; ++co) acc[co] = has_bias ? c_tc_b[co] : 0.f;
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci)
+#pragma unroll
+        for (int dz = 0; dz < 3; ++dz)
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const float *row = x + ci * vol + (size_t)(oz + dz) * HW + (size_t)(oy + dy) * W + ox;
+                const float v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2);
+#pragma unroll
+                for (int co = 0; co < CO; ++co) {
+                    const int wi = ((co * CI + ci) * 3 + dz) * 9 + dy * 3;
+                    acc[co] = fmaf(c_tc_w[wi], v0, acc[co]);
+                    acc[co] = fmaf(c_tc_w[wi + 1], v1, acc[co]);
+                    acc[co] = fmaf(c_tc_w[wi + 2], v2, acc[co]);
+                }
+            }
+    const size_t o = ((size_t)oz * OH + oy) * OW + ox;
+#pragma unroll
+    for (int co = 0; co < CO; ++co) y[co * ovol + o] = acc[co];
+}
+
+// dx[ci][z][y][x] = sum_{co,dz,dy,dx} w[co][ci][dz][dy][dx] * dy[co][z-dz][y-dy][x-dx]   (dy = 0 outside its extent)
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) thinconv_dgrad_kernel(const float *__restrict__ gy, float *__restrict__ gx, int D, int H, int W)
+{
+    const int OD = D - 2, OH = H - 2, OW = W - 2;
+    const int ix = blockIdx.x * 128 + (threadIdx.x & 127);
+    const int iy = blockIdx.y * 2 + (threadIdx.x >> 7);
+    const int iz = blockIdx.z;
+    if (ix >= W || iy >= H) return;
+    const size_t HW = (size_t)H * W, vol = HW * D, OHW = (size_t)OH * OW, ovol = OHW * OD;
+    float acc[CI];
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) acc[ci] = 0.f;
+#pragma unroll
+    for (int dz = 0; dz < 3; ++dz) {
+        const int z = iz - dz;
+        if ((unsigned)z >= (unsigned)OD) continue;
+#pragma unroll
+        for (int dy = 0; dy < 3; ++dy) {
+            const int yy = iy - dy;
+            if ((unsigned)yy >= (unsigned)OH) continue;
+            const bool p0 = (unsigned)ix < (unsigned)OW, p1 = (unsigned)(ix - 1) < (unsigned)OW, p2 = (unsigned)(ix - 2) < (unsigned)OW;
+#pragma unroll
+            for (int co = 0; co < CO; ++co) {
+                const float *row = gy + co * ovol + (size_t)z * OHW + (size_t)yy * OW + ix;
+                const float v0 = p0 ? __ldg(row) : 0.f, v1 = p1 ? __ldg(row - 1) : 0.f, v2 = p2 ? __ldg(row - 2) : 0.f;
+#pragma unroll
+                for (int ci = 0; ci < CI; ++ci) {
+                    const int wi = ((co * CI + ci) * 3 + dz) * 9 + dy * 3;
+                    acc[ci] = fmaf(c_tc_w[wi], v0, acc[ci]);
+                    acc[ci] = fmaf(c_tc_w[wi + 1], v1, acc[ci]);
+                    acc[ci] = fmaf(c_tc_w[wi + 2], v2, acc[ci]);
+                }
+            }
+        }
+    }
+    const size_t o = (size_t)iz * HW + (size_t)iy * W + ix;
+#pragma unroll
+    for (int ci = 0; ci < CI; ++ci) gx[ci * vol + o] = acc[ci];
+}
+
+// grid (blocks, CI * 3): group g = ci * 3 + dz.  part[g][block][9 * CO + CO] in fp64 (the last CO entries: sum dy, group 0 only)
+template <int CO>
+__global__ void __launch_bounds__(256) thinconv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ gy, int D, int H, int W,
+                                                              double *__restrict__ part)
+{
+    constexpr int NA = 9 * CO + CO;
+    __shared__ double sh[8][NA];
+    const int OD = D - 2, OH = H - 2, OW = W - 2;
+    const int g = blockIdx.y, ci = g / 3, dz = g - ci * 3;
+    const size_t HW = (size_t)H * W, vol = HW * D, OHW = (size_t)OH * OW, ovol = OHW * OD;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int rows = OD * OH;
+    float a[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) a[i] = 0.f;
+    double A[NA];
+#pragma unroll
+    for (int i = 0; i < NA; ++i) A[i] = 0.0;
+    int since = 0;
+    for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
+        const int z = r / OH, yy = r - z * OH;
+        const float *xr = x + ci * vol + (size_t)(z + dz) * HW + (size_t)yy * W;
+        const float *gr = gy + (size_t)z * OHW + (size_t)yy * OW;
+        for (int xx = lane; xx < OW; xx += 32) {
+            float gv[CO];
+#pragma unroll
+            for (int co = 0; co < CO; ++co) gv[co] = __ldg(gr + co * ovol + xx);
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy)
+#pragma unroll
+                for (int dx = 0; dx < 3; ++dx) {
+                    const float xv = __ldg(xr + (size_t)dy * W + xx + dx);
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) a[co * 9 + dy * 3 + dx] = fmaf(gv[co], xv, a[co * 9 + dy * 3 + dx]);
+                }
+#pragma unroll
+            for (int co = 0; co < CO; ++co) a[9 * CO + co] += gv[co];
+        }
+        if (++since == 4) {                    // fp32 runs of at most 4 rows per lane, fp64 above
+#pragma unroll
+            for (int i = 0; i < NA; ++i) { A[i] += (double)a[i]; a[i] = 0.f; }
+            since = 0;
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < NA; ++i) {
+        const double v = warp_sum(A[i] + (double)a[i]);
+        if (lane == 0) sh[warp][i] = v;
+    }
+    __syncthreads();
+    if (threadIdx.x < NA) {
+        double v = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) v += sh[w][threadIdx.x];
+        part[((size_t)g * gridDim.x + blockIdx.x) * NA + threadIdx.x] = v;
+    }
+}
+
+// dw[co][ci][dz][dy][dx] and db[co] from the block partials, fixed order
+__global__ void thinconv_wgrad_final_kernel(const double *__restrict__ part, int blocks, int CI, int CO, float *__restrict__ gw,
+                                            float *__restrict__ gb)
+{
+    const int NA = 9 * CO + CO;
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < CI * 3 * 9 * CO) {
+        const int g = i / (9 * CO), k = i - g * 9 * CO;          // k = co * 9 + (dy * 3 + dx)
+        const int ci = g / 3, dz = g - ci * 3, co = k / 9, d = k - co * 9;
+        double v = 0.0;
+        for (int b = 0; b < blocks; ++b) v += part[((size_t)g * blocks + b) * NA + k];
+        gw[((co * CI + ci) * 3 + dz) * 9 + d] = (float)v;
+    } else if (gb && i < CI * 3 * 9 * CO + CO) {
+        const int co = i - CI * 3 * 9 * CO;
+        double v = 0.0;
+        for (int b = 0; b < blocks; ++b) v += part[(size_t)b * NA + 9 * CO + co];      // group 0
+        gb[co] = (float)v;
+    }
+}
+
+constexpr int kTcWgradBlocks = 96;
+
+static int tc_validate(int CI, int CO, int D, int H, int W)
+{
+    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) { set_error("thin convolution handles 1..%d channels (got %d -> %d)", kTcMaxC, CI, CO); return TRB_ERR_UNSUPPORTED; }
+    if (D < 3 || H < 3 || W < 3 || D > 65537) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
+    if ((unsigned long long)D * H * W * kTcMaxC >= (1ull << 40)) { set_error("volume too large"); return TRB_ERR_UNSUPPORTED; }
+    return TRB_OK;
+}
+
+static int tc_upload(const float *w, const float *b, int CI, int CO, cudaStream_t s)
+{
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_tc_w, w, (size_t)CO * CI * 27 * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && b) e = cudaMemcpyToSymbolAsync(c_tc_b, b, (size_t)CO * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? TRB_OK : check_cuda(e, "cudaMemcpyToSymbolAsync(thin conv weights)");
+}
+
+#define TC_DISPATCH(KERNEL, ...)                                                                               \
+    switch (CI * 8 + CO) {                                                                                     \
+    case 1 * 8 + 1: KERNEL<1, 1> __VA_ARGS__; break; case 1 * 8 + 2: KERNEL<1, 2> __VA_ARGS__; break;          \
+    case 1 * 8 + 3: KERNEL<1, 3> __VA_ARGS__; break; case 1 * 8 + 4: KERNEL<1, 4> __VA_ARGS__; break;          \
+    case 2 * 8 + 1: KERNEL<2, 1> __VA_ARGS__; break; case 2 * 8 + 2: KERNEL<2, 2> __VA_ARGS__; break;          \
+    case 2 * 8 + 3: KERNEL<2, 3> __VA_ARGS__; break; case 2 * 8 + 4: KERNEL<2, 4> __VA_ARGS__; break;          \
+    case 3 * 8 + 1: KERNEL<3, 1> __VA_ARGS__; break; case 3 * 8 + 2: KERNEL<3, 2> __VA_ARGS__; break;          \
+    case 3 * 8 + 3: KERNEL<3, 3> __VA_ARGS__; break; case 3 * 8 + 4: KERNEL<3, 4> __VA_ARGS__; break;          \
+    case 4 * 8 + 1: KERNEL<4, 1> __VA_ARGS__; break; case 4 * 8 + 2: KERNEL<4, 2> __VA_ARGS__; break;          \
+    case 4 * 8 + 3: KERNEL<4, 3> __VA_ARGS__; break; default: KERNEL<4, 4> __VA_ARGS__; break;                 \
+    }
+
+}  // namespace trb
+
+using namespace trb;
+
+extern "C" size_t trb_thinconv3_workspace_bytes(int CI, int CO)
+{
+    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) return 0;
+    return (size_t)CI * 3 * kTcWgradBlocks * (9 * CO + CO) * sizeof(double);
+}
+
+extern "C" int trb_thinconv3_forward(const float *x_dev, const float *w_dev, const float *b_dev, float *y_dev, int n_batch, int CI,
+                                     int CO, int D, int H, int W, void *stream)
+{
+    int rc = tc_validate(CI, CO, D, H, W);
+    if (rc) return rc;
+    if (!x_dev || !w_dev || !y_dev || n_batch < 1) { set_error("null pointer / batch"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = tc_upload(w_dev, b_dev, CI, CO, s);
+    if (rc) return rc;
+    const int OD = D - 2, OH = H - 2, OW = W - 2;
+    const dim3 grid((OW + 127) / 128, (OH + 1) / 2, OD);
+    const size_t vol = (size_t)D * H * W, ovol = (size_t)OD * OH * OW;
+    for (int n = 0; n < n_batch; ++n) {
+        const float *xn = x_dev + (size_t)n * CI * vol;
+        float *yn = y_dev + (size_t)n * CO * ovol;
+        TC_DISPATCH(thinconv_fwd_kernel, <<<grid, 256, 0, s>>>(xn, yn, D, H, W, b_dev ? 1 : 0))
+    }
+    return check_cuda(cudaGetLastError(), "thinconv3_forward");
+}
+
+extern "C" int trb_thinconv3_backward(const float *x_dev, const float *w_dev, const float *gy_dev, float *gx_dev, float *gw_dev,
+                                      float *gb_dev, int n_batch, int CI, int CO, int D, int H, int W, void *workspace_dev,
+                                      size_t workspace_bytes, void *stream)
+{
+    int rc = tc_validate(CI, CO, D, H, W);
+    if (rc) return rc;
+    if (!x_dev || !w_dev || !gy_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    if (n_batch != 1 && gw_dev) { set_error("weight gradient: one sample per call"); return TRB_ERR_UNSUPPORTED; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const size_t vol = (size_t)D * H * W, ovol = (size_t)(D - 2) * (H - 2) * (W - 2);
+    if (gx_dev) {
+        rc = tc_upload(w_dev, nullptr, CI, CO, s);
+        if (rc) return rc;
+        const dim3 grid((W + 127) / 128, (H + 1) / 2, D);
+        for (int n = 0; n < n_batch; ++n) {
+            const float *gn = gy_dev + (size_t)n * CO * ovol;
+            float *xn = gx_dev + (size_t)n * CI * vol;
+            TC_DISPATCH(thinconv_dgrad_kernel, <<<grid, 256, 0, s>>>(gn, xn, D, H, W))
+        }
+    }
+    if (gw_dev) {
+        if (!workspace_dev || workspace_bytes < trb_thinconv3_workspace_bytes(CI, CO)) {
+            set_error("workspace too small: need %zu bytes", trb_thinconv3_workspace_bytes(CI, CO));
+            return TRB_ERR_WORKSPACE;
+        }
+        double *part = (double *)workspace_dev;
+        const dim3 grid(kTcWgradBlocks, CI * 3);
+        switch (CO) {
+        case 1: thinconv_wgrad_kernel<1><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        case 2: thinconv_wgrad_kernel<2><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        case 3: thinconv_wgrad_kernel<3><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        default: thinconv_wgrad_kernel<4><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        }
+        const int n = CI * 27 * CO + CO;
+        thinconv_wgrad_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, kTcWgradBlocks, CI, CO, gw_dev, gb_dev);
+    }
+    return check_cuda(cudaGetLastError(), "thinconv3_backward");
+}

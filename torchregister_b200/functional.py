@@ -597,6 +597,54 @@ def instance_norm_backward(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tenso
     return dx
 
 
+# --------------------------------------------------------------------------- #
+# thin 3x3x3 convolutions of the flow U-Net
+# --------------------------------------------------------------------------- #
+THIN_CONV_MAX_CHANNELS = 4
+
+
+def thin_conv3d_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """conv3d(x, weight, bias) for kernel 3, stride 1, no padding, <= 4 channels each way (csrc/thinconv.cu)."""
+    require_cuda(x, "x")
+    x, weight = x.contiguous(), weight.contiguous()
+    n, ci, D, H, W = (int(v) for v in x.shape)
+    co = int(weight.shape[0])
+    y = torch.empty(n, co, D - 2, H - 2, W - 2, dtype=torch.float32, device=x.device)
+    b = bias.contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().trb_thinconv3_forward(x.data_ptr(), weight.data_ptr(), _ptr(b), y.data_ptr(), n, ci, co, D, H, W,
+                                                _stream(x.device)), "thinconv3_forward")
+    return y
+
+
+def thin_conv3d_backward(x: torch.Tensor, weight: torch.Tensor, gy: torch.Tensor, need_gx: bool, need_gw: bool, need_gb: bool):
+    """-> (d/dx or None, d/dweight or None, d/dbias or None)."""
+    require_cuda(gy, "gy")
+    x, weight, gy = x.contiguous(), weight.contiguous(), gy.contiguous()
+    n, ci, D, H, W = (int(v) for v in x.shape)
+    co = int(weight.shape[0])
+    lib = _lib.load()
+    gx = torch.empty_like(x) if need_gx else None
+    want_w = need_gw or need_gb
+    gw = torch.empty_like(weight) if want_w else None
+    gb = torch.empty(co, dtype=torch.float32, device=x.device) if want_w else None
+    ws = torch.empty(max(int(lib.trb_thinconv3_workspace_bytes(ci, co)), 8), dtype=torch.uint8, device=x.device) if want_w else None
+    with torch.cuda.device(x.device):
+        if n == 1 or not want_w:
+            check(lib.trb_thinconv3_backward(x.data_ptr(), weight.data_ptr(), gy.data_ptr(), _ptr(gx), _ptr(gw), _ptr(gb), n, ci, co,
+                                             D, H, W, _ptr(ws), ws.numel() if ws is not None else 0, _stream(x.device)), "thinconv3_backward")
+        else:
+            check(lib.trb_thinconv3_backward(x.data_ptr(), weight.data_ptr(), gy.data_ptr(), _ptr(gx), None, None, n, ci, co,
+                                             D, H, W, None, 0, _stream(x.device)), "thinconv3_backward")
+            gw.zero_(); gb.zero_()
+            for i in range(n):            # the weight gradient handles one sample per call
+                gwi, gbi = torch.empty_like(gw), torch.empty_like(gb)
+                check(lib.trb_thinconv3_backward(x[i].data_ptr(), weight.data_ptr(), gy[i].data_ptr(), None, gwi.data_ptr(), gbi.data_ptr(),
+                                                 1, ci, co, D, H, W, ws.data_ptr(), ws.numel(), _stream(x.device)), "thinconv3_backward")
+                gw += gwi; gb += gbi
+    return gx, (gw if need_gw else None), (gb if need_gb else None)
+
+
 class DirectFlowProblem:
     """Per-voxel flow field optimised with SGD or Adam on
     loss = w_mse*MSE + w_ncc*100*(1-NCC) + smooth * mean_axes(mean(forward_diff(flow)^2)).

@@ -369,6 +369,43 @@ class InstanceNorm2dB200(_InstanceNormB200, nn.InstanceNorm2d):
     pass
 
 
+class _ThinConv3dFn(torch.autograd.Function):
+    """conv3d (kernel 3, stride 1, valid) with <= 4 channels each way on csrc/thinconv.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import functional as TF
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return TF.thin_conv3d_forward(x, weight, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import functional as TF
+        x, weight = ctx.saved_tensors
+        gx, gw, gb = TF.thin_conv3d_backward(x, weight, gy, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                             ctx.has_bias and ctx.needs_input_grad[2])
+        return gx, gw, gb
+
+
+class Conv3dB200(nn.Conv3d):
+    """nn.Conv3d whose thin 3x3x3 valid layers (<= 4 channels each way: the full-resolution layers of the flow U-Net at the
+    reference's n = 32) run on csrc/thinconv.cu instead of cuDNN's tensor-core GEMMs, whose tiles are 64..256 output
+    channels wide (74 ms of a 106 ms epoch at 256^3).  Same parameters, same state_dict; everything else is nn.Conv3d."""
+
+    def _thin(self, x):
+        from .functional import THIN_CONV_MAX_CHANNELS as M
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and self.weight.dtype == torch.float32
+                and tuple(self.kernel_size) == (3, 3, 3) and tuple(self.stride) == (1, 1, 1) and tuple(self.dilation) == (1, 1, 1)
+                and self.groups == 1 and self.padding in ((0, 0, 0), 0, 'valid') and self.in_channels <= M and self.out_channels <= M
+                and min(x.shape[2:]) >= 3)
+
+    def forward(self, x):
+        if self._thin(x):
+            return _ThinConv3dFn.apply(x, self.weight, self.bias)
+        return super().forward(x)
+
+
 def _relu_inorm(inorm, channels):
     """The reference's `nn.ReLU(), nn.InstanceNorm(co)` pair with the ReLU folded into the norm; an Identity keeps the
     positions (and therefore the parameter names of the convolutions) of the reference's nn.Sequential."""
@@ -378,7 +415,7 @@ def _relu_inorm(inorm, channels):
 
 
 def _nd(dims):
-    return (nn.Conv3d, nn.ConvTranspose3d, InstanceNorm3dB200, nn.MaxPool3d) if dims == 3 else \
+    return (Conv3dB200, nn.ConvTranspose3d, InstanceNorm3dB200, nn.MaxPool3d) if dims == 3 else \
            (nn.Conv2d, nn.ConvTranspose2d, InstanceNorm2dB200, nn.MaxPool2d)
 
 
