@@ -391,6 +391,15 @@ int trb_thinconv3_backward(const float *x_dev, const float *w_dev, const float *
                            float *gb_dev, int n_batch, int CI, int CO, int D, int H, int W, void *workspace_dev,
                            size_t workspace_bytes, void *stream);
 
+/* 1x1x1 convolutions with <= 4 channels each way (attention gates, utils.py:368-406): y[co][o] = b[co] + sum_ci w[co][ci] x[ci][o*stride];
+ * x [CI][D][H][W] (2-D: D = 1), y [CO][OD][OH][OW] with O* = (I* - 1) / stride + 1; one sample per call; NULL gradients are skipped. */
+size_t trb_pointconv_workspace_bytes(int CI, int CO);
+int trb_pointconv_forward(const float *x_dev, const float *w_dev, const float *b_dev, float *y_dev, int CI, int CO, int D,
+                          int H, int W, int stride, void *stream);
+int trb_pointconv_backward(const float *x_dev, const float *w_dev, const float *gy_dev, float *gx_dev, float *gw_dev,
+                           float *gb_dev, int CI, int CO, int D, int H, int W, int stride, void *workspace_dev,
+                           size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -790,6 +790,30 @@ def test_thin_conv3d_kernels_vs_torch(n, ci, co, shape, bias):
     assert torch.equal(gw2, grads[1])
 
 
+@pytest.mark.parametrize("ci,co,shape,stride,bias", [(2, 2, (20, 22, 40), 3, False), (2, 2, (21, 23, 41), 1, True), (2, 1, (9, 10, 11), 1, True),
+                                                     (4, 3, (7, 8, 9), 2, True), (1, 4, (5, 5, 5), 3, False)])
+def test_point_conv3d_kernels_vs_torch(ci, co, shape, stride, bias):
+    """The 1x1x1 convolutions of the attention gates (stride 3 projection of the skip, gate filter, psi) on csrc/thinconv.cu
+    against F.conv3d in float64: output and all gradients, sizes that are not multiples of the stride."""
+    import torch.nn.functional as F
+    from torchregister_b200.utils import Conv3dB200
+    torch.manual_seed(13)
+    conv = Conv3dB200(ci, co, kernel_size=1, stride=stride, bias=bias).to(DEV)
+    x = torch.randn(1, ci, *shape, device=DEV, requires_grad=True)
+    y = conv(x)
+    g = torch.randn_like(y)
+    grads = torch.autograd.grad(y, [x, conv.weight] + ([conv.bias] if bias else []), g)
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = conv.weight.detach().double().requires_grad_(True)
+    b64 = conv.bias.detach().double().requires_grad_(True) if bias else None
+    y64 = F.conv3d(x64, w64, b64, stride=stride)
+    ref = torch.autograd.grad(y64, [x64, w64] + ([b64] if bias else []), g.double())
+    assert tuple(y.shape) == tuple(y64.shape)
+    assert (y.double() - y64).abs().max().item() <= 1e-5 * max(1.0, y64.abs().max().item())
+    for a, b_ in zip(grads, ref):
+        assert (a.double() - b_).abs().max().item() <= 2e-5 * max(1.0, b_.abs().max().item())
+
+
 def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
     """Attention_UNet with the InstanceNorm kernels (ReLU folded in) and the thin-convolution kernels against the same network
     — same parameter names, same weights — built from stock nn.Conv3d + nn.ReLU + nn.InstanceNorm3d (cuDNN, TF32 off): flow

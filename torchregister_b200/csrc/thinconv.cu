@@ -273,3 +273,192 @@ extern "C" int trb_thinconv3_backward(const float *x_dev, const float *w_dev, co
     }
     return check_cuda(cudaGetLastError(), "thinconv3_backward");
 }
+
+// ---- 1x1x1 convolutions with few channels (the attention gates of the U-Net: utils.py:368-406) -----------------------
+// y[co][o] = b[co] + sum_ci w[co][ci] * x[ci][o * stride]  (stride 3 for the gate's projection of the skip, else 1).
+// Pure streaming: C_in loads and C_out stores per output voxel; cuDNN spends 1-3.5 ms per call on them at 236^3..252^3.
+namespace trb {
+
+// forward: one thread per output voxel
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) pointconv_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int D, int H, int W,
+                                                             int OD, int OH, int OW, int stride, int has_bias)
+{
+    const size_t vol = (size_t)D * H * W, ovol = (size_t)OD * OH * OW;
+    for (size_t o = (size_t)blockIdx.x * 256 + threadIdx.x; o < ovol; o += (size_t)gridDim.x * 256) {
+        size_t i = o;
+        if (stride != 1) {
+            const int ox = (int)(o % OW);
+            const size_t r = o / OW;
+            const int oy = (int)(r % OH), oz = (int)(r / OH);
+            i = ((size_t)oz * stride * H + (size_t)oy * stride) * W + (size_t)ox * stride;
+        }
+        float v[CI];
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) v[ci] = __ldg(x + ci * vol + i);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+            float a = has_bias ? c_tc_b[co] : 0.f;
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) a = fmaf(c_tc_w[co * CI + ci], v[ci], a);
+            y[co * ovol + o] = a;
+        }
+    }
+}
+
+// input gradient: one thread per INPUT voxel (zeros where the stride skips it)
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) pointconv_dgrad_kernel(const float *__restrict__ gy, float *__restrict__ gx, int D, int H, int W,
+                                                               int OD, int OH, int OW, int stride)
+{
+    const size_t vol = (size_t)D * H * W, ovol = (size_t)OD * OH * OW;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
+        size_t o = i;
+        bool hit = true;
+        if (stride != 1) {
+            const int ix = (int)(i % W);
+            const size_t r = i / W;
+            const int iy = (int)(r % H), iz = (int)(r / H);
+            const int ox = ix / stride, oy = iy / stride, oz = iz / stride;
+            hit = ox * stride == ix && oy * stride == iy && oz * stride == iz && ox < OW && oy < OH && oz < OD;
+            o = ((size_t)oz * OH + oy) * OW + ox;
+        }
+        float g[CO];
+#pragma unroll
+        for (int co = 0; co < CO; ++co) g[co] = hit ? __ldg(gy + co * ovol + o) : 0.f;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) {
+            float a = 0.f;
+#pragma unroll
+            for (int co = 0; co < CO; ++co) a = fmaf(c_tc_w[co * CI + ci], g[co], a);
+            gx[ci * vol + i] = a;
+        }
+    }
+}
+
+// weight / bias gradient: CI*CO + CO running sums per thread over the output voxels; block partials in fp64
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) pointconv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ gy, int D, int H, int W,
+                                                               int OD, int OH, int OW, int stride, double *__restrict__ part)
+{
+    constexpr int NA = CI * CO + CO;
+    __shared__ double sh[8][NA];
+    const size_t vol = (size_t)D * H * W, ovol = (size_t)OD * OH * OW;
+    float a[NA];
+    double A[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) { a[k] = 0.f; A[k] = 0.0; }
+    int since = 0;
+    for (size_t o = (size_t)blockIdx.x * 256 + threadIdx.x; o < ovol; o += (size_t)gridDim.x * 256) {
+        size_t i = o;
+        if (stride != 1) {
+            const int ox = (int)(o % OW);
+            const size_t r = o / OW;
+            const int oy = (int)(r % OH), oz = (int)(r / OH);
+            i = ((size_t)oz * stride * H + (size_t)oy * stride) * W + (size_t)ox * stride;
+        }
+        float v[CI], g[CO];
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) v[ci] = __ldg(x + ci * vol + i);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) g[co] = __ldg(gy + co * ovol + o);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+#pragma unroll
+            for (int ci = 0; ci < CI; ++ci) a[co * CI + ci] = fmaf(g[co], v[ci], a[co * CI + ci]);
+            a[CI * CO + co] += g[co];
+        }
+        if (++since == 32) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) { A[k] += (double)a[k]; a[k] = 0.f; }
+            since = 0;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const double s = warp_sum(A[k] + (double)a[k]);
+        if (lane == 0) sh[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NA) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+        part[(size_t)blockIdx.x * NA + threadIdx.x] = s;
+    }
+}
+
+__global__ void pointconv_wgrad_final_kernel(const double *__restrict__ part, int blocks, int CI, int CO, float *__restrict__ gw,
+                                             float *__restrict__ gb)
+{
+    const int NA = CI * CO + CO, k = threadIdx.x;
+    if (k >= NA) return;
+    double s = 0.0;
+    for (int b = 0; b < blocks; ++b) s += part[(size_t)b * NA + k];
+    if (k < CI * CO) gw[k] = (float)s;
+    else if (gb) gb[k - CI * CO] = (float)s;
+}
+
+constexpr int kPcBlocks = 148 * 4;
+
+static int pc_validate(int CI, int CO, int D, int H, int W, int stride)
+{
+    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) { set_error("thin 1x1 convolution handles 1..%d channels (got %d -> %d)", kTcMaxC, CI, CO); return TRB_ERR_UNSUPPORTED; }
+    if (D < 1 || H < 1 || W < 1 || stride < 1) { set_error("bad shape %dx%dx%d / stride %d", D, H, W, stride); return TRB_ERR_ARG; }
+    return TRB_OK;
+}
+
+}  // namespace trb
+
+extern "C" size_t trb_pointconv_workspace_bytes(int CI, int CO)
+{
+    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) return 0;
+    return (size_t)kPcBlocks * (CI * CO + CO) * sizeof(double);
+}
+
+extern "C" int trb_pointconv_forward(const float *x_dev, const float *w_dev, const float *b_dev, float *y_dev, int CI, int CO, int D,
+                                     int H, int W, int stride, void *stream)
+{
+    int rc = pc_validate(CI, CO, D, H, W, stride);
+    if (rc) return rc;
+    if (!x_dev || !w_dev || !y_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_tc_w, w_dev, (size_t)CO * CI * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && b_dev) e = cudaMemcpyToSymbolAsync(c_tc_b, b_dev, (size_t)CO * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbolAsync(1x1 conv weights)");
+    const int OD = (D - 1) / stride + 1, OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    const size_t ovol = (size_t)OD * OH * OW;
+    size_t nb = (ovol + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    TC_DISPATCH(pointconv_fwd_kernel, <<<(unsigned)nb, 256, 0, s>>>(x_dev, y_dev, D, H, W, OD, OH, OW, stride, b_dev ? 1 : 0))
+    return check_cuda(cudaGetLastError(), "pointconv_forward");
+}
+
+extern "C" int trb_pointconv_backward(const float *x_dev, const float *w_dev, const float *gy_dev, float *gx_dev, float *gw_dev,
+                                      float *gb_dev, int CI, int CO, int D, int H, int W, int stride, void *workspace_dev,
+                                      size_t workspace_bytes, void *stream)
+{
+    int rc = pc_validate(CI, CO, D, H, W, stride);
+    if (rc) return rc;
+    if (!x_dev || !w_dev || !gy_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    const int OD = (D - 1) / stride + 1, OH = (H - 1) / stride + 1, OW = (W - 1) / stride + 1;
+    if (gx_dev) {
+        cudaError_t e = cudaMemcpyToSymbolAsync(c_tc_w, w_dev, (size_t)CO * CI * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+        if (e != cudaSuccess) return check_cuda(e, "cudaMemcpyToSymbolAsync(1x1 conv weights)");
+        size_t nb = ((size_t)D * H * W + 255) / 256;
+        if (nb > 148 * 16) nb = 148 * 16;
+        TC_DISPATCH(pointconv_dgrad_kernel, <<<(unsigned)nb, 256, 0, s>>>(gy_dev, gx_dev, D, H, W, OD, OH, OW, stride))
+    }
+    if (gw_dev) {
+        if (!workspace_dev || workspace_bytes < trb_pointconv_workspace_bytes(CI, CO)) {
+            set_error("workspace too small: need %zu bytes", trb_pointconv_workspace_bytes(CI, CO));
+            return TRB_ERR_WORKSPACE;
+        }
+        double *part = (double *)workspace_dev;
+        TC_DISPATCH(pointconv_wgrad_kernel, <<<kPcBlocks, 256, 0, s>>>(x_dev, gy_dev, D, H, W, OD, OH, OW, stride, part))
+        pointconv_wgrad_final_kernel<<<1, 32, 0, s>>>(part, kPcBlocks, CI, CO, gw_dev, gb_dev);
+    }
+    return check_cuda(cudaGetLastError(), "pointconv_backward");
+}

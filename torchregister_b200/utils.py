@@ -388,10 +388,30 @@ class _ThinConv3dFn(torch.autograd.Function):
         return gx, gw, gb
 
 
+class _PointConv3dFn(torch.autograd.Function):
+    """1x1x1 conv3d (uniform stride, no padding) with <= 4 channels each way on csrc/thinconv.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, stride):
+        from . import functional as TF
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias, ctx.stride = bias is not None, stride
+        return TF.point_conv3d_forward(x, weight, bias, stride)
+
+    @staticmethod
+    def backward(ctx, gy):
+        from . import functional as TF
+        x, weight = ctx.saved_tensors
+        gx, gw, gb = TF.point_conv3d_backward(x, weight, gy, ctx.stride, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                              ctx.has_bias and ctx.needs_input_grad[2])
+        return gx, gw, gb, None
+
+
 class Conv3dB200(nn.Conv3d):
     """nn.Conv3d whose thin 3x3x3 valid layers (<= 4 channels each way: the full-resolution layers of the flow U-Net at the
     reference's n = 32) run on csrc/thinconv.cu instead of cuDNN's tensor-core GEMMs, whose tiles are 64..256 output
-    channels wide (74 ms of a 106 ms epoch at 256^3).  Same parameters, same state_dict; everything else is nn.Conv3d."""
+    channels wide (74 ms of a 106 ms epoch at 256^3); likewise the 1x1x1 layers of the attention gates (uniform stride).  Same
+    parameters, same state_dict; everything else is nn.Conv3d."""
 
     def _thin(self, x):
         from .functional import THIN_CONV_MAX_CHANNELS as M
@@ -400,9 +420,17 @@ class Conv3dB200(nn.Conv3d):
                 and self.groups == 1 and self.padding in ((0, 0, 0), 0, 'valid') and self.in_channels <= M and self.out_channels <= M
                 and min(x.shape[2:]) >= 3)
 
+    def _point(self, x):
+        from .functional import THIN_CONV_MAX_CHANNELS as M
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[0] == 1 and self.weight.dtype == torch.float32
+                and tuple(self.kernel_size) == (1, 1, 1) and len(set(self.stride)) == 1 and tuple(self.dilation) == (1, 1, 1)
+                and self.groups == 1 and self.padding in ((0, 0, 0), 0, 'valid') and self.in_channels <= M and self.out_channels <= M)
+
     def forward(self, x):
         if self._thin(x):
             return _ThinConv3dFn.apply(x, self.weight, self.bias)
+        if self._point(x):
+            return _PointConv3dFn.apply(x, self.weight, self.bias, int(self.stride[0]))
         return super().forward(x)
 
 
