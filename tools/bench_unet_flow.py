@@ -13,7 +13,7 @@ mov, tgt = make_pair((S, S, S), "flow", device=dev)
 torch.manual_seed(0)
 out = {"size": S, "epochs": E}
 for name, crit, w in (("mse+ncc", [nn.MSELoss(), tr.NCCLoss()], [0.5, 0.5]), ("mse", [nn.MSELoss()], [1.0])):
-    fr = tr.flow_register((S, S, S), mode="bilinear", n=32, lr=1e-3, max_epochs=1, criterions=crit, weights=w).to(dev)
+    fr = tr.flow_register((S, S, S), mode="bilinear", n=32, lr=1e-3, max_epochs=1, criterions=crit, weights=w, stop_crit=-1.0).to(dev)
     fr.optimize(mov, tgt, dev, debug=False)           # warm-up epoch (cuDNN autotune)
     torch.cuda.synchronize()
     fr.max_epochs = E
