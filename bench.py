@@ -564,7 +564,7 @@ def main():
         # C-ABI call per optim() (csrc/nmi_src.cu); per-epoch time = difference of a 130- and a 30-epoch call (wall clock)
         def default_loss_us(m_, t_):
             rd = tr.Register(mode="affine", device=dev)
-            rd.optim(m_, t_, lr=1e-5, max_epochs=3)
+            rd.optim(m_, t_, lr=1e-5, max_epochs=30)        # warm-up with the timed call's own shape (allocator, lazy module loads)
             wall = []
             for ep in (30, 130):
                 torch.cuda.synchronize(dev)
@@ -578,6 +578,39 @@ def main():
                                                          "note": "wall clock through Register, per-epoch slope"}
         us = default_loss_us(mov, tgt)
         extra["batch_8x192x192x160_default_loss_mse+ncc+nmi"] = {"us_per_epoch": us, "voxel_warps_per_s": PAIRS_PER_GPU * vox / (us * 1e-6)}
+        # BASELINE configs[2] as the reference runs it: Register(mode='flow') = the attention U-Net (n = 32) + fused head/warp/
+        # similarity node at 256^3, MSE + NCC, per-epoch slope of the stock call (wall clock; InstanceNorm / thin convolutions on
+        # csrc/instnorm.cu, csrc/thinconv.cu, the rest cuDNN); and the direct per-voxel flow with the smoothness regulariser
+        del mov, tgt
+        torch.cuda.empty_cache()
+        try:
+            import torch.nn as nn
+            fm, ft = make_pair((256, 256, 256), "flow", device=dev)
+            wall = []
+            for ep in (2, 2, 6):
+                torch.manual_seed(0)
+                fr = tr.flow_register((256, 256, 256), mode="bilinear", n=32, lr=1e-3, max_epochs=ep, criterions=[nn.MSELoss(), tr.NCCLoss()],
+                                      weights=[0.5, 0.5], stop_crit=-1.0).to(dev)
+                torch.cuda.synchronize(dev)
+                t0 = time.perf_counter()
+                fr.optimize(fm, ft, dev, debug=False)
+                torch.cuda.synchronize(dev)
+                wall.append(time.perf_counter() - t0)
+                del fr
+            ms = (wall[2] - wall[1]) / 4 * 1e3
+            extra["configs2_flow_unet_256^3_mse+ncc"] = {"ms_per_epoch": ms, "voxel_warps_per_s": 256 ** 3 / (ms * 1e-3),
+                                                         "peak_mem_GB": torch.cuda.max_memory_allocated(dev) / 1e9}
+            dp = TF.DirectFlowProblem(fm, ft, 120, optimiser="sgd")
+            dp.run(20, 0.05, 0.5, 0.5, 2.0)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); dp.run(100, 0.05, 0.5, 0.5, 2.0); b.record()
+            torch.cuda.synchronize(dev)
+            us = a.elapsed_time(b) * 10.0
+            extra["configs2_direct_flow_256^3_sgd_mse+ncc+smooth"] = {"us_per_epoch": us, "voxel_warps_per_s": 256 ** 3 / (us * 1e-6),
+                                                                      "frac_of_hbm_peak_at_32B_per_voxel": 32.0 * 256 ** 3 / (us * 1e-6) / 1e9 / peak}
+            del fm, ft, dp
+        except Exception as e:          # keep the headline line even if an extra fails
+            extra["configs2_flow"] = {"error": repr(e)}
     if not args.no_extra and world > 1:
         del prob
         torch.cuda.empty_cache()
