@@ -379,8 +379,8 @@ int trb_instnorm_backward(const float *x_dev, const float *dy_dev, float *dx_dev
                           void *stream);
 
 /* ---- thin 3x3x3 convolutions of the flow U-Net (csrc/thinconv.cu) -----------------------
- * Replaces nn.Conv3d(kernel_size=3) (stride 1, no padding, C_in, C_out <= 4: the full-resolution layers of Attention_UNet at
- * the reference's n = 32, utils.py:409-520) and autograd's backward.  x [n][CI][D][H][W] -> y [n][CO][D-2][H-2][W-2];
+ * Replaces nn.Conv3d(kernel_size=3) (stride 1, no padding; any C_in, C_out <= 4 and the pairs 8->4, 4->8, 8->8: the two finest
+ * levels of Attention_UNet at the reference's n = 32, utils.py:409-520) and autograd's backward.  x [n][CI][D][H][W] -> y [n][CO][D-2][H-2][W-2];
  * w [CO][CI][3][3][3], b [CO] or NULL, all device fp32.  backward: gx_dev and/or gw_dev (+ gb_dev) may be NULL to skip
  * that gradient; the weight gradient handles one sample per call.  Weights travel through constant memory on `stream`:
  * calls on different streams of one device must not overlap. */

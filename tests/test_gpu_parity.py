@@ -763,7 +763,8 @@ def test_instance_norm_kernels_vs_torch(shape, relu):
 
 
 @pytest.mark.parametrize("n,ci,co,shape,bias", [(1, 1, 2, (20, 22, 40), True), (1, 4, 2, (12, 35, 133), True), (2, 2, 2, (9, 10, 11), True),
-                                                (1, 3, 4, (8, 8, 8), False), (1, 4, 4, (5, 6, 7), True), (1, 2, 1, (3, 3, 3), True)])
+                                                (1, 3, 4, (8, 8, 8), False), (1, 4, 4, (5, 6, 7), True), (1, 2, 1, (3, 3, 3), True),
+                                                (1, 8, 4, (10, 12, 70), True), (1, 4, 8, (6, 9, 33), True), (1, 8, 8, (7, 7, 9), False)])
 def test_thin_conv3d_kernels_vs_torch(n, ci, co, shape, bias):
     """csrc/thinconv.cu (3x3x3 valid convolutions with <= 4 channels each way) against F.conv3d in float64: output, input
     gradient, weight and bias gradients; ragged rows, batches, smallest volume."""

@@ -18,9 +18,10 @@
 
 namespace trb {
 
-constexpr int kTcMaxC = 4;
-__constant__ float c_tc_w[kTcMaxC * kTcMaxC * 27];
-__constant__ float c_tc_b[kTcMaxC];
+constexpr int kTcMaxC = 4;                    // every pair up to here; above it the U-Net's own pairs (8,4), (4,8), (8,8)
+constexpr int kTcMaxC8 = 8;
+__constant__ float c_tc_w[kTcMaxC8 * kTcMaxC8 * 27];
+__constant__ float c_tc_b[kTcMaxC8];
 
 // y[co][z][y][x] = b[co] + sum_{ci,dz,dy,dx} w[co][ci][dz][dy][dx] * x[ci][z+dz][y+dy][x+dx]
 template <int CI, int CO>
@@ -98,43 +99,51 @@ __global__ void __launch_bounds__(256) thinconv_dgrad_kernel(const float *__rest
     for (int ci = 0; ci < CI; ++ci) gx[ci * vol + o] = acc[ci];
 }
 
-// grid (blocks, CI * 3): group g = ci * 3 + dz.  part[g][block][9 * CO + CO] in fp64 (the last CO entries: sum dy, group 0 only)
-template <int CO>
+// grid (blocks, CI * 3 * co_groups): group g = (ci * 3 + dz) * co_groups + cg handles output channels [cg * COG, (cg + 1) * COG).
+// part[g][block][9 * COG + COG] in fp64 (the last COG entries: sum dy, taken from the groups with ci = dz = 0).  A lane takes 4
+// x positions per step so that 4 x (COG + 9) loads are in flight before the first FMA.
+template <int COG>
 __global__ void __launch_bounds__(256) thinconv_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ gy, int D, int H, int W,
-                                                              double *__restrict__ part)
+                                                              int co_groups, double *__restrict__ part)
 {
-    constexpr int NA = 9 * CO + CO;
+    constexpr int NA = 9 * COG + COG, XB = 4;
     __shared__ double sh[8][NA];
     const int OD = D - 2, OH = H - 2, OW = W - 2;
-    const int g = blockIdx.y, ci = g / 3, dz = g - ci * 3;
+    const int g = blockIdx.y, cg = g % co_groups, cd = g / co_groups, ci = cd / 3, dz = cd - ci * 3;
     const size_t HW = (size_t)H * W, vol = HW * D, OHW = (size_t)OH * OW, ovol = OHW * OD;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int rows = OD * OH;
     float a[NA];
-#pragma unroll
-    for (int i = 0; i < NA; ++i) a[i] = 0.f;
     double A[NA];
 #pragma unroll
-    for (int i = 0; i < NA; ++i) A[i] = 0.0;
+    for (int i = 0; i < NA; ++i) { a[i] = 0.f; A[i] = 0.0; }
     int since = 0;
     for (int r = blockIdx.x * 8 + warp; r < rows; r += gridDim.x * 8) {
         const int z = r / OH, yy = r - z * OH;
         const float *xr = x + ci * vol + (size_t)(z + dz) * HW + (size_t)yy * W;
-        const float *gr = gy + (size_t)z * OHW + (size_t)yy * OW;
-        for (int xx = lane; xx < OW; xx += 32) {
-            float gv[CO];
+        const float *gr = gy + (size_t)(cg * COG) * ovol + (size_t)z * OHW + (size_t)yy * OW;
+        for (int x0 = 0; x0 < OW; x0 += 32 * XB) {
+            float gv[XB][COG], xv[XB][9];
 #pragma unroll
-            for (int co = 0; co < CO; ++co) gv[co] = __ldg(gr + co * ovol + xx);
+            for (int j = 0; j < XB; ++j) {
+                const int xx = x0 + 32 * j + lane;
+                const bool in = xx < OW;
 #pragma unroll
-            for (int dy = 0; dy < 3; ++dy)
+                for (int co = 0; co < COG; ++co) gv[j][co] = in ? __ldg(gr + co * ovol + xx) : 0.f;
 #pragma unroll
-                for (int dx = 0; dx < 3; ++dx) {
-                    const float xv = __ldg(xr + (size_t)dy * W + xx + dx);
+                for (int dy = 0; dy < 3; ++dy)
 #pragma unroll
-                    for (int co = 0; co < CO; ++co) a[co * 9 + dy * 3 + dx] = fmaf(gv[co], xv, a[co * 9 + dy * 3 + dx]);
-                }
+                    for (int dx = 0; dx < 3; ++dx) xv[j][dy * 3 + dx] = in ? __ldg(xr + (size_t)dy * W + xx + dx) : 0.f;
+            }
 #pragma unroll
-            for (int co = 0; co < CO; ++co) a[9 * CO + co] += gv[co];
+            for (int j = 0; j < XB; ++j) {
+#pragma unroll
+                for (int k = 0; k < 9; ++k)
+#pragma unroll
+                    for (int co = 0; co < COG; ++co) a[co * 9 + k] = fmaf(gv[j][co], xv[j][k], a[co * 9 + k]);
+#pragma unroll
+                for (int co = 0; co < COG; ++co) a[9 * COG + co] += gv[j][co];
+            }
         }
         if (++since == 4) {                    // fp32 runs of at most 4 rows per lane, fp64 above
 #pragma unroll
@@ -157,32 +166,39 @@ __global__ void __launch_bounds__(256) thinconv_wgrad_kernel(const float *__rest
 }
 
 // dw[co][ci][dz][dy][dx] and db[co] from the block partials, fixed order
-__global__ void thinconv_wgrad_final_kernel(const double *__restrict__ part, int blocks, int CI, int CO, float *__restrict__ gw,
+__global__ void thinconv_wgrad_final_kernel(const double *__restrict__ part, int blocks, int CI, int CO, int COG, float *__restrict__ gw,
                                             float *__restrict__ gb)
 {
-    const int NA = 9 * CO + CO;
+    const int NA = 9 * COG + COG, co_groups = CO / COG;
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < CI * 3 * 9 * CO) {
-        const int g = i / (9 * CO), k = i - g * 9 * CO;          // k = co * 9 + (dy * 3 + dx)
-        const int ci = g / 3, dz = g - ci * 3, co = k / 9, d = k - co * 9;
+    if (i < CO * CI * 27) {
+        const int d = i % 9, dz = (i / 9) % 3, ci = (i / 27) % CI, co = i / (27 * CI);
+        const int g = (ci * 3 + dz) * co_groups + co / COG, k = (co % COG) * 9 + d;
         double v = 0.0;
         for (int b = 0; b < blocks; ++b) v += part[((size_t)g * blocks + b) * NA + k];
-        gw[((co * CI + ci) * 3 + dz) * 9 + d] = (float)v;
-    } else if (gb && i < CI * 3 * 9 * CO + CO) {
-        const int co = i - CI * 3 * 9 * CO;
+        gw[i] = (float)v;
+    } else if (gb && i < CO * CI * 27 + CO) {
+        const int co = i - CO * CI * 27;
+        const int g = co / COG;                                  // ci = dz = 0
         double v = 0.0;
-        for (int b = 0; b < blocks; ++b) v += part[(size_t)b * NA + 9 * CO + co];      // group 0
+        for (int b = 0; b < blocks; ++b) v += part[((size_t)g * blocks + b) * NA + 9 * COG + co % COG];
         gb[co] = (float)v;
     }
 }
 
 constexpr int kTcWgradBlocks = 96;
 
+static bool tc_pair_ok(int CI, int CO)
+{
+    if (CI >= 1 && CI <= kTcMaxC && CO >= 1 && CO <= kTcMaxC) return true;
+    return (CI == 8 && CO == 4) || (CI == 4 && CO == 8) || (CI == 8 && CO == 8);
+}
+
 static int tc_validate(int CI, int CO, int D, int H, int W)
 {
-    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) { set_error("thin convolution handles 1..%d channels (got %d -> %d)", kTcMaxC, CI, CO); return TRB_ERR_UNSUPPORTED; }
+    if (!tc_pair_ok(CI, CO)) { set_error("thin convolution handles 1..%d channels each way and 8->4, 4->8, 8->8 (got %d -> %d)", kTcMaxC, CI, CO); return TRB_ERR_UNSUPPORTED; }
     if (D < 3 || H < 3 || W < 3 || D > 65537) { set_error("bad volume shape %dx%dx%d", D, H, W); return TRB_ERR_ARG; }
-    if ((unsigned long long)D * H * W * kTcMaxC >= (1ull << 40)) { set_error("volume too large"); return TRB_ERR_UNSUPPORTED; }
+    if ((unsigned long long)D * H * W * kTcMaxC8 >= (1ull << 40)) { set_error("volume too large"); return TRB_ERR_UNSUPPORTED; }
     return TRB_OK;
 }
 
@@ -204,15 +220,23 @@ static int tc_upload(const float *w, const float *b, int CI, int CO, cudaStream_
     case 4 * 8 + 1: KERNEL<4, 1> __VA_ARGS__; break; case 4 * 8 + 2: KERNEL<4, 2> __VA_ARGS__; break;          \
     case 4 * 8 + 3: KERNEL<4, 3> __VA_ARGS__; break; default: KERNEL<4, 4> __VA_ARGS__; break;                 \
     }
+#define TC_DISPATCH3(KERNEL, ...)                                                                              \
+    if (CI == 8 && CO == 4) { KERNEL<8, 4> __VA_ARGS__; }                                                      \
+    else if (CI == 4 && CO == 8) { KERNEL<4, 8> __VA_ARGS__; }                                                 \
+    else if (CI == 8 && CO == 8) { KERNEL<8, 8> __VA_ARGS__; }                                                 \
+    else { TC_DISPATCH(KERNEL, __VA_ARGS__) }
 
 }  // namespace trb
 
 using namespace trb;
 
+static int tc_cog(int CO) { return CO > 4 ? 4 : CO; }
+
 extern "C" size_t trb_thinconv3_workspace_bytes(int CI, int CO)
 {
-    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) return 0;
-    return (size_t)CI * 3 * kTcWgradBlocks * (9 * CO + CO) * sizeof(double);
+    if (!tc_pair_ok(CI, CO)) return 0;
+    const int COG = tc_cog(CO);
+    return (size_t)CI * 3 * (CO / COG) * kTcWgradBlocks * (9 * COG + COG) * sizeof(double);
 }
 
 extern "C" int trb_thinconv3_forward(const float *x_dev, const float *w_dev, const float *b_dev, float *y_dev, int n_batch, int CI,
@@ -230,7 +254,7 @@ extern "C" int trb_thinconv3_forward(const float *x_dev, const float *w_dev, con
     for (int n = 0; n < n_batch; ++n) {
         const float *xn = x_dev + (size_t)n * CI * vol;
         float *yn = y_dev + (size_t)n * CO * ovol;
-        TC_DISPATCH(thinconv_fwd_kernel, <<<grid, 256, 0, s>>>(xn, yn, D, H, W, b_dev ? 1 : 0))
+        TC_DISPATCH3(thinconv_fwd_kernel, <<<grid, 256, 0, s>>>(xn, yn, D, H, W, b_dev ? 1 : 0))
     }
     return check_cuda(cudaGetLastError(), "thinconv3_forward");
 }
@@ -252,7 +276,7 @@ extern "C" int trb_thinconv3_backward(const float *x_dev, const float *w_dev, co
         for (int n = 0; n < n_batch; ++n) {
             const float *gn = gy_dev + (size_t)n * CO * ovol;
             float *xn = gx_dev + (size_t)n * CI * vol;
-            TC_DISPATCH(thinconv_dgrad_kernel, <<<grid, 256, 0, s>>>(gn, xn, D, H, W))
+            TC_DISPATCH3(thinconv_dgrad_kernel, <<<grid, 256, 0, s>>>(gn, xn, D, H, W))
         }
     }
     if (gw_dev) {
@@ -261,15 +285,16 @@ extern "C" int trb_thinconv3_backward(const float *x_dev, const float *w_dev, co
             return TRB_ERR_WORKSPACE;
         }
         double *part = (double *)workspace_dev;
-        const dim3 grid(kTcWgradBlocks, CI * 3);
-        switch (CO) {
-        case 1: thinconv_wgrad_kernel<1><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
-        case 2: thinconv_wgrad_kernel<2><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
-        case 3: thinconv_wgrad_kernel<3><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
-        default: thinconv_wgrad_kernel<4><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        const int COG = tc_cog(CO), cgs = CO / COG;
+        const dim3 grid(kTcWgradBlocks, CI * 3 * cgs);
+        switch (COG) {
+        case 1: thinconv_wgrad_kernel<1><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, cgs, part); break;
+        case 2: thinconv_wgrad_kernel<2><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, cgs, part); break;
+        case 3: thinconv_wgrad_kernel<3><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, cgs, part); break;
+        default: thinconv_wgrad_kernel<4><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, cgs, part); break;
         }
         const int n = CI * 27 * CO + CO;
-        thinconv_wgrad_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, kTcWgradBlocks, CI, CO, gw_dev, gb_dev);
+        thinconv_wgrad_final_kernel<<<(n + 127) / 128, 128, 0, s>>>(part, kTcWgradBlocks, CI, CO, COG, gw_dev, gb_dev);
     }
     return check_cuda(cudaGetLastError(), "thinconv3_backward");
 }

@@ -417,8 +417,8 @@ class Conv3dB200(nn.Conv3d):
         from .functional import THIN_CONV_MAX_CHANNELS as M
         return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and self.weight.dtype == torch.float32
                 and tuple(self.kernel_size) == (3, 3, 3) and tuple(self.stride) == (1, 1, 1) and tuple(self.dilation) == (1, 1, 1)
-                and self.groups == 1 and self.padding in ((0, 0, 0), 0, 'valid') and self.in_channels <= M and self.out_channels <= M
-                and min(x.shape[2:]) >= 3)
+                and self.groups == 1 and self.padding in ((0, 0, 0), 0, 'valid') and min(x.shape[2:]) >= 3
+                and ((self.in_channels <= M and self.out_channels <= M) or (self.in_channels, self.out_channels) in ((8, 4), (4, 8), (8, 8))))
 
     def _point(self, x):
         from .functional import THIN_CONV_MAX_CHANNELS as M
