@@ -511,8 +511,9 @@ int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *tar
                              const float *state_dev, double *moments_dev, int flags, int target_sums,
                              float *warped_out, bool *wrote_warped, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
-    // target_sums: 0 = the caller does not need sum t / sum t^2 (vjp pass), 1 = compute them, 2 = an earlier call with 1 on
-    // this workspace and these targets left them valid (only the persistent kernel keeps them apart from the pass)
+    // target_sums: 0 = the caller does not need sum t / sum t^2 (vjp pass), 1 = compute them (stand-alone call), 3 = compute
+    // them and keep them for later calls, 2 = an earlier call with 3 on this workspace and these targets left them valid
+    // (only the persistent kernel keeps them apart from the pass)
     if (wrote_warped) *wrote_warped = false;
     AffineParams p{};
     int rc = fill_params(p, ndim, moving_dev, target_dev, pair_stride, n_pairs, D, H, W, xb_dev, yb_dev, zb_dev,
@@ -531,11 +532,13 @@ int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *tar
         const bool store = warped_out && s_begin == 0 && s_end == D && pair_stride == (long long)D * H * W;
         // One pass of the persistent kernel (steady-state rate of the fused loop, ~15 us of cooperative launch + publish)
         // against the per-epoch kernel (lower fixed cost, 25 % slower per tile): large rotations always (its gather
-        // variant is 2-3x faster than the per-epoch kernel's uncached fallback), else from ~10 tiles per SM on
+        // variant is 2-3x faster than the per-epoch kernel's uncached fallback), else from ~10 tiles per SM on — unless the
+        // pass would have to recompute the target sums (a separate pass over the targets in the persistent design: the
+        // default-loss loop caches them after its first epoch, a stand-alone trb_affine_moments call cannot)
         const long long tiles = (long long)n_pairs * ((W + TX - 1) / TX) * ((H + TY - 1) / TY) * ((s_end - s_begin + TZ - 1) / TZ);
-        if (p.gather || tiles >= 10LL * sm_count()) {
+        if (p.gather || (target_sums != 1 && tiles >= 10LL * sm_count())) {
             if (store) p.warped_out = warped_out;
-            rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, target_sums == 0 ? 2 : (target_sums == 2 ? 3 : 1));
+            rc = launch_affine3d_persist(p, n_pairs, 0, 1, s, target_sums == 0 ? 2 : (target_sums == 2 ? 3 : 1));   // 1 and 3: compute
             if (rc != TRB_ERR_UNSUPPORTED) {
                 if (rc == TRB_OK && store && wrote_warped) *wrote_warped = true;
                 return rc;

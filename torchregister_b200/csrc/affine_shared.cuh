@@ -17,7 +17,7 @@ bool tma_path_eligible(int ndim, const AffineParams &a, int n_pairs);
 int launch_affine3d_tma(AffineParams a, int n_pairs, bool fused, int epoch0, int n_launch, cudaStream_t stream);
 // moments of slices [s_begin, s_end) for all pairs (trb_affine_moments_ex); warped_out (optional, 3-D): the warped volumes
 // as a by-product when a TMA-tile kernel takes the pass — *wrote_warped says whether it did; target_sums: 0 not needed,
-// 1 compute, 2 still valid from an earlier call with 1 on the same workspace and targets
+// 1 compute, 3 compute and keep, 2 still valid from an earlier call with 3 on the same workspace and targets
 int affine_moments_impl(int ndim, const float *moving_dev, const float *target_dev, long long pair_stride, int n_pairs, int D, int H,
                         int W, int s_begin, int s_end, const float *xb_dev, const float *yb_dev, const float *zb_dev,
                         const float *state_dev, double *moments_dev, int flags, int target_sums, float *warped_out,

@@ -561,7 +561,7 @@ extern "C" int trb_affine_optim_nmi(int ndim, int mode, const float *moving_dev,
     for (int e = 0; e < n_epochs; ++e) {
         bool have_warped = false;
         rc = affine_moments_impl(ndim, moving_dev, target_dev, vol, n_pairs, Dn, H, W, 0, slices, xb_dev, yb_dev, zb_dev, state_dev, mom, flags,
-                                 e == 0 ? 1 : 2, warped_scratch_dev, &have_warped, workspace_dev, workspace_bytes, stream);
+                                 e == 0 ? 3 : 2, warped_scratch_dev, &have_warped, workspace_dev, workspace_bytes, stream);
         if (rc) return rc;
         if (!have_warped) {             // the pass ran on a kernel without the by-product (2-D / shape / rotation): separate warp
             nmi_src_theta_kernel<<<nb, 128, 0, s>>>(state_dev, theta, n_pairs, nt);
