@@ -567,11 +567,14 @@ def main():
             rd.optim(m_, t_, lr=1e-5, max_epochs=30)        # warm-up with the timed call's own shape (allocator, lazy module loads)
             wall = []
             for ep in (30, 130):
-                torch.cuda.synchronize(dev)
-                t0 = time.perf_counter()
-                rd.optim(m_, t_, lr=1e-5, max_epochs=ep)
-                torch.cuda.synchronize(dev)
-                wall.append(time.perf_counter() - t0)
+                best = 1e9
+                for _ in range(3):      # min of 3: a call's set-up (allocator, value bounds, target moments) varies by milliseconds
+                    torch.cuda.synchronize(dev)
+                    t0 = time.perf_counter()
+                    rd.optim(m_, t_, lr=1e-5, max_epochs=ep)
+                    torch.cuda.synchronize(dev)
+                    best = min(best, time.perf_counter() - t0)
+                wall.append(best)
             return (wall[1] - wall[0]) / 100 * 1e6
         us = default_loss_us(one_m, one_t)
         extra["single_pair_default_loss_mse+ncc+nmi"] = {"us_per_epoch": us, "voxel_warps_per_s": vox / (us * 1e-6),
