@@ -85,6 +85,16 @@ const char *trb_affine_kernel_status(void);
 /* Bytes of scratch (dev) needed by trb_affine_* for `n_pairs` pairs. */
 size_t trb_affine_workspace_bytes(int n_pairs);
 
+/* Pair volume for the large-rotation (gather) variant of the 3-D loops: P[pair][z][y][xr] = (v[xr-2], v[xr-1]), W + 3 records of
+ * two floats per row, zeros outside — one 8-byte gather per (y, z) corner instead of two 4-byte ones (the gathers of a rotated
+ * warp are bound by cache lines touched).  trb_affine_build_pairs fills it from the moving volumes ([n_pairs][D][H][W]
+ * contiguous); trb_affine_attach_pairs records its address in the workspace that the trb_affine_* calls of this batch use
+ * (NULL detaches).  Optional: without it the gather variant reads the moving volumes themselves.  The buffer must stay alive
+ * and unchanged while attached. */
+size_t trb_affine_pairs_bytes(int n_pairs, int D, int H, int W);
+int trb_affine_build_pairs(const float *moving_dev, float *pairs_dev, int n_pairs, int D, int H, int W, void *stream);
+int trb_affine_attach_pairs(void *workspace_dev, size_t workspace_bytes, int n_pairs, const float *pairs_dev, void *stream);
+
 /* Write start parameters from HOST memory into state[.][0..n_params) of n_pairs pairs (n_rows == 1: the same row for
  * every pair, else n_rows == n_pairs).  The values travel as kernel arguments: asynchronous, stream ordered, no pinned
  * memory and no host wait behind the work already queued on the stream.  Call trb_affine_init_state afterwards. */

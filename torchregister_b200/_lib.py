@@ -23,6 +23,9 @@ _SIGNATURES = {
     "trb_affine_kernel_status": (C.c_char_p, []),
     "trb_affine_workspace_bytes": (_sz, [_i]),
     "trb_affine_init_state": (_i, [_i, _i, c_fp, _i, c_fp]),
+    "trb_affine_pairs_bytes": (_sz, [_i, _i, _i, _i]),
+    "trb_affine_build_pairs": (_i, [c_fp, c_fp, _i, _i, _i, _i, c_fp]),
+    "trb_affine_attach_pairs": (_i, [c_fp, _sz, _i, c_fp, c_fp]),
     "trb_affine_set_params": (_i, [c_fp, _i, _i, c_fp, _i, c_fp]),
     "trb_affine_optim": (_i, [_i, _i, c_fp, c_fp, _ll, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i,
                               _i, _i, _f, _f, _f, _i, _f, _f, _f, c_fp, _sz, c_fp]),

@@ -365,6 +365,49 @@ static int validate_common(int ndim, int n_pairs, int D, int H, int W)
     return TRB_OK;
 }
 
+// ---- pair volume for the large-rotation (gather) variant --------------------------------------------------------------
+__global__ void __launch_bounds__(256) affine_build_pairs_kernel(const float *__restrict__ mov, float2 *__restrict__ P, long long rows, int W)
+{
+    const int Wp = W + 3;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < rows * Wp; i += (long long)gridDim.x * 256) {
+        const long long r = i / Wp;
+        const int xr = (int)(i - r * Wp);
+        const float *row = mov + r * W;
+        const int xa = xr - 2, xb = xr - 1;
+        P[i] = make_float2((unsigned)xa < (unsigned)W ? __ldg(row + xa) : 0.f, (unsigned)xb < (unsigned)W ? __ldg(row + xb) : 0.f);
+    }
+}
+__global__ void affine_attach_pairs_kernel(unsigned *tickets, unsigned long long addr)
+{
+    if (threadIdx.x == 0) *reinterpret_cast<unsigned long long *>(tickets + kPairsWord) = addr;
+}
+
+extern "C" size_t trb_affine_pairs_bytes(int n_pairs, int D, int H, int W)
+{
+    if (n_pairs < 1 || D < 1 || H < 1 || W < 1) return 0;
+    return (size_t)n_pairs * D * H * (W + 3) * sizeof(float2);
+}
+
+extern "C" int trb_affine_build_pairs(const float *moving_dev, float *pairs_dev, int n_pairs, int D, int H, int W, void *stream)
+{
+    int rc = validate_common(3, n_pairs, D, H, W);
+    if (rc) return rc;
+    if (!moving_dev || !pairs_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    const long long rows = (long long)n_pairs * D * H;
+    long long nb = (rows * (W + 3) + 255) / 256;
+    if (nb > 148 * 32) nb = 148 * 32;
+    affine_build_pairs_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(moving_dev, reinterpret_cast<float2 *>(pairs_dev), rows, W);
+    return check_cuda(cudaGetLastError(), "affine_build_pairs");
+}
+
+extern "C" int trb_affine_attach_pairs(void *workspace_dev, size_t workspace_bytes, int n_pairs, const float *pairs_dev, void *stream)
+{
+    if (!workspace_dev || n_pairs < 1 || workspace_bytes < affine_ws_bytes(n_pairs)) { set_error("workspace too small / null"); return TRB_ERR_WORKSPACE; }
+    unsigned *tickets = (unsigned *)((char *)workspace_dev + (size_t)n_pairs * kMaxBlocksPerPair * TRB_MOMENTS * sizeof(double));
+    affine_attach_pairs_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(tickets, (unsigned long long)(uintptr_t)pairs_dev);
+    return check_cuda(cudaGetLastError(), "affine_attach_pairs");
+}
+
 extern "C" int trb_affine_set_params(float *state_dev, int n_pairs, int n_params, const float *params_host, int n_rows, void *stream)
 {
     if (!state_dev || !params_host || n_pairs < 1) { set_error("null state / params"); return TRB_ERR_ARG; }

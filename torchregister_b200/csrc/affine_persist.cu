@@ -71,6 +71,8 @@ struct PersistParams {
     int n_epochs;                    // epochs in this launch (<= chunk capacity of the accumulator region)
     unsigned long long *acc;         // [n_epochs][n_pairs][kAccWords], zeroed before the launch
     const unsigned *targets;         // tickets region; word [pair*kTicketStride + kTargetWord]
+    const unsigned long long *pairs_slot;   // gather variant: device word holding the address of the pair volume (or 0)
+    int pair0;                       // first pair of this launch within the batch (sub-batches)
 };
 
 using PL = SmemLayout<kBX, kBY, kBZ>;
@@ -663,6 +665,10 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
     bool valid = false;
     float xv = 0.f, yv = 0.f, pxy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f};
     const float *__restrict__ mov = p.a.moving;
+    // gather variant: the pair volume (trb_affine_attach_pairs), if the caller built one
+    const float2 *pairs_all = ROT ? reinterpret_cast<const float2 *>(__ldcg(pp.pairs_slot)) : nullptr;
+    const float2 *pairs = nullptr;
+    const size_t pair_pitch = (size_t)D * H * (W + kPairPad);
     float *wcol0 = nullptr;              // STORE: this thread's column of the warped output
     Acc2 A;
     int kcol = 0;
@@ -692,6 +698,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                 sz[r] = pc.coef[r * 4 + 2] * inv_d2;
             }
             mov = p.a.moving + (size_t)pc.pair * p.a.pair_stride;
+            if (ROT && pairs_all) pairs = pairs_all + (size_t)(pp.pair0 + pc.pair) * pair_pitch;
             if constexpr (STORE) wcol0 = p.a.warped_out + (size_t)pc.pair * p.a.pair_stride + (size_t)y * W + x;
 #pragma unroll
             for (int i = 0; i < 12; ++i) A.a[i] = f2(0.f);
@@ -763,8 +770,10 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
 #pragma unroll 4
                 for (int zz = 0; zz < nz; ++zz) {
                     const float zf = m.zf0 + (float)zz;
-                    const float wv = voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]),
-                                                             fmaf(sz[2], zf, pxy[2]), lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    const float qx = fmaf(sz[0], zf, pxy[0]), qy = fmaf(sz[1], zf, pxy[1]), qz = fmaf(sz[2], zf, pxy[2]);
+                    const float tv = lds_f_dyn(tg + zz * (TX * TY * 4));
+                    const float wv = pairs ? voxel_direct2p<MSE_ONLY>(pairs, D, H, W, qx, qy, qz, tv, zf, A)
+                                           : voxel_direct2<MSE_ONLY>(mov, D, H, W, qx, qy, qz, tv, zf, A);
                     if (wcol) __stcs(wcol + (size_t)zz * H * W, wv);
                 }
             } else {
@@ -952,6 +961,8 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
             set_contributions_kernel<<<1, ContribBlock::kPairs, 0, stream>>>(as.tickets + (size_t)c0 * kTicketStride, n, cb);
         }
         pp.acc = reinterpret_cast<unsigned long long *>(as.partials);
+        pp.pairs_slot = reinterpret_cast<const unsigned long long *>(a.tickets + kPairsWord);     // slot of the WHOLE batch
+        pp.pair0 = p0;
         pp.targets = as.tickets;
         pp.tsum_blocks = (mse_only || moments_mode == 2) ? 0 : kTsumBlocks;
         pp.moments_only = moments_only ? 1 : 0;

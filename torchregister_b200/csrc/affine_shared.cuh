@@ -10,6 +10,7 @@
 namespace trb {
 
 constexpr int kTicketStride = 128;  // unsigned counters per pair in the workspace (direct kernel uses [127])
+constexpr int kPairsWord = 120;     // tickets[120..121] of pair 0: address of the pair volume (trb_affine_attach_pairs) or 0
 constexpr int kMaxSlots = 1024;      // partial-sum slots per pair in the workspace (>= CTAs contributing to a pair)
 
 struct AffineParams;

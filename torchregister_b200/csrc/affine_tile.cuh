@@ -391,6 +391,39 @@ __device__ __forceinline__ float voxel_direct2(const float *__restrict__ mov, in
     return val;
 }
 
+// the same voxel from the PAIR volume (large-rotation variant): P[z][y][xr] = (v[xr-2], v[xr-1]) with W + 3 records per row and
+// zeros outside, so ONE 8-byte load per (y, z) corner brings both x neighbours and the zero padding in x: 4 gathers instead of 8
+// — the gathers of a rotated warp are bound by the number of cache lines they touch, not by bytes
+constexpr int kPairPad = 3;
+template <bool MSE_ONLY>
+__device__ __forceinline__ float voxel_direct2p(const float2 *__restrict__ P, int D, int H, int W, float ix, float iy, float iz,
+                                                float t, float zf, Acc2 &A)
+{
+    ix = fminf(fmaxf(ix, -2.f), (float)W + 0.5f);       // x0 in [-2, W]: records 0 and W + 2 are (0, 0)
+    iy = fminf(fmaxf(iy, -4.f), (float)H + 4.f);
+    iz = fminf(fmaxf(iz, -4.f), (float)D + 4.f);
+    const float fx = __fadd_rd(ix, kMagic) - kMagic, fy = __fadd_rd(iy, kMagic) - kMagic, fz = __fadd_rd(iz, kMagic) - kMagic;
+    const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const bool vy0 = (unsigned)y0 < (unsigned)H, vy1 = (unsigned)(y0 + 1) < (unsigned)H;
+    const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+    const long long Wp = W + kPairPad, HWp = (long long)H * Wp, o = ((long long)z0 * H + y0) * Wp + (x0 + 2);
+    const float2 zero = make_float2(0.f, 0.f);
+    const float2 r00 = (vz0 & vy0) ? __ldg(P + o) : zero, r01 = (vz0 & vy1) ? __ldg(P + o + Wp) : zero;
+    const float2 r10 = (vz1 & vy0) ? __ldg(P + o + HWp) : zero, r11 = (vz1 & vy1) ? __ldg(P + o + HWp + Wp) : zero;
+    const float d00 = r00.y - r00.x, d01 = r01.y - r01.x, d10 = r10.y - r10.x, d11 = r11.y - r11.x;
+    const float v00 = fmaf(tx, d00, r00.x), v01 = fmaf(tx, d01, r01.x), v10 = fmaf(tx, d10, r10.x), v11 = fmaf(tx, d11, r11.x);
+    const float e0 = v01 - v00, e1 = v11 - v10;
+    const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
+    const float G2 = w1 - w0;
+    const float val = fmaf(tz, G2, w0);
+    const float G1 = fmaf(tz, e1 - e0, e0);
+    const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
+    const float G0 = fmaf(tz, dx1 - dx0, dx0);
+    moments_accumulate<MSE_ONLY>(t, zf, val, G0, G1, G2, A);
+    return val;
+}
+
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
 template <bool MSE_ONLY>
 __device__ __forceinline__ float voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,
