@@ -43,6 +43,7 @@ extern "C" {
 #define TRB_OPT_SGD 0      /* torch.optim.SGD(lr), warpings.py:58,131,192 */
 #define TRB_OPT_ADAM 1     /* extension (north_star item 3); no reference counterpart */
 #define TRB_FLAG_LARGE_ROTATION 1   /* trb_affine_optim_ex / trb_warp_affine_batch: see there */
+#define TRB_FLAG_PAIR_VOLUME 2      /* with TRB_FLAG_LARGE_ROTATION: a pair volume is attached to the workspace (trb_affine_attach_pairs) */
 
 /* Per-pair optimiser state: TRB_STATE_FLOATS fp32 values, device resident.
  *   [ 0..11] params        (rigid: 6|3 used, affine: 12|6 used)

@@ -498,7 +498,7 @@ extern "C" int trb_affine_optim_ex(int ndim, int mode, const float *moving_dev, 
     p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride;
     p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
-    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
+    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? ((flags & TRB_FLAG_PAIR_VOLUME) ? 2 : 1) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
         if (n_epochs <= 0) return TRB_OK;
@@ -568,7 +568,7 @@ int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *tar
     p.s_begin = s_begin; p.s_end = s_end;
     p.state = const_cast<float *>(state_dev);
     p.moments_out = moments_dev;
-    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? 1 : 0;
+    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? ((flags & TRB_FLAG_PAIR_VOLUME) ? 2 : 1) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
         // both TMA-tile kernels store the warped samples on request (whole volumes of single-channel pairs only)

@@ -405,7 +405,10 @@ __device__ __forceinline__ void acquire_theta(const PersistParams &pp, int e_rel
 // the 8 corner loads of a patch touch a compact source region — and gathers the moving volume through L1.
 // STORE (unfused one-pass mode only): the staged path also leaves the warped samples in a.warped_out (the gather
 // variant decides that at run time)
-template <bool MSE_ONLY, bool ROT, bool STORE = false>
+// PAIRS (gather variant only): the moving volume is read through the pair volume whose address sits in the workspace
+// (trb_affine_attach_pairs; the caller says so with TRB_FLAG_PAIR_VOLUME) — a separate instantiation, so that the scalar
+// gather loop keeps its registers and its unrolling
+template <bool MSE_ONLY, bool ROT, bool STORE = false, bool PAIRS = false>
 __global__ void __launch_bounds__(kPersistThreads, 1)
 affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensorMap map_mov,
                         const __grid_constant__ CUtensorMap map_tgt)
@@ -666,9 +669,8 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
     float xv = 0.f, yv = 0.f, pxy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f};
     const float *__restrict__ mov = p.a.moving;
     // gather variant: the pair volume (trb_affine_attach_pairs), if the caller built one
-    const float2 *pairs_all = ROT ? reinterpret_cast<const float2 *>(__ldcg(pp.pairs_slot)) : nullptr;
+    const float2 *pairs_all = PAIRS ? reinterpret_cast<const float2 *>(__ldcg(pp.pairs_slot)) : nullptr;
     const float2 *pairs = nullptr;
-    const size_t pair_pitch = (size_t)D * H * (W + kPairPad);
     float *wcol0 = nullptr;              // STORE: this thread's column of the warped output
     Acc2 A;
     int kcol = 0;
@@ -698,7 +700,7 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                 sz[r] = pc.coef[r * 4 + 2] * inv_d2;
             }
             mov = p.a.moving + (size_t)pc.pair * p.a.pair_stride;
-            if (ROT && pairs_all) pairs = pairs_all + (size_t)(pp.pair0 + pc.pair) * pair_pitch;
+            if constexpr (PAIRS) pairs = pairs_all + (size_t)(pp.pair0 + pc.pair) * ((size_t)D * H * (W + kPairPad));
             if constexpr (STORE) wcol0 = p.a.warped_out + (size_t)pc.pair * p.a.pair_stride + (size_t)y * W + x;
 #pragma unroll
             for (int i = 0; i < 12; ++i) A.a[i] = f2(0.f);
@@ -770,10 +772,13 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
 #pragma unroll 4
                 for (int zz = 0; zz < nz; ++zz) {
                     const float zf = m.zf0 + (float)zz;
-                    const float qx = fmaf(sz[0], zf, pxy[0]), qy = fmaf(sz[1], zf, pxy[1]), qz = fmaf(sz[2], zf, pxy[2]);
-                    const float tv = lds_f_dyn(tg + zz * (TX * TY * 4));
-                    const float wv = pairs ? voxel_direct2p<MSE_ONLY>(pairs, D, H, W, qx, qy, qz, tv, zf, A)
-                                           : voxel_direct2<MSE_ONLY>(mov, D, H, W, qx, qy, qz, tv, zf, A);
+                    float wv;
+                    if constexpr (PAIRS)
+                        wv = voxel_direct2p<MSE_ONLY>(pairs, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
+                                                      lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    else
+                        wv = voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
+                                                     lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
                     if (wcol) __stcs(wcol + (size_t)zz * H * W, wv);
                 }
             } else {
@@ -891,7 +896,9 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
     const bool mse_only = !moments_only && a.w_ncc == 0.f;
     const bool rot = a.gather != 0;
     const bool store = moments_only && !rot && a.warped_out != nullptr;
-    auto kern = rot ? (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>)
+    const bool pairs = rot && a.gather == 2;
+    auto kern = rot ? (pairs ? (mse_only ? affine3d_persist_kernel<true, true, false, true> : affine3d_persist_kernel<false, true, false, true>)
+                             : (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>))
                     : (mse_only ? affine3d_persist_kernel<true, false>
                                 : (store ? affine3d_persist_kernel<false, false, true> : affine3d_persist_kernel<false, false>));
     const size_t kPersistSmem = rot ? Ring<true>::kSmem : Ring<false>::kSmem;
@@ -993,7 +1000,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         }
     }
     snprintf(g_persist_status, sizeof(g_persist_status), "launched: grid %d, %d SMs, %s variant, sub-batches of %d pair(s)",
-             (int)(sms < (long long)n_pairs * cpp * tiles_z ? sms : (long long)n_pairs * cpp * tiles_z), sms, rot ? "gather" : "tma", sub);
+             (int)(sms < (long long)n_pairs * cpp * tiles_z ? sms : (long long)n_pairs * cpp * tiles_z), sms, rot ? (pairs ? "gather (pair volume)" : "gather") : "tma", sub);
     return check_cuda(cudaGetLastError(), "affine3d_persist");
 }
 const char *persist_status() { return g_persist_status; }

@@ -50,7 +50,8 @@ struct AffineParams {
     float *warped_out;           // optional [n_pairs][D][H][W]: the unfused 3-D TMA moments pass also stores the warped volume
     const double *extra;         // optional [n_pairs][13]: extra loss term and its d/dtheta (e.g. the NMI term), or NULL
     int extra_pair;              // row of `extra` (set by the epilogue wrappers)
-    int gather;                  // 1: large-rotation variant of the persistent kernel (L1 gathers instead of TMA-staged boxes)
+    int gather;                  // 1: large-rotation variant of the persistent kernel (L1 gathers instead of TMA-staged boxes);
+                                 // 2: the same, reading the pair volume attached to the workspace
     PeerExchange peer;
 };
 

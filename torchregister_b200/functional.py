@@ -161,6 +161,7 @@ class AffineProblem:
                                                       self.H, self.W, _stream(self.device)), "affine_build_pairs")
                 check(self.lib.trb_affine_attach_pairs(self.workspace.data_ptr(), self.workspace.numel(), self.n_pairs,
                                                        self.moving_pairs.data_ptr(), _stream(self.device)), "affine_attach_pairs")
+            self.flags |= 2               # TRB_FLAG_PAIR_VOLUME
 
     def _start_needs_gather(self, p0: torch.Tensor) -> bool:
         import ctypes as C
