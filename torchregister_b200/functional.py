@@ -616,9 +616,9 @@ def instance_norm_backward(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tenso
 # thin 3x3x3 convolutions of the flow U-Net
 # --------------------------------------------------------------------------- #
 THIN_CONV_MAX_CHANNELS = 4
-# the pair volume of the gather variant pays while it stays L2 resident (126 MB on B200); beyond that its doubled bytes cost
-# more HBM traffic than the halved gathers save (measured: one 192x192x160 pair 52 -> 43 us, a batch of 8 388 -> 435 us)
-PAIR_VOLUME_MAX_BYTES = 100 << 20
+# the pair volume of the gather variant costs 2x the moving volumes in memory (measured gain: one 192x192x160 pair 55 -> 36 us,
+# 256^3 144 -> 117, a batch of 8 389 -> 287); beyond this size the scalar gathers are used
+PAIR_VOLUME_MAX_BYTES = 16 << 30
 
 
 def thin_conv3d_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
