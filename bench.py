@@ -433,7 +433,7 @@ def main():
     ms = float(tmax.item())
     losses = prob.losses[0, W:W + 3].tolist()
     value = world * PAIRS_PER_GPU * vox * K / (ms * 1e-3)
-    launches = -(-K // CHUNK_EPOCHS) + 1          # persistent launches + target_sums_kernel
+    launches = -(-K // CHUNK_EPOCHS) + 2          # persistent launches + set_contributions_kernel + target_sums_kernel (once per call)
 
     # ---- end to end through the public API with host buffers ------------------------------
     er, ea = max(1, int(README_EPOCHS[0] * args.e2e_scale)), max(1, int(README_EPOCHS[1] * args.e2e_scale))
