@@ -340,6 +340,7 @@ class _InstanceNormFn(torch.autograd.Function):
         return y
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, dy):
         from . import functional as TF
         x, stats = ctx.saved_tensors
@@ -380,6 +381,7 @@ class _ThinConv3dFn(torch.autograd.Function):
         return TF.thin_conv3d_forward(x, weight, bias)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         from . import functional as TF
         x, weight = ctx.saved_tensors
@@ -399,6 +401,7 @@ class _PointConv3dFn(torch.autograd.Function):
         return TF.point_conv3d_forward(x, weight, bias, stride)
 
     @staticmethod
+    @torch.autograd.function.once_differentiable
     def backward(ctx, gy):
         from . import functional as TF
         x, weight = ctx.saved_tensors
