@@ -44,6 +44,7 @@ extern "C" {
 #define TRB_OPT_ADAM 1     /* extension (north_star item 3); no reference counterpart */
 #define TRB_FLAG_LARGE_ROTATION 1   /* trb_affine_optim_ex / trb_warp_affine_batch: see there */
 #define TRB_FLAG_PAIR_VOLUME 2      /* with TRB_FLAG_LARGE_ROTATION: a pair volume is attached to the workspace (trb_affine_attach_pairs) */
+#define TRB_FLAG_QUAD_VOLUME 4      /* with TRB_FLAG_LARGE_ROTATION: a quad volume is attached instead (trb_affine_build_quads) */
 
 /* Per-pair optimiser state: TRB_STATE_FLOATS fp32 values, device resident.
  *   [ 0..11] params        (rigid: 6|3 used, affine: 12|6 used)
@@ -94,6 +95,11 @@ size_t trb_affine_workspace_bytes(int n_pairs);
  * and unchanged while attached. */
 size_t trb_affine_pairs_bytes(int n_pairs, int D, int H, int W);
 int trb_affine_build_pairs(const float *moving_dev, float *pairs_dev, int n_pairs, int D, int H, int W, void *stream);
+/* Quad volume: Q[pair][z][yr][xr] = (v[y][x], v[y][x+1], v[y+1][x], v[y+1][x+1]) at (x, y) = (xr-2, yr-2), (H+3) x (W+3) records of four
+ * floats per slice, zeros outside — one 16-byte gather per z plane of a cell (2 per voxel).  4x the moving volumes in memory: worth
+ * it while it stays L2 resident.  Attached with trb_affine_attach_pairs like the pair volume; flag TRB_FLAG_QUAD_VOLUME. */
+size_t trb_affine_quads_bytes(int n_pairs, int D, int H, int W);
+int trb_affine_build_quads(const float *moving_dev, float *quads_dev, int n_pairs, int D, int H, int W, void *stream);
 int trb_affine_attach_pairs(void *workspace_dev, size_t workspace_bytes, int n_pairs, const float *pairs_dev, void *stream);
 
 /* Write start parameters from HOST memory into state[.][0..n_params) of n_pairs pairs (n_rows == 1: the same row for

@@ -862,8 +862,8 @@ def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
 
 def test_gather_variant_pair_volume_is_bit_identical(monkeypatch):
     """Large rotations (the reference's torch.rand(6) start): the gather variant reading the PAIR volume (x neighbours side by
-    side, zero columns around: 4 eight-byte gathers per voxel) performs the same arithmetic on the same values as the one
-    reading the moving volume itself (8 four-byte gathers with bounds predicates) — losses and theta must be bit-identical,
+    side, zero columns around: 4 eight-byte gathers per voxel) or the QUAD volume (x and y neighbours in one record: 2
+    sixteen-byte gathers) performs the same arithmetic on the same values as the one reading the moving volume itself (8 four-byte gathers with bounds predicates) — losses and theta must be bit-identical,
     including samples far outside the volume."""
     TF = _tf()
     from torchregister_b200.synth import make_pair
@@ -872,14 +872,15 @@ def test_gather_variant_pair_volume_is_bit_identical(monkeypatch):
     tgt = torch.cat([p[1] for p in pairs]).to(DEV)
     p0 = torch.tensor([[0.5, 0.77, 0.09, 0.13, 0.31, 0.63], [0.9, -0.7, 0.8, 0.6, -0.9, 0.3], [-1.4, 0.2, 1.1, 0.9, 0.9, -0.9]])
     out = {}
-    for flag in ("0", "1"):
+    for flag, name in (("0", "gather variant"), ("1", "gather (pair volume)"), ("2", "gather (quad volume)")):
         monkeypatch.setenv("TRB_PAIRS", flag)
         prob = TF.AffineProblem(mov, tgt, "rigid", p0, 6)
-        assert prob.flags & 1 and (prob.moving_pairs is not None) == (flag == "1")
+        assert prob.flags & 1 and (prob.moving_pairs is not None) == (flag != "0")
         prob.run(6, 1e-3, 0.5, 0.5)
-        assert "gather" in prob.lib.trb_affine_kernel_status().decode()
+        assert name in prob.lib.trb_affine_kernel_status().decode()
         out[flag] = (prob.losses.clone(), prob.final_theta.clone())
-    assert torch.equal(out["0"][0], out["1"][0]) and torch.equal(out["0"][1], out["1"][1])
+    for flag in ("1", "2"):
+        assert torch.equal(out["0"][0], out[flag][0]) and torch.equal(out["0"][1], out[flag][1]), flag
 
 
 def test_many_pairs_host_start_parameters_and_contribution_upload():

@@ -25,6 +25,8 @@ _SIGNATURES = {
     "trb_affine_init_state": (_i, [_i, _i, c_fp, _i, c_fp]),
     "trb_affine_pairs_bytes": (_sz, [_i, _i, _i, _i]),
     "trb_affine_build_pairs": (_i, [c_fp, c_fp, _i, _i, _i, _i, c_fp]),
+    "trb_affine_quads_bytes": (_sz, [_i, _i, _i, _i]),
+    "trb_affine_build_quads": (_i, [c_fp, c_fp, _i, _i, _i, _i, c_fp]),
     "trb_affine_attach_pairs": (_i, [c_fp, _sz, _i, c_fp, c_fp]),
     "trb_affine_set_params": (_i, [c_fp, _i, _i, c_fp, _i, c_fp]),
     "trb_affine_optim": (_i, [_i, _i, c_fp, c_fp, _ll, _i, _i, _i, _i, c_fp, c_fp, c_fp, c_fp, c_fp, _i,

@@ -382,6 +382,39 @@ __global__ void affine_attach_pairs_kernel(unsigned *tickets, unsigned long long
     if (threadIdx.x == 0) *reinterpret_cast<unsigned long long *>(tickets + kPairsWord) = addr;
 }
 
+__global__ void __launch_bounds__(256) affine_build_quads_kernel(const float *__restrict__ mov, float4 *__restrict__ Q, long long slices,
+                                                                 int H, int W)
+{
+    const int Wp = W + 3, Hp = H + 3;
+    const long long per = (long long)Hp * Wp;
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < slices * per; i += (long long)gridDim.x * 256) {
+        const long long sl = i / per;
+        const int r = (int)(i - sl * per), yr = r / Wp, xr = r - yr * Wp;
+        const int x = xr - 2, y = yr - 2;
+        const float *pl = mov + sl * H * W;
+        auto at = [&](int yy, int xx) { return ((unsigned)yy < (unsigned)H && (unsigned)xx < (unsigned)W) ? __ldg(pl + (long long)yy * W + xx) : 0.f; };
+        Q[i] = make_float4(at(y, x), at(y, x + 1), at(y + 1, x), at(y + 1, x + 1));
+    }
+}
+
+extern "C" size_t trb_affine_quads_bytes(int n_pairs, int D, int H, int W)
+{
+    if (n_pairs < 1 || D < 1 || H < 1 || W < 1) return 0;
+    return (size_t)n_pairs * D * (H + 3) * (W + 3) * sizeof(float4);
+}
+
+extern "C" int trb_affine_build_quads(const float *moving_dev, float *quads_dev, int n_pairs, int D, int H, int W, void *stream)
+{
+    int rc = validate_common(3, n_pairs, D, H, W);
+    if (rc) return rc;
+    if (!moving_dev || !quads_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    const long long slices = (long long)n_pairs * D;
+    long long nb = (slices * (H + 3) * (W + 3) + 255) / 256;
+    if (nb > 148 * 32) nb = 148 * 32;
+    affine_build_quads_kernel<<<(unsigned)nb, 256, 0, (cudaStream_t)stream>>>(moving_dev, reinterpret_cast<float4 *>(quads_dev), slices, H, W);
+    return check_cuda(cudaGetLastError(), "affine_build_quads");
+}
+
 extern "C" size_t trb_affine_pairs_bytes(int n_pairs, int D, int H, int W)
 {
     if (n_pairs < 1 || D < 1 || H < 1 || W < 1) return 0;
@@ -498,7 +531,7 @@ extern "C" int trb_affine_optim_ex(int ndim, int mode, const float *moving_dev, 
     p.state = state_dev; p.loss_log = loss_log_dev; p.log_stride = log_stride;
     p.w_mse = w_mse; p.w_ncc = w_ncc; p.lr = lr; p.mode = mode; p.optimiser = optimiser;
     p.beta1 = beta1; p.beta2 = beta2; p.adam_eps = adam_eps;
-    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? ((flags & TRB_FLAG_PAIR_VOLUME) ? 2 : 1) : 0;
+    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? ((flags & TRB_FLAG_QUAD_VOLUME) ? 3 : (flags & TRB_FLAG_PAIR_VOLUME) ? 2 : 1) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
         if (n_epochs <= 0) return TRB_OK;
@@ -568,7 +601,7 @@ int trb::affine_moments_impl(int ndim, const float *moving_dev, const float *tar
     p.s_begin = s_begin; p.s_end = s_end;
     p.state = const_cast<float *>(state_dev);
     p.moments_out = moments_dev;
-    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? ((flags & TRB_FLAG_PAIR_VOLUME) ? 2 : 1) : 0;
+    p.gather = (flags & TRB_FLAG_LARGE_ROTATION) ? ((flags & TRB_FLAG_QUAD_VOLUME) ? 3 : (flags & TRB_FLAG_PAIR_VOLUME) ? 2 : 1) : 0;
     cudaStream_t s = (cudaStream_t)stream;
     if (!g_force_direct && tma_path_eligible(ndim, p, n_pairs)) {
         // both TMA-tile kernels store the warped samples on request (whole volumes of single-channel pairs only)

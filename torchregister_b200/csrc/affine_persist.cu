@@ -408,7 +408,7 @@ __device__ __forceinline__ void acquire_theta(const PersistParams &pp, int e_rel
 // PAIRS (gather variant only): the moving volume is read through the pair volume whose address sits in the workspace
 // (trb_affine_attach_pairs; the caller says so with TRB_FLAG_PAIR_VOLUME) — a separate instantiation, so that the scalar
 // gather loop keeps its registers and its unrolling
-template <bool MSE_ONLY, bool ROT, bool STORE = false, bool PAIRS = false>
+template <bool MSE_ONLY, bool ROT, bool STORE = false, int PAIRS = 0>     // PAIRS: 0 scalar gathers, 1 pair volume, 2 quad volume
 __global__ void __launch_bounds__(kPersistThreads, 1)
 affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensorMap map_mov,
                         const __grid_constant__ CUtensorMap map_tgt)
@@ -669,8 +669,8 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
     float xv = 0.f, yv = 0.f, pxy[3] = {0.f, 0.f, 0.f}, sz[3] = {0.f, 0.f, 0.f};
     const float *__restrict__ mov = p.a.moving;
     // gather variant: the pair volume (trb_affine_attach_pairs), if the caller built one
-    const float2 *pairs_all = PAIRS ? reinterpret_cast<const float2 *>(__ldcg(pp.pairs_slot)) : nullptr;
-    const float2 *pairs = nullptr;
+    const char *pairs_all = PAIRS ? reinterpret_cast<const char *>(__ldcg(pp.pairs_slot)) : nullptr;
+    const char *pairs = nullptr;
     float *wcol0 = nullptr;              // STORE: this thread's column of the warped output
     Acc2 A;
     int kcol = 0;
@@ -700,7 +700,8 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                 sz[r] = pc.coef[r * 4 + 2] * inv_d2;
             }
             mov = p.a.moving + (size_t)pc.pair * p.a.pair_stride;
-            if constexpr (PAIRS) pairs = pairs_all + (size_t)(pp.pair0 + pc.pair) * ((size_t)D * H * (W + kPairPad));
+            if constexpr (PAIRS == 1) pairs = pairs_all + (size_t)(pp.pair0 + pc.pair) * ((size_t)D * H * (W + kPairPad)) * sizeof(float2);
+            if constexpr (PAIRS == 2) pairs = pairs_all + (size_t)(pp.pair0 + pc.pair) * ((size_t)D * (H + kPairPad) * (W + kPairPad)) * sizeof(float4);
             if constexpr (STORE) wcol0 = p.a.warped_out + (size_t)pc.pair * p.a.pair_stride + (size_t)y * W + x;
 #pragma unroll
             for (int i = 0; i < 12; ++i) A.a[i] = f2(0.f);
@@ -773,9 +774,12 @@ affine3d_persist_kernel(const PersistParams pp, const __grid_constant__ CUtensor
                 for (int zz = 0; zz < nz; ++zz) {
                     const float zf = m.zf0 + (float)zz;
                     float wv;
-                    if constexpr (PAIRS)
-                        wv = voxel_direct2p<MSE_ONLY>(pairs, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
-                                                      lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    if constexpr (PAIRS == 1)
+                        wv = voxel_direct2p<MSE_ONLY>(reinterpret_cast<const float2 *>(pairs), D, H, W, fmaf(sz[0], zf, pxy[0]),
+                                                      fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]), lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
+                    else if constexpr (PAIRS == 2)
+                        wv = voxel_direct2q<MSE_ONLY>(reinterpret_cast<const float4 *>(pairs), D, H, W, fmaf(sz[0], zf, pxy[0]),
+                                                      fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]), lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
                     else
                         wv = voxel_direct2<MSE_ONLY>(mov, D, H, W, fmaf(sz[0], zf, pxy[0]), fmaf(sz[1], zf, pxy[1]), fmaf(sz[2], zf, pxy[2]),
                                                      lds_f_dyn(tg + zz * (TX * TY * 4)), zf, A);
@@ -896,9 +900,10 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
     const bool mse_only = !moments_only && a.w_ncc == 0.f;
     const bool rot = a.gather != 0;
     const bool store = moments_only && !rot && a.warped_out != nullptr;
-    const bool pairs = rot && a.gather == 2;
-    auto kern = rot ? (pairs ? (mse_only ? affine3d_persist_kernel<true, true, false, true> : affine3d_persist_kernel<false, true, false, true>)
-                             : (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>))
+    const bool pairs = rot && a.gather >= 2;
+    auto kern = rot ? (a.gather == 3 ? (mse_only ? affine3d_persist_kernel<true, true, false, 2> : affine3d_persist_kernel<false, true, false, 2>)
+                       : a.gather == 2 ? (mse_only ? affine3d_persist_kernel<true, true, false, 1> : affine3d_persist_kernel<false, true, false, 1>)
+                                       : (mse_only ? affine3d_persist_kernel<true, true> : affine3d_persist_kernel<false, true>))
                     : (mse_only ? affine3d_persist_kernel<true, false>
                                 : (store ? affine3d_persist_kernel<false, false, true> : affine3d_persist_kernel<false, false>));
     const size_t kPersistSmem = rot ? Ring<true>::kSmem : Ring<false>::kSmem;
@@ -1000,7 +1005,7 @@ int launch_affine3d_persist(AffineParams a, int n_pairs, int epoch0, int n_epoch
         }
     }
     snprintf(g_persist_status, sizeof(g_persist_status), "launched: grid %d, %d SMs, %s variant, sub-batches of %d pair(s)",
-             (int)(sms < (long long)n_pairs * cpp * tiles_z ? sms : (long long)n_pairs * cpp * tiles_z), sms, rot ? (pairs ? "gather (pair volume)" : "gather") : "tma", sub);
+             (int)(sms < (long long)n_pairs * cpp * tiles_z ? sms : (long long)n_pairs * cpp * tiles_z), sms, rot ? (a.gather == 3 ? "gather (quad volume)" : pairs ? "gather (pair volume)" : "gather") : "tma", sub);
     return check_cuda(cudaGetLastError(), "affine3d_persist");
 }
 const char *persist_status() { return g_persist_status; }

@@ -424,6 +424,36 @@ __device__ __forceinline__ float voxel_direct2p(const float2 *__restrict__ P, in
     return val;
 }
 
+// and from the QUAD volume: Q[z][yr][xr] = (v[y][x], v[y][x+1], v[y+1][x], v[y+1][x+1]) at (x, y) = (xr - 2, yr - 2), H + 3 rows
+// of W + 3 records, zeros outside: ONE 16-byte load per z plane of the cell brings its four corners and the zero padding in x
+// and y — 2 gathers per voxel
+template <bool MSE_ONLY>
+__device__ __forceinline__ float voxel_direct2q(const float4 *__restrict__ Q, int D, int H, int W, float ix, float iy, float iz,
+                                                float t, float zf, Acc2 &A)
+{
+    ix = fminf(fmaxf(ix, -2.f), (float)W + 0.5f);       // x0 in [-2, W], y0 in [-2, H]: the border records are zero
+    iy = fminf(fmaxf(iy, -2.f), (float)H + 0.5f);
+    iz = fminf(fmaxf(iz, -4.f), (float)D + 4.f);
+    const float fx = __fadd_rd(ix, kMagic) - kMagic, fy = __fadd_rd(iy, kMagic) - kMagic, fz = __fadd_rd(iz, kMagic) - kMagic;
+    const float tx = ix - fx, ty = iy - fy, tz = iz - fz;
+    const int x0 = (int)fx, y0 = (int)fy, z0 = (int)fz;
+    const bool vz0 = (unsigned)z0 < (unsigned)D, vz1 = (unsigned)(z0 + 1) < (unsigned)D;
+    const long long Wp = W + kPairPad, HWp = (long long)(H + kPairPad) * Wp, o = (long long)z0 * HWp + (long long)(y0 + 2) * Wp + (x0 + 2);
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float4 q0 = vz0 ? __ldg(Q + o) : zero, q1 = vz1 ? __ldg(Q + o + HWp) : zero;      // (c00, c01, c10, c11) of plane z0 / z0 + 1
+    const float d00 = q0.y - q0.x, d01 = q0.w - q0.z, d10 = q1.y - q1.x, d11 = q1.w - q1.z;
+    const float v00 = fmaf(tx, d00, q0.x), v01 = fmaf(tx, d01, q0.z), v10 = fmaf(tx, d10, q1.x), v11 = fmaf(tx, d11, q1.z);
+    const float e0 = v01 - v00, e1 = v11 - v10;
+    const float w0 = fmaf(ty, e0, v00), w1 = fmaf(ty, e1, v10);
+    const float G2 = w1 - w0;
+    const float val = fmaf(tz, G2, w0);
+    const float G1 = fmaf(tz, e1 - e0, e0);
+    const float dx0 = fmaf(ty, d01 - d00, d00), dx1 = fmaf(ty, d11 - d10, d10);
+    const float G0 = fmaf(tz, dx1 - dx0, dx0);
+    moments_accumulate<MSE_ONLY>(t, zf, val, G0, G1, G2, A);
+    return val;
+}
+
 // fallback for tiles whose source footprint does not fit the TMA box: one voxel, global gathers
 template <bool MSE_ONLY>
 __device__ __forceinline__ float voxel_direct(const float *__restrict__ mov, int D, int H, int W, float ix, float iy, float iz,

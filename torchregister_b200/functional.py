@@ -150,18 +150,22 @@ class AffineProblem:
         # gather variant: a pair volume (x neighbours side by side) halves the number of gathers; it costs 2x the moving
         # volumes in memory and one pass to build
         self.moving_pairs = None
-        nbytes = int(self.lib.trb_affine_pairs_bytes(self.n_pairs, self.D, self.H, self.W)) if self.ndim == 3 else 0
         import os
-        force = os.environ.get("TRB_PAIRS")
-        use_pairs = nbytes <= PAIR_VOLUME_MAX_BYTES if force is None else force == "1"
-        if self.flags & 1 and self.pair_stride == self.D * self.H * self.W and use_pairs:
-            self.moving_pairs = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
-            with torch.cuda.device(self.device):
-                check(self.lib.trb_affine_build_pairs(self.moving.data_ptr(), self.moving_pairs.data_ptr(), self.n_pairs, self.D,
-                                                      self.H, self.W, _stream(self.device)), "affine_build_pairs")
-                check(self.lib.trb_affine_attach_pairs(self.workspace.data_ptr(), self.workspace.numel(), self.n_pairs,
-                                                       self.moving_pairs.data_ptr(), _stream(self.device)), "affine_attach_pairs")
-            self.flags |= 2               # TRB_FLAG_PAIR_VOLUME
+        force = os.environ.get("TRB_PAIRS")           # test / A-B hook: "0" scalar gathers, "1" pair volume, "2" quad volume
+        if self.flags & 1 and self.pair_stride == self.D * self.H * self.W and force != "0":
+            qbytes = int(self.lib.trb_affine_quads_bytes(self.n_pairs, self.D, self.H, self.W))
+            pbytes = int(self.lib.trb_affine_pairs_bytes(self.n_pairs, self.D, self.H, self.W))
+            quad = pbytes > PAIR_VOLUME_L2_BYTES if force is None else force == "2"
+            nbytes = qbytes if quad else pbytes
+            if nbytes <= PAIR_VOLUME_MAX_BYTES:
+                self.moving_pairs = torch.empty(nbytes // 4, dtype=torch.float32, device=self.device)
+                build = self.lib.trb_affine_build_quads if quad else self.lib.trb_affine_build_pairs
+                with torch.cuda.device(self.device):
+                    check(build(self.moving.data_ptr(), self.moving_pairs.data_ptr(), self.n_pairs, self.D, self.H, self.W,
+                                _stream(self.device)), "affine_build_pairs")
+                    check(self.lib.trb_affine_attach_pairs(self.workspace.data_ptr(), self.workspace.numel(), self.n_pairs,
+                                                           self.moving_pairs.data_ptr(), _stream(self.device)), "affine_attach_pairs")
+                self.flags |= 4 if quad else 2          # TRB_FLAG_QUAD_VOLUME / TRB_FLAG_PAIR_VOLUME
 
     def _start_needs_gather(self, p0: torch.Tensor) -> bool:
         import ctypes as C
@@ -619,6 +623,10 @@ THIN_CONV_MAX_CHANNELS = 4
 # the pair volume of the gather variant costs 2x the moving volumes in memory (measured gain: one 192x192x160 pair 55 -> 36 us,
 # 256^3 144 -> 117, a batch of 8 389 -> 287); beyond this size the scalar gathers are used
 PAIR_VOLUME_MAX_BYTES = 16 << 30
+# Measured (same box, us/epoch, scalar / pair / quad): one 192x192x160 pair 56.6 / 37.0 / 41.8; 256^3 143 / 146 / 115; 8 pairs
+# 388 / 358 / 286.  While the pair volume sits in L2 the four 8-byte gathers win; once it streams from HBM the quad volume
+# (x and y neighbours in one 16-byte record, 2 gathers per voxel, 4x the memory) touches half as many sectors per voxel
+PAIR_VOLUME_L2_BYTES = 64 << 20
 
 
 def thin_conv3d_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
