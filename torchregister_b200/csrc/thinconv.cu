@@ -414,15 +414,19 @@ __global__ void __launch_bounds__(256) pointconv_wgrad_kernel(const float *__res
     }
 }
 
+// one warp per sum: lanes stride over the block partials (fixed order), then a shuffle tree
 __global__ void pointconv_wgrad_final_kernel(const double *__restrict__ part, int blocks, int CI, int CO, float *__restrict__ gw,
                                              float *__restrict__ gb)
 {
-    const int NA = CI * CO + CO, k = threadIdx.x;
+    const int NA = CI * CO + CO, k = blockIdx.x, lane = threadIdx.x;
     if (k >= NA) return;
     double s = 0.0;
-    for (int b = 0; b < blocks; ++b) s += part[(size_t)b * NA + k];
-    if (k < CI * CO) gw[k] = (float)s;
-    else if (gb) gb[k - CI * CO] = (float)s;
+    for (int b = lane; b < blocks; b += 32) s += part[(size_t)b * NA + k];
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (k < CI * CO) gw[k] = (float)s;
+        else if (gb) gb[k - CI * CO] = (float)s;
+    }
 }
 
 constexpr int kPcBlocks = 148 * 4;
@@ -483,7 +487,7 @@ extern "C" int trb_pointconv_backward(const float *x_dev, const float *w_dev, co
         }
         double *part = (double *)workspace_dev;
         TC_DISPATCH(pointconv_wgrad_kernel, <<<kPcBlocks, 256, 0, s>>>(x_dev, gy_dev, D, H, W, OD, OH, OW, stride, part))
-        pointconv_wgrad_final_kernel<<<1, 32, 0, s>>>(part, kPcBlocks, CI, CO, gw_dev, gb_dev);
+        pointconv_wgrad_final_kernel<<<CI * CO + CO, 32, 0, s>>>(part, kPcBlocks, CI, CO, gw_dev, gb_dev);
     }
     return check_cuda(cudaGetLastError(), "pointconv_backward");
 }
