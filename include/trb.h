@@ -417,6 +417,15 @@ int trb_pointconv_backward(const float *x_dev, const float *w_dev, const float *
                            float *gb_dev, int CI, int CO, int D, int H, int W, int stride, void *workspace_dev,
                            size_t workspace_bytes, void *stream);
 
+/* 2x2x2 stride-2 transposed convolutions with <= 4 channels each way (the U-Net's last up-sampling, utils.py:409-520):
+ * y[co][2z+a][2y+b][2x+c] = b[co] + sum_ci w[ci][co][a][b][c] x[ci][z][y][x]; x [CI][D][H][W] -> y [CO][2D][2H][2W], w in
+ * nn.ConvTranspose3d's layout [CI][CO][2][2][2]; one sample per call; NULL gradients are skipped. */
+size_t trb_upconv2_workspace_bytes(int CI, int CO);
+int trb_upconv2_forward(const float *x_dev, const float *w_dev, const float *b_dev, float *y_dev, int CI, int CO, int D, int H,
+                        int W, void *stream);
+int trb_upconv2_backward(const float *x_dev, const float *w_dev, const float *gy_dev, float *gx_dev, float *gw_dev, float *gb_dev,
+                         int CI, int CO, int D, int H, int W, void *workspace_dev, size_t workspace_bytes, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

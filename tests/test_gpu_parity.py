@@ -815,6 +815,29 @@ def test_point_conv3d_kernels_vs_torch(ci, co, shape, stride, bias):
         assert (a.double() - b_).abs().max().item() <= 2e-5 * max(1.0, b_.abs().max().item())
 
 
+@pytest.mark.parametrize("ci,co,shape,bias", [(4, 2, (10, 12, 33), True), (2, 2, (5, 6, 7), False), (4, 4, (3, 4, 5), True), (1, 3, (2, 2, 2), True)])
+def test_up_conv3d_kernels_vs_torch(ci, co, shape, bias):
+    """The U-Net's thin 2x2x2 stride-2 transposed convolution on csrc/thinconv.cu against F.conv_transpose3d in float64: output
+    and all gradients."""
+    import torch.nn.functional as F
+    from torchregister_b200.utils import ConvTranspose3dB200
+    torch.manual_seed(17)
+    conv = ConvTranspose3dB200(ci, co, kernel_size=2, stride=2, bias=bias).to(DEV)
+    x = torch.randn(1, ci, *shape, device=DEV, requires_grad=True)
+    y = conv(x)
+    g = torch.randn_like(y)
+    grads = torch.autograd.grad(y, [x, conv.weight] + ([conv.bias] if bias else []), g)
+    x64 = x.detach().double().requires_grad_(True)
+    w64 = conv.weight.detach().double().requires_grad_(True)
+    b64 = conv.bias.detach().double().requires_grad_(True) if bias else None
+    y64 = F.conv_transpose3d(x64, w64, b64, stride=2)
+    ref = torch.autograd.grad(y64, [x64, w64] + ([b64] if bias else []), g.double())
+    assert tuple(y.shape) == tuple(y64.shape)
+    assert (y.double() - y64).abs().max().item() <= 1e-5 * max(1.0, y64.abs().max().item())
+    for a, b_ in zip(grads, ref):
+        assert (a.double() - b_).abs().max().item() <= 2e-5 * max(1.0, b_.abs().max().item())
+
+
 def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
     """Attention_UNet with the InstanceNorm kernels (ReLU folded in) and the thin-convolution kernels against the same network
     — same parameter names, same weights — built from stock nn.Conv3d + nn.ReLU + nn.InstanceNorm3d (cuDNN, TF32 off): flow
@@ -837,6 +860,8 @@ def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
         for name, child in list(m.named_children()):
             if isinstance(child, U.Conv3dB200):
                 child.__class__ = nn.Conv3d                  # same attributes: cuDNN instead of csrc/thinconv.cu
+            elif isinstance(child, U.ConvTranspose3dB200):
+                child.__class__ = nn.ConvTranspose3d
             elif isinstance(child, U._InstanceNormB200):
                 new = (nn.InstanceNorm3d if isinstance(child, nn.InstanceNorm3d) else nn.InstanceNorm2d)(child.num_features)
                 relu = child.fuse_relu

@@ -74,6 +74,9 @@ _SIGNATURES = {
     "trb_pointconv_workspace_bytes": (_sz, [_i, _i]),
     "trb_pointconv_forward": (_i, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, _i, c_fp]),
     "trb_pointconv_backward": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, _i, c_fp, _sz, c_fp]),
+    "trb_upconv2_workspace_bytes": (_sz, [_i, _i]),
+    "trb_upconv2_forward": (_i, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp]),
+    "trb_upconv2_backward": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, _sz, c_fp]),
     "trb_instnorm_workspace_bytes": (_sz, [_i, _ll]),
     "trb_instnorm_forward": (_i, [c_fp, c_fp, _i, _ll, _f, _i, c_fp, c_fp, _sz, c_fp]),
     "trb_instnorm_backward": (_i, [c_fp, c_fp, c_fp, _i, _ll, _i, c_fp, c_fp, c_fp, _sz, c_fp]),

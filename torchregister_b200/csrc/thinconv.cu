@@ -491,3 +491,205 @@ extern "C" int trb_pointconv_backward(const float *x_dev, const float *w_dev, co
     }
     return check_cuda(cudaGetLastError(), "pointconv_backward");
 }
+
+// ---- 2x2x2 stride-2 transposed convolutions with few channels (the last up-sampling of the U-Net: utils.py:409-520) ---------
+// y[co][2z+a][2y+b][2x+c] = bias[co] + sum_ci w[ci][co][a][b][c] * x[ci][z][y][x]: every output voxel has ONE source voxel, so
+// this is a streaming kernel (C_in loads, 8 C_out stores per input voxel); cuDNN spends 1.5 ms each way on [4,118^3] -> [2,236^3].
+namespace trb {
+
+__constant__ float c_up_w[kTcMaxC * kTcMaxC * 8];
+
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) upconv2_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int D, int H, int W, int has_bias)
+{
+    const size_t vol = (size_t)D * H * W, ovol = vol * 8;
+    const int OW = 2 * W, OH = 2 * H;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
+        const int ix = (int)(i % W);
+        const size_t r = i / W;
+        const int iy = (int)(r % H), iz = (int)(r / H);
+        float v[CI];
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) v[ci] = __ldg(x + ci * vol + i);
+#pragma unroll
+        for (int co = 0; co < CO; ++co) {
+            const float b = has_bias ? c_tc_b[co] : 0.f;
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) {
+                    float o0 = b, o1 = b;
+#pragma unroll
+                    for (int ci = 0; ci < CI; ++ci) {
+                        o0 = fmaf(c_up_w[(ci * CO + co) * 8 + a * 4 + bb * 2], v[ci], o0);
+                        o1 = fmaf(c_up_w[(ci * CO + co) * 8 + a * 4 + bb * 2 + 1], v[ci], o1);
+                    }
+                    float2 *dst = reinterpret_cast<float2 *>(y + co * ovol + ((size_t)(2 * iz + a) * OH + (2 * iy + bb)) * OW + 2 * ix);
+                    __stcs(dst, make_float2(o0, o1));
+                }
+        }
+    }
+}
+
+// gx[ci][v] = sum_{co,a,b,c} w[ci][co][a][b][c] * gy[co][2v + (a,b,c)]
+template <int CI, int CO>
+__global__ void __launch_bounds__(256) upconv2_dgrad_kernel(const float *__restrict__ gy, float *__restrict__ gx, int D, int H, int W)
+{
+    const size_t vol = (size_t)D * H * W, ovol = vol * 8;
+    const int OW = 2 * W, OH = 2 * H;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
+        const int ix = (int)(i % W);
+        const size_t r = i / W;
+        const int iy = (int)(r % H), iz = (int)(r / H);
+        float acc[CI];
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) acc[ci] = 0.f;
+#pragma unroll
+        for (int co = 0; co < CO; ++co)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) {
+                    const float2 g = __ldg(reinterpret_cast<const float2 *>(gy + co * ovol + ((size_t)(2 * iz + a) * OH + (2 * iy + bb)) * OW + 2 * ix));
+#pragma unroll
+                    for (int ci = 0; ci < CI; ++ci) {
+                        acc[ci] = fmaf(c_up_w[(ci * CO + co) * 8 + a * 4 + bb * 2], g.x, acc[ci]);
+                        acc[ci] = fmaf(c_up_w[(ci * CO + co) * 8 + a * 4 + bb * 2 + 1], g.y, acc[ci]);
+                    }
+                }
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) gx[ci * vol + i] = acc[ci];
+    }
+}
+
+// gw[ci][co][a][b][c] = sum_v x[ci][v] * gy[co][2v + (a,b,c)];  gb[co] = sum gy[co].  grid (blocks, CI): block partials in fp64
+template <int CO>
+__global__ void __launch_bounds__(256) upconv2_wgrad_kernel(const float *__restrict__ x, const float *__restrict__ gy, int D, int H, int W,
+                                                             double *__restrict__ part)
+{
+    constexpr int NA = 8 * CO + CO;
+    __shared__ double sh[8][NA];
+    const int ci = blockIdx.y;
+    const size_t vol = (size_t)D * H * W, ovol = vol * 8;
+    const int OW = 2 * W, OH = 2 * H;
+    float acc[NA];
+    double A[NA];
+#pragma unroll
+    for (int k = 0; k < NA; ++k) { acc[k] = 0.f; A[k] = 0.0; }
+    int since = 0;
+    for (size_t i = (size_t)blockIdx.x * 256 + threadIdx.x; i < vol; i += (size_t)gridDim.x * 256) {
+        const int ix = (int)(i % W);
+        const size_t r = i / W;
+        const int iy = (int)(r % H), iz = (int)(r / H);
+        const float xv = __ldg(x + ci * vol + i);
+#pragma unroll
+        for (int co = 0; co < CO; ++co)
+#pragma unroll
+            for (int a = 0; a < 2; ++a)
+#pragma unroll
+                for (int bb = 0; bb < 2; ++bb) {
+                    const float2 g = __ldg(reinterpret_cast<const float2 *>(gy + co * ovol + ((size_t)(2 * iz + a) * OH + (2 * iy + bb)) * OW + 2 * ix));
+                    acc[co * 8 + a * 4 + bb * 2] = fmaf(xv, g.x, acc[co * 8 + a * 4 + bb * 2]);
+                    acc[co * 8 + a * 4 + bb * 2 + 1] = fmaf(xv, g.y, acc[co * 8 + a * 4 + bb * 2 + 1]);
+                    acc[8 * CO + co] += g.x + g.y;
+                }
+        if (++since == 32) {
+#pragma unroll
+            for (int k = 0; k < NA; ++k) { A[k] += (double)acc[k]; acc[k] = 0.f; }
+            since = 0;
+        }
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int k = 0; k < NA; ++k) {
+        const double s = warp_sum(A[k] + (double)acc[k]);
+        if (lane == 0) sh[warp][k] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NA) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) s += sh[w][threadIdx.x];
+        part[((size_t)ci * gridDim.x + blockIdx.x) * NA + threadIdx.x] = s;
+    }
+}
+
+// one warp per entry: gw[ci][co][8] (k < 8*CO of group ci) and gb[co] (from group 0)
+__global__ void upconv2_wgrad_final_kernel(const double *__restrict__ part, int blocks, int CI, int CO, float *__restrict__ gw, float *__restrict__ gb)
+{
+    const int NA = 8 * CO + CO, e = blockIdx.x, lane = threadIdx.x;
+    int ci, k;
+    if (e < CI * CO * 8) { ci = e / (CO * 8); k = e - ci * CO * 8; }
+    else { ci = 0; k = 8 * CO + (e - CI * CO * 8); }
+    double s = 0.0;
+    for (int b = lane; b < blocks; b += 32) s += part[((size_t)ci * blocks + b) * NA + k];
+    s = warp_sum(s);
+    if (lane == 0) {
+        if (e < CI * CO * 8) gw[e] = (float)s;          // [ci][co][a][b][c] is exactly e
+        else if (gb) gb[e - CI * CO * 8] = (float)s;
+    }
+}
+
+constexpr int kUpBlocks = 148 * 2;
+
+static int up_upload(const float *w, const float *b, int CI, int CO, cudaStream_t s)
+{
+    cudaError_t e = cudaMemcpyToSymbolAsync(c_up_w, w, (size_t)CI * CO * 8 * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    if (e == cudaSuccess && b) e = cudaMemcpyToSymbolAsync(c_tc_b, b, (size_t)CO * sizeof(float), 0, cudaMemcpyDeviceToDevice, s);
+    return e == cudaSuccess ? TRB_OK : check_cuda(e, "cudaMemcpyToSymbolAsync(transposed conv weights)");
+}
+
+}  // namespace trb
+
+extern "C" size_t trb_upconv2_workspace_bytes(int CI, int CO)
+{
+    if (CI < 1 || CI > kTcMaxC || CO < 1 || CO > kTcMaxC) return 0;
+    return (size_t)CI * kUpBlocks * (8 * CO + CO) * sizeof(double);
+}
+
+extern "C" int trb_upconv2_forward(const float *x_dev, const float *w_dev, const float *b_dev, float *y_dev, int CI, int CO, int D, int H,
+                                   int W, void *stream)
+{
+    int rc = pc_validate(CI, CO, D, H, W, 1);
+    if (rc) return rc;
+    if (!x_dev || !w_dev || !y_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    rc = up_upload(w_dev, b_dev, CI, CO, s);
+    if (rc) return rc;
+    size_t nb = ((size_t)D * H * W + 255) / 256;
+    if (nb > 148 * 16) nb = 148 * 16;
+    TC_DISPATCH(upconv2_fwd_kernel, <<<(unsigned)nb, 256, 0, s>>>(x_dev, y_dev, D, H, W, b_dev ? 1 : 0))
+    return check_cuda(cudaGetLastError(), "upconv2_forward");
+}
+
+extern "C" int trb_upconv2_backward(const float *x_dev, const float *w_dev, const float *gy_dev, float *gx_dev, float *gw_dev, float *gb_dev,
+                                    int CI, int CO, int D, int H, int W, void *workspace_dev, size_t workspace_bytes, void *stream)
+{
+    int rc = pc_validate(CI, CO, D, H, W, 1);
+    if (rc) return rc;
+    if (!x_dev || !w_dev || !gy_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    cudaStream_t s = (cudaStream_t)stream;
+    if (gx_dev) {
+        rc = up_upload(w_dev, nullptr, CI, CO, s);
+        if (rc) return rc;
+        size_t nb = ((size_t)D * H * W + 255) / 256;
+        if (nb > 148 * 16) nb = 148 * 16;
+        TC_DISPATCH(upconv2_dgrad_kernel, <<<(unsigned)nb, 256, 0, s>>>(gy_dev, gx_dev, D, H, W))
+    }
+    if (gw_dev) {
+        if (!workspace_dev || workspace_bytes < trb_upconv2_workspace_bytes(CI, CO)) {
+            set_error("workspace too small: need %zu bytes", trb_upconv2_workspace_bytes(CI, CO));
+            return TRB_ERR_WORKSPACE;
+        }
+        double *part = (double *)workspace_dev;
+        const dim3 grid(kUpBlocks, CI);
+        switch (CO) {
+        case 1: upconv2_wgrad_kernel<1><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        case 2: upconv2_wgrad_kernel<2><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        case 3: upconv2_wgrad_kernel<3><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        default: upconv2_wgrad_kernel<4><<<grid, 256, 0, s>>>(x_dev, gy_dev, D, H, W, part); break;
+        }
+        upconv2_wgrad_final_kernel<<<CI * CO * 8 + CO, 32, 0, s>>>(part, kUpBlocks, CI, CO, gw_dev, gb_dev);
+    }
+    return check_cuda(cudaGetLastError(), "upconv2_backward");
+}

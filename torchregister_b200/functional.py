@@ -704,6 +704,37 @@ def point_conv3d_backward(x: torch.Tensor, weight: torch.Tensor, gy: torch.Tenso
     return gx, (gw if need_gw else None), (gb if need_gb else None)
 
 
+def up_conv3d_forward(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor]) -> torch.Tensor:
+    """conv_transpose3d(x, weight, bias, stride=2) for a 2x2x2 kernel, <= 4 channels each way, x [1,CI,D,H,W]."""
+    require_cuda(x, "x")
+    x, weight = x.contiguous(), weight.contiguous()
+    _, ci, D, H, W = (int(v) for v in x.shape)
+    co = int(weight.shape[1])
+    y = torch.empty(1, co, 2 * D, 2 * H, 2 * W, dtype=torch.float32, device=x.device)
+    b = bias.contiguous() if bias is not None else None
+    with torch.cuda.device(x.device):
+        check(_lib.load().trb_upconv2_forward(x.data_ptr(), weight.data_ptr(), _ptr(b), y.data_ptr(), ci, co, D, H, W,
+                                              _stream(x.device)), "upconv2_forward")
+    return y
+
+
+def up_conv3d_backward(x: torch.Tensor, weight: torch.Tensor, gy: torch.Tensor, need_gx: bool, need_gw: bool, need_gb: bool):
+    require_cuda(gy, "gy")
+    x, weight, gy = x.contiguous(), weight.contiguous(), gy.contiguous()
+    _, ci, D, H, W = (int(v) for v in x.shape)
+    co = int(weight.shape[1])
+    lib = _lib.load()
+    want_w = need_gw or need_gb
+    gx = torch.empty_like(x) if need_gx else None
+    gw = torch.empty_like(weight) if want_w else None
+    gb = torch.empty(co, dtype=torch.float32, device=x.device) if want_w else None
+    ws = torch.empty(max(int(lib.trb_upconv2_workspace_bytes(ci, co)), 8), dtype=torch.uint8, device=x.device) if want_w else None
+    with torch.cuda.device(x.device):
+        check(lib.trb_upconv2_backward(x.data_ptr(), weight.data_ptr(), gy.data_ptr(), _ptr(gx), _ptr(gw), _ptr(gb), ci, co, D, H, W,
+                                       _ptr(ws), ws.numel() if ws is not None else 0, _stream(x.device)), "upconv2_backward")
+    return gx, (gw if need_gw else None), (gb if need_gb else None)
+
+
 class DirectFlowProblem:
     """Per-voxel flow field optimised with SGD or Adam on
     loss = w_mse*MSE + w_ncc*100*(1-NCC) + smooth * mean_axes(mean(forward_diff(flow)^2)).

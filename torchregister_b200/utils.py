@@ -437,6 +437,42 @@ class Conv3dB200(nn.Conv3d):
         return super().forward(x)
 
 
+class _UpConv3dFn(torch.autograd.Function):
+    """conv_transpose3d (kernel 2, stride 2) with <= 4 channels each way on csrc/thinconv.cu."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        from . import functional as TF
+        ctx.save_for_backward(x, weight)
+        ctx.has_bias = bias is not None
+        return TF.up_conv3d_forward(x, weight, bias)
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, gy):
+        from . import functional as TF
+        x, weight = ctx.saved_tensors
+        return TF.up_conv3d_backward(x, weight, gy, ctx.needs_input_grad[0], ctx.needs_input_grad[1],
+                                     ctx.has_bias and ctx.needs_input_grad[2])
+
+
+class ConvTranspose3dB200(nn.ConvTranspose3d):
+    """nn.ConvTranspose3d whose thin 2x2x2 stride-2 layers (<= 4 channels each way: the U-Net's last up-sampling at n = 32) run
+    as a streaming kernel of csrc/thinconv.cu — every output voxel has one source voxel.  Same parameters, same state_dict."""
+
+    def _thin(self, x):
+        from .functional import THIN_CONV_MAX_CHANNELS as M
+        return (x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and x.shape[0] == 1 and self.weight.dtype == torch.float32
+                and tuple(self.kernel_size) == (2, 2, 2) and tuple(self.stride) == (2, 2, 2) and tuple(self.dilation) == (1, 1, 1)
+                and tuple(self.padding) == (0, 0, 0) and tuple(self.output_padding) == (0, 0, 0) and self.groups == 1
+                and self.in_channels <= M and self.out_channels <= M)
+
+    def forward(self, x, output_size=None):
+        if output_size is None and self._thin(x):
+            return _UpConv3dFn.apply(x, self.weight, self.bias)
+        return super().forward(x, output_size)
+
+
 def _relu_inorm(inorm, channels):
     """The reference's `nn.ReLU(), nn.InstanceNorm(co)` pair with the ReLU folded into the norm; an Identity keeps the
     positions (and therefore the parameter names of the convolutions) of the reference's nn.Sequential."""
@@ -446,7 +482,7 @@ def _relu_inorm(inorm, channels):
 
 
 def _nd(dims):
-    return (Conv3dB200, nn.ConvTranspose3d, InstanceNorm3dB200, nn.MaxPool3d) if dims == 3 else \
+    return (Conv3dB200, ConvTranspose3dB200, InstanceNorm3dB200, nn.MaxPool3d) if dims == 3 else \
            (nn.Conv2d, nn.ConvTranspose2d, InstanceNorm2dB200, nn.MaxPool2d)
 
 
