@@ -10,8 +10,8 @@
 // profiles/r02_unet_flow_profile.txt).  As a gather/stencil this is 27 * C_in loads and 27 * C_in * C_out FMAs per voxel
 // — L1-resident loads, weights as constant-bank operands (copied device -> constant memory on the stream): no layout
 // change, no im2col.
-//   forward: one thread per output voxel, all C_out at once.
-//   dgrad  : one thread per input voxel, all C_in at once (dy read with bounds predicates = the zero extension).
+//   forward: one thread per (x, y) and block of 4 output slices, all C_out at once (an input plane serves three slices).
+//   dgrad  : the same on the input side, all C_in at once (dy read with bounds predicates = the zero extension).
 //   wgrad  : groups (c_in, dz): a warp walks rows of the output, 9 * C_out (+ C_out for the bias) running sums per
 //            thread, block partials in fp64, fixed-order final sum (deterministic).
 #include "common.cuh"
@@ -24,6 +24,9 @@ __constant__ float c_tc_w[kTcMaxC8 * kTcMaxC8 * 27];
 __constant__ float c_tc_b[kTcMaxC8];
 
 // y[co][z][y][x] = b[co] + sum_{ci,dz,dy,dx} w[co][ci][dz][dy][dx] * x[ci][z+dz][y+dy][x+dx]
+// A thread owns kZB consecutive output slices of one (x, y): every input plane it loads serves up to three of them, so a voxel
+// costs 13.5 C_in loads instead of 27 C_in, with kZB * C_out independent accumulator chains.
+constexpr int kZB = 4;
 template <int CI, int CO>
 __global__ void __launch_bounds__(256) thinconv_fwd_kernel(const float *__restrict__ x, float *__restrict__ y, int D, int H, int W,
                                                             int has_bias)
@@ -31,72 +34,96 @@ __global__ void __launch_bounds__(256) thinconv_fwd_kernel(const float *__restri
     const int OD = D - 2, OH = H - 2, OW = W - 2;
     const int ox = blockIdx.x * 128 + (threadIdx.x & 127);
     const int oy = blockIdx.y * 2 + (threadIdx.x >> 7);
-    const int oz = blockIdx.z;
+    const int oz0 = blockIdx.z * kZB;
     if (ox >= OW || oy >= OH) return;
     const size_t HW = (size_t)H * W, vol = HW * D, ovol = (size_t)OD * OH * OW;
-    float acc[CO];
+    float acc[kZB][CO];
 #pragma unroll
-    for (int co = 0; co < CO; ++co) acc[co] = has_bias ? c_tc_b[co] : 0.f;
+    for (int zo = 0; zo < kZB; ++zo)
+#pragma unroll
+        for (int co = 0; co < CO; ++co) acc[zo][co] = has_bias ? c_tc_b[co] : 0.f;
 #pragma unroll
     for (int ci = 0; ci < CI; ++ci)
 #pragma unroll
-        for (int dz = 0; dz < 3; ++dz)
+        for (int p = 0; p < kZB + 2; ++p) {
+            if (oz0 + p >= D) break;                       // uniform over the block
 #pragma unroll
             for (int dy = 0; dy < 3; ++dy) {
-                const float *row = x + ci * vol + (size_t)(oz + dz) * HW + (size_t)(oy + dy) * W + ox;
+                const float *row = x + ci * vol + (size_t)(oz0 + p) * HW + (size_t)(oy + dy) * W + ox;
                 const float v0 = __ldg(row), v1 = __ldg(row + 1), v2 = __ldg(row + 2);
 #pragma unroll
-                for (int co = 0; co < CO; ++co) {
-                    const int wi = ((co * CI + ci) * 3 + dz) * 9 + dy * 3;
-                    acc[co] = fmaf(c_tc_w[wi], v0, acc[co]);
-                    acc[co] = fmaf(c_tc_w[wi + 1], v1, acc[co]);
-                    acc[co] = fmaf(c_tc_w[wi + 2], v2, acc[co]);
+                for (int dz = 0; dz < 3; ++dz) {
+                    const int zo = p - dz;                 // compile-time after unrolling
+                    if (zo < 0 || zo >= kZB) continue;
+#pragma unroll
+                    for (int co = 0; co < CO; ++co) {
+                        const int wi = ((co * CI + ci) * 3 + dz) * 9 + dy * 3;
+                        acc[zo][co] = fmaf(c_tc_w[wi], v0, acc[zo][co]);
+                        acc[zo][co] = fmaf(c_tc_w[wi + 1], v1, acc[zo][co]);
+                        acc[zo][co] = fmaf(c_tc_w[wi + 2], v2, acc[zo][co]);
+                    }
                 }
             }
-    const size_t o = ((size_t)oz * OH + oy) * OW + ox;
+        }
 #pragma unroll
-    for (int co = 0; co < CO; ++co) y[co * ovol + o] = acc[co];
+    for (int zo = 0; zo < kZB; ++zo) {
+        if (oz0 + zo >= OD) break;
+        const size_t o = ((size_t)(oz0 + zo) * OH + oy) * OW + ox;
+#pragma unroll
+        for (int co = 0; co < CO; ++co) y[co * ovol + o] = acc[zo][co];
+    }
 }
 
 // dx[ci][z][y][x] = sum_{co,dz,dy,dx} w[co][ci][dz][dy][dx] * dy[co][z-dz][y-dy][x-dx]   (dy = 0 outside its extent)
+// The same z blocking on the input side: gradient plane q serves the input slices q, q + 1, q + 2.
 template <int CI, int CO>
 __global__ void __launch_bounds__(256) thinconv_dgrad_kernel(const float *__restrict__ gy, float *__restrict__ gx, int D, int H, int W)
 {
     const int OD = D - 2, OH = H - 2, OW = W - 2;
     const int ix = blockIdx.x * 128 + (threadIdx.x & 127);
     const int iy = blockIdx.y * 2 + (threadIdx.x >> 7);
-    const int iz = blockIdx.z;
+    const int iz0 = blockIdx.z * kZB;
     if (ix >= W || iy >= H) return;
     const size_t HW = (size_t)H * W, vol = HW * D, OHW = (size_t)OH * OW, ovol = OHW * OD;
-    float acc[CI];
+    float acc[kZB][CI];
 #pragma unroll
-    for (int ci = 0; ci < CI; ++ci) acc[ci] = 0.f;
+    for (int zi = 0; zi < kZB; ++zi)
 #pragma unroll
-    for (int dz = 0; dz < 3; ++dz) {
-        const int z = iz - dz;
-        if ((unsigned)z >= (unsigned)OD) continue;
+        for (int ci = 0; ci < CI; ++ci) acc[zi][ci] = 0.f;
+    const bool p0 = (unsigned)ix < (unsigned)OW, p1 = (unsigned)(ix - 1) < (unsigned)OW, p2 = (unsigned)(ix - 2) < (unsigned)OW;
 #pragma unroll
-        for (int dy = 0; dy < 3; ++dy) {
-            const int yy = iy - dy;
-            if ((unsigned)yy >= (unsigned)OH) continue;
-            const bool p0 = (unsigned)ix < (unsigned)OW, p1 = (unsigned)(ix - 1) < (unsigned)OW, p2 = (unsigned)(ix - 2) < (unsigned)OW;
+    for (int co = 0; co < CO; ++co)
 #pragma unroll
-            for (int co = 0; co < CO; ++co) {
-                const float *row = gy + co * ovol + (size_t)z * OHW + (size_t)yy * OW + ix;
+        for (int p = 0; p < kZB + 2; ++p) {
+            const int q = iz0 + p - 2;                     // gradient plane; uniform over the block
+            if ((unsigned)q >= (unsigned)OD) continue;
+#pragma unroll
+            for (int dy = 0; dy < 3; ++dy) {
+                const int yy = iy - dy;
+                if ((unsigned)yy >= (unsigned)OH) continue;
+                const float *row = gy + co * ovol + (size_t)q * OHW + (size_t)yy * OW + ix;
                 const float v0 = p0 ? __ldg(row) : 0.f, v1 = p1 ? __ldg(row - 1) : 0.f, v2 = p2 ? __ldg(row - 2) : 0.f;
 #pragma unroll
-                for (int ci = 0; ci < CI; ++ci) {
-                    const int wi = ((co * CI + ci) * 3 + dz) * 9 + dy * 3;
-                    acc[ci] = fmaf(c_tc_w[wi], v0, acc[ci]);
-                    acc[ci] = fmaf(c_tc_w[wi + 1], v1, acc[ci]);
-                    acc[ci] = fmaf(c_tc_w[wi + 2], v2, acc[ci]);
+                for (int dz = 0; dz < 3; ++dz) {
+                    const int zi = p - 2 + dz;             // input slice iz0 + zi = q + dz; compile-time after unrolling
+                    if (zi < 0 || zi >= kZB) continue;
+#pragma unroll
+                    for (int ci = 0; ci < CI; ++ci) {
+                        const int wi = ((co * CI + ci) * 3 + dz) * 9 + dy * 3;
+                        acc[zi][ci] = fmaf(c_tc_w[wi], v0, acc[zi][ci]);
+                        acc[zi][ci] = fmaf(c_tc_w[wi + 1], v1, acc[zi][ci]);
+                        acc[zi][ci] = fmaf(c_tc_w[wi + 2], v2, acc[zi][ci]);
+                    }
                 }
             }
         }
-    }
-    const size_t o = (size_t)iz * HW + (size_t)iy * W + ix;
 #pragma unroll
-    for (int ci = 0; ci < CI; ++ci) gx[ci * vol + o] = acc[ci];
+    for (int zi = 0; zi < kZB; ++zi) {
+        if (iz0 + zi >= D) break;
+        const size_t o = (size_t)(iz0 + zi) * HW + (size_t)iy * W + ix;
+#pragma unroll
+        for (int ci = 0; ci < CI; ++ci) gx[ci * vol + o] = acc[zi][ci];
+    }
 }
 
 // grid (blocks, CI * 3 * co_groups): group g = (ci * 3 + dz) * co_groups + cg handles output channels [cg * COG, (cg + 1) * COG).
@@ -249,7 +276,7 @@ extern "C" int trb_thinconv3_forward(const float *x_dev, const float *w_dev, con
     rc = tc_upload(w_dev, b_dev, CI, CO, s);
     if (rc) return rc;
     const int OD = D - 2, OH = H - 2, OW = W - 2;
-    const dim3 grid((OW + 127) / 128, (OH + 1) / 2, OD);
+    const dim3 grid((OW + 127) / 128, (OH + 1) / 2, (OD + kZB - 1) / kZB);
     const size_t vol = (size_t)D * H * W, ovol = (size_t)OD * OH * OW;
     for (int n = 0; n < n_batch; ++n) {
         const float *xn = x_dev + (size_t)n * CI * vol;
@@ -272,7 +299,7 @@ extern "C" int trb_thinconv3_backward(const float *x_dev, const float *w_dev, co
     if (gx_dev) {
         rc = tc_upload(w_dev, nullptr, CI, CO, s);
         if (rc) return rc;
-        const dim3 grid((W + 127) / 128, (H + 1) / 2, D);
+        const dim3 grid((W + 127) / 128, (H + 1) / 2, (D + kZB - 1) / kZB);
         for (int n = 0; n < n_batch; ++n) {
             const float *gn = gy_dev + (size_t)n * CO * ovol;
             float *xn = gx_dev + (size_t)n * CI * vol;
