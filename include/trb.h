@@ -389,11 +389,13 @@ int trb_affine_optim_nmi(int ndim, int mode, const float *moving_dev, const floa
  * y = IN(max(x, 0))).  x, y, dy, dx: [n_inst][S] contiguous (n_inst = N*C instances of S spatial elements);
  * stats_dev [n_inst][2] = (mean, rstd) written by forward and read by backward; coef_dev [n_inst][2] scratch. */
 size_t trb_instnorm_workspace_bytes(int n_inst, long long S);
-int trb_instnorm_forward(const float *x_dev, float *y_dev, int n_inst, long long S, float eps, int relu,
+/* gate_dev (optional, [S], shared by the instances = channels of ONE sample, no ReLU): y_c = IN(x_c * gate) — the attention gate's
+ * `bnorm(x * w)` (utils.py:403-405) without the product tensor; backward then also returns dgate_dev [S] = sum_c dv_c x_c. */
+int trb_instnorm_forward(const float *x_dev, const float *gate_dev, float *y_dev, int n_inst, long long S, float eps, int relu,
                          float *stats_dev, void *workspace_dev, size_t workspace_bytes, void *stream);
-int trb_instnorm_backward(const float *x_dev, const float *dy_dev, float *dx_dev, int n_inst, long long S, int relu,
-                          const float *stats_dev, float *coef_dev, void *workspace_dev, size_t workspace_bytes,
-                          void *stream);
+int trb_instnorm_backward(const float *x_dev, const float *gate_dev, const float *dy_dev, float *dx_dev, float *dgate_dev,
+                          int n_inst, long long S, int relu, const float *stats_dev, float *coef_dev, void *workspace_dev,
+                          size_t workspace_bytes, void *stream);
 
 /* ---- thin 3x3x3 convolutions of the flow U-Net (csrc/thinconv.cu) -----------------------
  * Replaces nn.Conv3d(kernel_size=3) (stride 1, no padding; any C_in, C_out <= 4 and the pairs 8->4, 4->8, 8->8: the two finest

@@ -838,6 +838,27 @@ def test_up_conv3d_kernels_vs_torch(ci, co, shape, bias):
         assert (a.double() - b_).abs().max().item() <= 2e-5 * max(1.0, b_.abs().max().item())
 
 
+@pytest.mark.parametrize("shape", [(1, 2, 30, 31, 32), (1, 8, 9, 10, 12), (1, 3, 40, 37)])
+def test_gated_instance_norm_vs_torch(shape):
+    """The attention gate's bnorm(x * w) (utils.py:403-405) as one fused op — the product is never materialised — against
+    nn.InstanceNorm(x * w) in float64: output, d/dx and d/dw (sum over channels)."""
+    import torch.nn as nn
+    from torchregister_b200.utils import _GatedInstanceNormFn
+    torch.manual_seed(21)
+    x = (torch.randn(shape, device=DEV) * 1.3 + 0.2).requires_grad_(True)
+    w = torch.rand((1, 1) + tuple(shape[2:]), device=DEV).requires_grad_(True)
+    g = torch.randn(shape, device=DEV)
+    y = _GatedInstanceNormFn.apply(x, w, 1e-5)
+    dx, dw = torch.autograd.grad(y, [x, w], g)
+    x64, w64 = x.detach().double().requires_grad_(True), w.detach().double().requires_grad_(True)
+    ref = (nn.InstanceNorm3d if len(shape) == 5 else nn.InstanceNorm2d)(shape[1]).double()
+    y64 = ref(x64 * w64)
+    dx64, dw64 = torch.autograd.grad(y64, [x64, w64], g.double())
+    assert (y.double() - y64).abs().max().item() <= 2e-5
+    assert (dx.double() - dx64).abs().max().item() <= 2e-5 * max(1.0, dx64.abs().max().item())
+    assert (dw.double() - dw64).abs().max().item() <= 2e-5 * max(1.0, dw64.abs().max().item())
+
+
 def test_unet_with_kernel_instance_norm_matches_torch_instance_norm():
     """Attention_UNet with the InstanceNorm kernels (ReLU folded in) and the thin-convolution kernels against the same network
     — same parameter names, same weights — built from stock nn.Conv3d + nn.ReLU + nn.InstanceNorm3d (cuDNN, TF32 off): flow

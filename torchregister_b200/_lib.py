@@ -78,8 +78,8 @@ _SIGNATURES = {
     "trb_upconv2_forward": (_i, [c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp]),
     "trb_upconv2_backward": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, c_fp, _i, _i, _i, _i, _i, c_fp, _sz, c_fp]),
     "trb_instnorm_workspace_bytes": (_sz, [_i, _ll]),
-    "trb_instnorm_forward": (_i, [c_fp, c_fp, _i, _ll, _f, _i, c_fp, c_fp, _sz, c_fp]),
-    "trb_instnorm_backward": (_i, [c_fp, c_fp, c_fp, _i, _ll, _i, c_fp, c_fp, c_fp, _sz, c_fp]),
+    "trb_instnorm_forward": (_i, [c_fp, c_fp, c_fp, _i, _ll, _f, _i, c_fp, c_fp, _sz, c_fp]),
+    "trb_instnorm_backward": (_i, [c_fp, c_fp, c_fp, c_fp, c_fp, _i, _ll, _i, c_fp, c_fp, c_fp, _sz, c_fp]),
     "trb_nmi_src_workspace_bytes": (_sz, [_i, _i, _i, _i, _i]),
     "trb_nmi_src_prepare": (_i, [_i, c_fp, _ll, _i, _i, _i, _i, _f, _f, _f, c_fp, _sz, c_fp]),
     "trb_nmi_src_loss_grad": (_i, [_i, c_fp, _ll, _i, _i, _i, _i, _f, _f, _f, _f, _f, c_fp, _i, c_fp, c_fp, _sz, c_fp]),

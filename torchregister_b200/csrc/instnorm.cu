@@ -42,7 +42,8 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double (*sh)[2]
 
 // grid (chunks, instances).  BWD = false: (sum v, sum v^2) of v = relu?(x);  BWD = true: (sum dy, sum dy*y), y from x and stats.
 template <bool BWD, bool VEC>
-__global__ void __launch_bounds__(256) instnorm_sums_kernel(const float *__restrict__ x, const float *__restrict__ dy, long long S,
+__global__ void __launch_bounds__(256) instnorm_sums_kernel(const float *__restrict__ x, const float *__restrict__ gate,
+                                                             const float *__restrict__ dy, long long S,
                                                              int relu, const float *__restrict__ stats, double *__restrict__ part)
 {
     __shared__ double sh[8][2];
@@ -53,7 +54,7 @@ __global__ void __launch_bounds__(256) instnorm_sums_kernel(const float *__restr
     const float mean = BWD ? stats[2 * inst] : 0.f, rstd = BWD ? stats[2 * inst + 1] : 0.f;
     float a = 0.f, b = 0.f;
     double A = 0.0, B = 0.0;
-    auto add = [&](float xv, float dv) {
+    auto add = [&](float xv, float dv) {                  // xv: already multiplied by the gate, if any
         const float v = relu ? fmaxf(xv, 0.f) : xv;
         if (BWD) { const float y = (v - mean) * rstd; a += dv; b = fmaf(dv, y, b); }
         else { a += v; b = fmaf(v, v, b); }
@@ -62,9 +63,11 @@ __global__ void __launch_bounds__(256) instnorm_sums_kernel(const float *__restr
         // S % 4 == 0 and 16-byte aligned bases: chunk borders are rounded to float4s
         const long long v0 = (i0 + 3) / 4, v1 = chunk + 1 == chunks ? S / 4 : (i1 + 3) / 4;
         const float4 *x4 = reinterpret_cast<const float4 *>(xi), *d4 = reinterpret_cast<const float4 *>(di);
+        const float4 *g4 = reinterpret_cast<const float4 *>(gate);
         int n = 0;
         for (long long i = v0 + threadIdx.x; i < v1; i += 256) {
-            const float4 xv = __ldg(x4 + i);
+            float4 xv = __ldg(x4 + i);
+            if (gate) { const float4 gv = __ldg(g4 + i); xv.x *= gv.x; xv.y *= gv.y; xv.z *= gv.z; xv.w *= gv.w; }
             float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (BWD) dv = __ldg(d4 + i);
             add(xv.x, dv.x); add(xv.y, dv.y); add(xv.z, dv.z); add(xv.w, dv.w);
@@ -73,7 +76,7 @@ __global__ void __launch_bounds__(256) instnorm_sums_kernel(const float *__restr
     } else {
         int n = 0;
         for (long long i = i0 + threadIdx.x; i < i1; i += 256) {
-            add(__ldg(xi + i), BWD ? __ldg(di + i) : 0.f);
+            add(gate ? __ldg(xi + i) * __ldg(gate + i) : __ldg(xi + i), BWD ? __ldg(di + i) : 0.f);
             if (++n == 32) { A += (double)a; B += (double)b; a = b = 0.f; n = 0; }
         }
     }
@@ -110,7 +113,8 @@ __global__ void __launch_bounds__(256) instnorm_finalise_kernel(const double *__
 
 // grid (blocks, instances).  FWD: y = (relu?(x) - mean) * rstd.  BWD: dx = rstd * (dy - m1 - y * m2), times (x > 0) with relu.
 template <bool BWD, bool VEC>
-__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float *__restrict__ x, const float *__restrict__ dy, long long S, int relu,
+__global__ void __launch_bounds__(256) instnorm_apply_kernel(const float *__restrict__ x, const float *__restrict__ gate,
+                                                              const float *__restrict__ dy, long long S, int relu,
                                                               const float *__restrict__ stats, const float *__restrict__ coef,
                                                               float *__restrict__ out)
 {
@@ -131,15 +135,44 @@ __global__ void __launch_bounds__(256) instnorm_apply_kernel(const float *__rest
     if (VEC) {
         const float4 *x4 = reinterpret_cast<const float4 *>(xi), *d4 = reinterpret_cast<const float4 *>(di);
         float4 *o4 = reinterpret_cast<float4 *>(oi);
+        const float4 *g4 = reinterpret_cast<const float4 *>(gate);
         for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < S / 4; i += stride) {
-            const float4 xv = __ldg(x4 + i);
+            float4 xv = __ldg(x4 + i);
+            if (gate) { const float4 gv = __ldg(g4 + i); xv.x *= gv.x; xv.y *= gv.y; xv.z *= gv.z; xv.w *= gv.w; }
             float4 dv = make_float4(0.f, 0.f, 0.f, 0.f);
             if (BWD) dv = __ldg(d4 + i);
             o4[i] = make_float4(f(xv.x, dv.x), f(xv.y, dv.y), f(xv.z, dv.z), f(xv.w, dv.w));
         }
     } else {
         for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < S; i += stride)
-            oi[i] = f(__ldg(xi + i), BWD ? __ldg(di + i) : 0.f);
+            oi[i] = f(gate ? __ldg(xi + i) * __ldg(gate + i) : __ldg(xi + i), BWD ? __ldg(di + i) : 0.f);
+    }
+}
+
+// Gated form y_c = IN(x_c * g) (the attention gate's `bnorm(x * w)`, utils.py:403-405; one sample, g shared by its channels):
+// backward for ALL channels of a voxel in one thread: dv_c = rstd_c (dy_c - m1_c - y_c m2_c), dx_c = dv_c g, dg = sum_c dv_c x_c.
+constexpr int kInMaxGatedC = 64;
+__global__ void __launch_bounds__(256) instnorm_gated_bwd_kernel(const float *__restrict__ x, const float *__restrict__ gate,
+                                                                  const float *__restrict__ dy, long long S, int C,
+                                                                  const float *__restrict__ stats, const float *__restrict__ coef,
+                                                                  float *__restrict__ dx, float *__restrict__ dgate)
+{
+    __shared__ float sc[kInMaxGatedC][4];
+    for (int c = threadIdx.x; c < C; c += 256) {
+        sc[c][0] = stats[2 * c]; sc[c][1] = stats[2 * c + 1]; sc[c][2] = coef[2 * c]; sc[c][3] = coef[2 * c + 1];
+    }
+    __syncthreads();
+    for (long long i = (long long)blockIdx.x * 256 + threadIdx.x; i < S; i += (long long)gridDim.x * 256) {
+        const float g = __ldg(gate + i);
+        float dg = 0.f;
+        for (int c = 0; c < C; ++c) {
+            const float xv = __ldg(x + (size_t)c * S + i);
+            const float y = (xv * g - sc[c][0]) * sc[c][1];
+            const float dv = sc[c][1] * (__ldg(dy + (size_t)c * S + i) - sc[c][2] - y * sc[c][3]);
+            dx[(size_t)c * S + i] = dv * g;
+            dg = fmaf(dv, xv, dg);
+        }
+        dgate[i] = dg;
     }
 }
 
@@ -171,41 +204,47 @@ extern "C" size_t trb_instnorm_workspace_bytes(int n_inst, long long S)
     return (size_t)n_inst * in_chunks(S) * 2 * sizeof(double);
 }
 
-extern "C" int trb_instnorm_forward(const float *x_dev, float *y_dev, int n_inst, long long S, float eps, int relu,
+extern "C" int trb_instnorm_forward(const float *x_dev, const float *gate_dev, float *y_dev, int n_inst, long long S, float eps, int relu,
                                     float *stats_dev, void *workspace_dev, size_t workspace_bytes, void *stream)
 {
     int rc = in_validate(x_dev, y_dev, n_inst, S, workspace_dev, workspace_bytes);
     if (rc) return rc;
     if (!stats_dev) { set_error("null stats"); return TRB_ERR_ARG; }
+    if (gate_dev && relu) { set_error("the gated form has no ReLU"); return TRB_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     double *part = (double *)workspace_dev;
     const int chunks = in_chunks(S);
-    const bool vec = S % 4 == 0 && (((uintptr_t)x_dev | (uintptr_t)y_dev) & 15) == 0;
+    const bool vec = S % 4 == 0 && (((uintptr_t)x_dev | (uintptr_t)y_dev | (uintptr_t)gate_dev) & 15) == 0;
     const dim3 gs(chunks, n_inst), ga(in_apply_blocks(S, n_inst), n_inst);
-    if (vec) instnorm_sums_kernel<false, true><<<gs, 256, 0, s>>>(x_dev, nullptr, S, relu, nullptr, part);
-    else instnorm_sums_kernel<false, false><<<gs, 256, 0, s>>>(x_dev, nullptr, S, relu, nullptr, part);
+    if (vec) instnorm_sums_kernel<false, true><<<gs, 256, 0, s>>>(x_dev, gate_dev, nullptr, S, relu, nullptr, part);
+    else instnorm_sums_kernel<false, false><<<gs, 256, 0, s>>>(x_dev, gate_dev, nullptr, S, relu, nullptr, part);
     instnorm_finalise_kernel<<<n_inst, 256, 0, s>>>(part, chunks, S, eps, 0, stats_dev);
-    if (vec) instnorm_apply_kernel<false, true><<<ga, 256, 0, s>>>(x_dev, nullptr, S, relu, stats_dev, nullptr, y_dev);
-    else instnorm_apply_kernel<false, false><<<ga, 256, 0, s>>>(x_dev, nullptr, S, relu, stats_dev, nullptr, y_dev);
+    if (vec) instnorm_apply_kernel<false, true><<<ga, 256, 0, s>>>(x_dev, gate_dev, nullptr, S, relu, stats_dev, nullptr, y_dev);
+    else instnorm_apply_kernel<false, false><<<ga, 256, 0, s>>>(x_dev, gate_dev, nullptr, S, relu, stats_dev, nullptr, y_dev);
     return check_cuda(cudaGetLastError(), "instnorm_forward");
 }
 
-extern "C" int trb_instnorm_backward(const float *x_dev, const float *dy_dev, float *dx_dev, int n_inst, long long S, int relu,
-                                     const float *stats_dev, float *coef_dev, void *workspace_dev, size_t workspace_bytes,
-                                     void *stream)
+extern "C" int trb_instnorm_backward(const float *x_dev, const float *gate_dev, const float *dy_dev, float *dx_dev, float *dgate_dev,
+                                     int n_inst, long long S, int relu, const float *stats_dev, float *coef_dev, void *workspace_dev,
+                                     size_t workspace_bytes, void *stream)
 {
     int rc = in_validate(x_dev, dy_dev, n_inst, S, workspace_dev, workspace_bytes);
     if (rc) return rc;
     if (!dx_dev || !stats_dev || !coef_dev) { set_error("null pointer"); return TRB_ERR_ARG; }
+    if (gate_dev && (relu || !dgate_dev || n_inst > kInMaxGatedC)) { set_error("gated form: no ReLU, dgate required, <= %d channels", kInMaxGatedC); return TRB_ERR_ARG; }
     cudaStream_t s = (cudaStream_t)stream;
     double *part = (double *)workspace_dev;
     const int chunks = in_chunks(S);
-    const bool vec = S % 4 == 0 && (((uintptr_t)x_dev | (uintptr_t)dy_dev | (uintptr_t)dx_dev) & 15) == 0;
+    const bool vec = S % 4 == 0 && (((uintptr_t)x_dev | (uintptr_t)dy_dev | (uintptr_t)dx_dev | (uintptr_t)gate_dev) & 15) == 0;
     const dim3 gs(chunks, n_inst), ga(in_apply_blocks(S, n_inst), n_inst);
-    if (vec) instnorm_sums_kernel<true, true><<<gs, 256, 0, s>>>(x_dev, dy_dev, S, relu, stats_dev, part);
-    else instnorm_sums_kernel<true, false><<<gs, 256, 0, s>>>(x_dev, dy_dev, S, relu, stats_dev, part);
+    if (vec) instnorm_sums_kernel<true, true><<<gs, 256, 0, s>>>(x_dev, gate_dev, dy_dev, S, relu, stats_dev, part);
+    else instnorm_sums_kernel<true, false><<<gs, 256, 0, s>>>(x_dev, gate_dev, dy_dev, S, relu, stats_dev, part);
     instnorm_finalise_kernel<<<n_inst, 256, 0, s>>>(part, chunks, S, 0.f, 1, coef_dev);
-    if (vec) instnorm_apply_kernel<true, true><<<ga, 256, 0, s>>>(x_dev, dy_dev, S, relu, stats_dev, coef_dev, dx_dev);
-    else instnorm_apply_kernel<true, false><<<ga, 256, 0, s>>>(x_dev, dy_dev, S, relu, stats_dev, coef_dev, dx_dev);
+    if (gate_dev) {
+        long long nb = (S + 255) / 256;
+        if (nb > 148 * 16) nb = 148 * 16;
+        instnorm_gated_bwd_kernel<<<(unsigned)nb, 256, 0, s>>>(x_dev, gate_dev, dy_dev, S, n_inst, stats_dev, coef_dev, dx_dev, dgate_dev);
+    } else if (vec) instnorm_apply_kernel<true, true><<<ga, 256, 0, s>>>(x_dev, nullptr, dy_dev, S, relu, stats_dev, coef_dev, dx_dev);
+    else instnorm_apply_kernel<true, false><<<ga, 256, 0, s>>>(x_dev, nullptr, dy_dev, S, relu, stats_dev, coef_dev, dx_dev);
     return check_cuda(cudaGetLastError(), "instnorm_backward");
 }

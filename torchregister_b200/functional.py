@@ -586,34 +586,42 @@ def _instnorm_ws(device, n_inst: int, S: int) -> torch.Tensor:
     return ws
 
 
-def instance_norm_forward(x: torch.Tensor, eps: float = 1e-5, relu: bool = False):
-    """y = InstanceNorm(relu?(x)) for x [N,C,*spatial] (affine=False, no running statistics) -> (y, stats [N*C,2])."""
+def instance_norm_forward(x: torch.Tensor, eps: float = 1e-5, relu: bool = False, gate: Optional[torch.Tensor] = None):
+    """y = InstanceNorm(relu?(x)) for x [N,C,*spatial] (affine=False, no running statistics) -> (y, stats [N*C,2]).
+    gate ([1,1,*spatial], N == 1, no ReLU): y = InstanceNorm(x * gate) without the product tensor."""
     require_cuda(x, "x")
     x = x.contiguous()
     n_inst = int(x.shape[0] * x.shape[1])
     S = x.numel() // n_inst
+    if gate is not None:
+        gate = gate.contiguous()
+        if x.shape[0] != 1 or gate.numel() != S or relu:
+            raise ValueError("gated instance norm: one sample, gate [1,1,*spatial], no ReLU")
     y = torch.empty_like(x)
     stats = torch.empty(n_inst, 2, dtype=torch.float32, device=x.device)
     ws = _instnorm_ws(x.device, n_inst, S)
     with torch.cuda.device(x.device):
-        check(_lib.load().trb_instnorm_forward(x.data_ptr(), y.data_ptr(), n_inst, S, float(eps), int(bool(relu)), stats.data_ptr(),
-                                               ws.data_ptr(), ws.numel(), _stream(x.device)), "instnorm_forward")
+        check(_lib.load().trb_instnorm_forward(x.data_ptr(), _ptr(gate), y.data_ptr(), n_inst, S, float(eps), int(bool(relu)),
+                                               stats.data_ptr(), ws.data_ptr(), ws.numel(), _stream(x.device)), "instnorm_forward")
     return y, stats
 
 
-def instance_norm_backward(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, relu: bool = False) -> torch.Tensor:
+def instance_norm_backward(x: torch.Tensor, dy: torch.Tensor, stats: torch.Tensor, relu: bool = False,
+                           gate: Optional[torch.Tensor] = None):
+    """-> d/dx, or (d/dx, d/dgate) with a gate."""
     require_cuda(dy, "dy")
     x, dy = x.contiguous(), dy.contiguous()
     n_inst = int(x.shape[0] * x.shape[1])
     S = x.numel() // n_inst
     dx = torch.empty_like(x)
+    dgate = torch.empty_like(gate) if gate is not None else None
     coef = torch.empty(n_inst, 2, dtype=torch.float32, device=x.device)
     ws = _instnorm_ws(x.device, n_inst, S)
     with torch.cuda.device(x.device):
-        check(_lib.load().trb_instnorm_backward(x.data_ptr(), dy.data_ptr(), dx.data_ptr(), n_inst, S, int(bool(relu)),
-                                                stats.data_ptr(), coef.data_ptr(), ws.data_ptr(), ws.numel(),
+        check(_lib.load().trb_instnorm_backward(x.data_ptr(), _ptr(gate), dy.data_ptr(), dx.data_ptr(), _ptr(dgate), n_inst, S,
+                                                int(bool(relu)), stats.data_ptr(), coef.data_ptr(), ws.data_ptr(), ws.numel(),
                                                 _stream(x.device)), "instnorm_backward")
-    return dx
+    return dx if gate is None else (dx, dgate)
 
 
 # --------------------------------------------------------------------------- #

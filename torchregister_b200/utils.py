@@ -347,6 +347,26 @@ class _InstanceNormFn(torch.autograd.Function):
         return TF.instance_norm_backward(x, dy, stats, ctx.relu), None, None
 
 
+class _GatedInstanceNormFn(torch.autograd.Function):
+    """y = InstanceNorm(x * gate), gate [1,1,*spatial] shared by the channels of one sample (the attention gate's bnorm(x * w))."""
+
+    @staticmethod
+    def forward(ctx, x, gate, eps):
+        from . import functional as TF
+        x, gate = x.contiguous(), gate.contiguous()
+        y, stats = TF.instance_norm_forward(x, eps, False, gate)
+        ctx.save_for_backward(x, gate, stats)
+        return y
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, dy):
+        from . import functional as TF
+        x, gate, stats = ctx.saved_tensors
+        dx, dgate = TF.instance_norm_backward(x, dy, stats, False, gate)
+        return dx, dgate, None
+
+
 class _InstanceNormB200:
     """Mixin over nn.InstanceNorm{2,3}d: float32 CUDA inputs of a plain instance norm (affine=False, no running statistics:
     the reference's configuration, utils.py:368-520) run on csrc/instnorm.cu — PyTorch parallelises instance norm over
@@ -506,6 +526,11 @@ class attention_grid(nn.Module):
             b = padNd(b, a, device)
         w = torch.sigmoid(self.psi(F.relu(a + b)))
         w = F.interpolate(w, size=x.shape[2:], mode=self.mode)
+        b = self.bnorm
+        if (isinstance(b, _InstanceNormB200) and not b.affine and not b.track_running_stats and not b.fuse_relu and x.is_cuda
+                and x.dtype == torch.float32 and w.dtype == torch.float32 and x.shape[0] == 1 and w.shape[1] == 1
+                and x.shape[1] <= 64 and tuple(w.shape[2:]) == tuple(x.shape[2:])):
+            return _GatedInstanceNormFn.apply(x, w, float(b.eps)), w       # the product x * w is never materialised
         return self.bnorm(x * w), w
 
 
