@@ -501,7 +501,7 @@ def main():
     peak, peak_src = _peaks()
     traffic, traffic_src = _traffic()
     us_epoch = ms * 1e3 / K
-    kernel = "trb::affine3d_persist_kernel<false> (csrc/affine_persist.cu)"
+    kernel = "trb::affine3d_persist_kernel<MSE_ONLY=false, ROT=false> (csrc/affine_persist.cu)"
     roof = roofline_entry(us_epoch, SHAPE, PAIRS_PER_GPU, peak, kernel)
     roof.update({"traffic": traffic * min(K, CHUNK_EPOCHS) if traffic else None, "traffic_per_epoch": traffic, "traffic_source": traffic_src,
                  "peak_source": peak_src, "epochs_per_launch": min(K, CHUNK_EPOCHS),
