@@ -196,3 +196,25 @@ def test_tile_fits_helper_runs_on_the_host():
     assert lib.trb_affine_tile_fits(192, 192, 160, rot_z(0.5)) == 0
     assert lib.trb_affine_tile_fits(256, 256, 256, rot_z(1.0)) == 0
     assert lib.trb_affine_tile_fits(0, 0, 0, rot_z(0.0)) == 0
+
+
+def test_committed_bench_line_follows_the_contract():
+    """The bench line committed at the end of the round (profiles/r02_bench_n1_final.json) carries every key of the driver's
+    contract, the two roofline objects with consistent arithmetic, a reference-kind CPU baseline and a real end-to-end figure."""
+    import json
+    import os
+    path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "profiles", "r02_bench_n1_final.json")
+    d = json.load(open(path))
+    for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+              "dtype", "data", "config", "e2e", "gpu_launches", "roofline", "roofline_256", "cpu_baseline", "clocks"):
+        assert k in d, k
+    assert d["vs_baseline"] is None and d["dtype"] == "f32" and d["n_gpus"] == 1 and d["gpu_launches"] > 0
+    assert "workload" in d["config"] and "model" not in d["config"]
+    for r in (d["roofline"], d["roofline_256"]):
+        assert r["bound"] == "hbm" and r["unit"] == "GB/s"
+        assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+        assert abs(r["achieved"] - r["algorithmic_bytes_per_epoch"] / (r["kernel_us_per_epoch"] * 1e-6) / 1e9) < 1e-6 * r["achieved"]
+    assert d["roofline"]["traffic"] is None or d["roofline"]["traffic_per_epoch"] >= 0.99 * d["roofline"]["algorithmic_bytes_per_epoch"]
+    assert d["cpu_baseline"]["kind"] in ("reference", "port") and d["cpu_baseline"]["cores"] >= 1
+    assert d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0 and d["e2e"]["value"] < d["value"]
+    assert "rejected" not in d["clocks"] or d["clocks"]["rejected"] is False
